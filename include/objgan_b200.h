@@ -1,0 +1,142 @@
+/* objgan_b200 -- C ABI of libobjgan_b200.so (sm_100a kernels for the Obj-GAN image_generation hot path).
+ *
+ * Plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise; every call is
+ * asynchronous on `stream` and re-entrant (no global mutable state), which is what the reference's one FFI
+ * crossing requires (models/roi_align/src/roi_align_cuda.c:5,31: global THCState, current-stream launch).
+ *
+ * Return convention: og_* functions return 0 on success, else the cudaError_t of the failed call.  The two
+ * ROIAlign*Laucher symbols keep the reference convention (1 = ok, 0 = error) because they are the literal
+ * drop-ins for models/roi_align/src/roi_align_kernel.h:13-27.  Nothing in this library calls exit().
+ *
+ * Activations are NHWC fp32 ("rows" = pixels, channels contiguous), channel counts padded to a multiple of
+ * 8 with zero lanes; the module boundary (NCHW, unpadded -- the reference's public layout) is crossed with
+ * og_nchw_to_nhwc / og_nhwc_to_nchw.  All "ref:" paths are relative to /root/reference/image_generation/.
+ */
+#ifndef OBJGAN_B200_H
+#define OBJGAN_B200_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- codes ---- */
+enum { OG_ACT_NONE = 0, OG_ACT_LRELU = 1, OG_ACT_TANH = 2, OG_ACT_SIGMOID = 3 };  /* conv epilogue activations  */
+enum { OG_NA_NONE = 0, OG_NA_LRELU = 1, OG_NA_GLU = 2 };                          /* norm-apply fusions         */
+enum { OG_PAD_ZERO = 0, OG_PAD_REFLECT = 1, OG_UPSAMPLE2X = 2, OG_TRANSPOSED = 3 }; /* conv source addressing   */
+
+/* ------------------------------------------------------------------------------------------------------
+ * ROIAlign -- replaces ref: models/roi_align/src/roi_align_kernel.h:13-27 (same names, argument order,
+ * NCHW fp32 features, rois = [batch_idx, x1, y1, x2, y2] rows, caller zero-fills outputs;
+ * callers: models/roi_align/src/roi_align_cuda.c:33-38, 70-73).
+ * ---------------------------------------------------------------------------------------------------- */
+int ROIAlignForwardLaucher(const float* bottom_data, const float spatial_scale, const int num_rois, const int height,
+                           const int width, const int channels, const int aligned_height, const int aligned_width,
+                           const float* bottom_rois, float* top_data, cudaStream_t stream);
+int ROIAlignBackwardLaucher(const float* top_diff, const float spatial_scale, const int batch_size, const int num_rois,
+                            const int height, const int width, const int channels, const int aligned_height,
+                            const int aligned_width, const float* bottom_rois, float* bottom_diff, cudaStream_t stream);
+/* fused RoIAlignAvg(AH, AW, scale) = align to (AH+1)x(AW+1) then avg_pool2d(2, 1)
+ * -- replaces ref: models/roi_align/modules/roi_align.py:18-29 (used at model.py:1241, 1307). */
+int og_roi_align_avg_fwd(const float* features, int height, int width, int channels, const float* rois, int num_rois,
+                         int AH, int AW, float spatial_scale, float* out, cudaStream_t stream);
+int og_roi_align_avg_bwd(const float* grad_out, int height, int width, int channels, const float* rois, int num_rois,
+                         int AH, int AW, float spatial_scale, float* grad_features, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Convolutions / linear layers as implicit GEMM -- replaces the cuDNN/cuBLAS calls behind nn.Conv2d /
+ * nn.Linear in ref: model.py:36-39 (conv3x3), 43-49 (upBlock), 52-60 (downBlock_G), 63-81 (HmapResBlock),
+ * 455-518 (CA_NET / INIT_STAGE_G fc), 589-617 (G_HMAP), 708-719 (GET_IMAGE_G), 999-1048 (D stacks).
+ * x: source NHWC [N,H,W,C] with element strides (xsn,xsh,xsw); y likewise [N,OH,OW,K]; C % 8 == 0, K % 4 == 0.
+ * mode selects how a (row pixel, tap) pair maps to a source pixel: zero padding, reflection padding
+ * (nn.ReflectionPad2d), nearest-2x upsampling followed by zero padding (nn.Upsample + conv), or the
+ * transposed map used for the input gradient.  wpacked is produced by og_pack_weights.
+ * ---------------------------------------------------------------------------------------------------- */
+int og_conv2d_simt(const float* x, int N, int H, int W, int C, long long xsn, long long xsh, long long xsw,
+                   const float* wpacked, float* y, int OH, int OW, int K, long long ysn, long long ysh, long long ysw,
+                   int KH, int KW, int stride, int pad, int mode, const float* bias, int act, float slope,
+                   int allow_splitk, cudaStream_t stream);
+int og_conv2d_wgrad_simt(const float* x, int N, int H, int W, int C, long long xsn, long long xsh, long long xsw,
+                         const float* g, int OH, int OW, int K, long long gsn, long long gsh, long long gsw,
+                         float* dw_packed, int KH, int KW, int stride, int pad, int mode, cudaStream_t stream);
+/* OIHW parameter (state_dict layout) <-> kernel-native matrices.  split/splitp: GLU halves of the
+ * output channels are each padded to splitp.  transposed=1 gives the dgrad operand.  out_lo != NULL also writes
+ * the tf32 hi/lo split used by the tensor-core path. */
+int og_pack_weights(const float* w_oihw, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split, int splitp,
+                    int transposed, float* out, float* out_lo, cudaStream_t stream);
+int og_unpack_wgrad(const float* dw_packed, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split, int splitp,
+                    float* grad_oihw, int accumulate, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * InstanceNorm2d / BatchNorm (train mode) + fused GLU / LeakyReLU / residual
+ * -- replaces ref: model.py:19-27 (GLU), 47, 70, 75, 497, 602, 992, 1011 (norm layers).
+ * groups = N (instance norm) or 1 (batch norm); P pixels per group; contiguous rows of C channels.
+ * ---------------------------------------------------------------------------------------------------- */
+int og_norm_stats(const float* x, int groups, long long P, int C, float eps, double* stats, float* mean, float* rstd,
+                  float* running_mean, float* running_var, float momentum, int real_c, long long* num_batches_tracked,
+                  cudaStream_t stream);
+int og_norm_apply(const float* y, int groups, long long P, int Cy, const float* mean, const float* rstd,
+                  const float* gamma, const float* beta, const float* res, int act, float slope, float* out,
+                  cudaStream_t stream);
+int og_norm_backward(const float* y, const float* g, int groups, long long P, int Cy, const float* mean,
+                     const float* rstd, const float* gamma, const float* beta, int act, float slope, double* bstats,
+                     float* dy, float* dgamma, float* dbeta, int accumulate_param_grads, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Attention -- replaces ref: GlobalAttention.py:32-70 (func_attention), 73-122 (GlobalAttentionGeneral),
+ * 125-181 (GlobalBUAttentionGeneral) and miscc/utils.py:401-413 (pprocess_bt_attns).
+ * mask: [B][L] bytes, 1 = padding word; the reference's mask-row permutation quirk is reproduced.
+ * ---------------------------------------------------------------------------------------------------- */
+int og_words_proj(const float* words, const float* W, int B, int idf, int cdf, int L, float* src, cudaStream_t stream);
+int og_words_proj_bwd(const float* words, const float* W, const float* gsrc, int B, int idf, int cdf, int L, float* gW,
+                      int accumulate, float* gwords, cudaStream_t stream);
+int og_att_general_fwd(const float* h, const float* src, const unsigned char* mask, int B, int Q, int idf, int cs,
+                       int L, float* wc, float* attn, cudaStream_t stream);
+int og_att_general_bwd(const float* h, const float* src, const float* attn, const float* g_wc, const float* g_attn,
+                       int B, int Q, int idf, int cs, int L, float* g_h, float* g_src, cudaStream_t stream);
+int og_bu_att_fwd(const float* labels, const float* glove, const float* src, const unsigned char* mask, int B, int E,
+                  int R, int L, int idf, int norm, float eps, float* wc, float* attn, cudaStream_t stream);
+int og_bu_att_bwd(const float* attn, const float* g_wc, int B, int R, int L, int idf, float* g_src,
+                  cudaStream_t stream);
+int og_paint_max_fwd(const float* f, const float* m, int B, int num, int R, int Rtot, long long P, float* out,
+                     int dstride, int doff, cudaStream_t stream);
+int og_paint_max_bwd(const float* f, const float* m, const float* g, int gstride, int goff, int B, int num, int R,
+                     int Rtot, long long P, float* g_f, cudaStream_t stream);
+int og_func_attention_fwd(const float* query, const float* ctx, int B, int ndf, int Lq, int S, float gamma1, float* wc,
+                          float* attn, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Layout, adjoints of pad / upsample, concat, losses, optimiser
+ * -- replaces ATen elementwise kernels behind ref: model.py:45 (Upsample), 67 (ReflectionPad2d), torch.cat at
+ * model.py:579, 697, 1041; nn.BCELoss in miscc/losses.py:178-208, 378-393; KL_loss miscc/losses.py:533-537;
+ * CA_NET.reparametrize model.py:470-478; optim.Adam + EMA trainer.py:197-224, 461-462.
+ * ---------------------------------------------------------------------------------------------------- */
+int og_nchw_to_nhwc(const float* x, int N, int C, int H, int W, int Cp, float* y, cudaStream_t stream);
+int og_nhwc_to_nchw(const float* y, int N, int C, int H, int W, int Cp, float* x, cudaStream_t stream);
+int og_act_backward(const float* out, const float* g, long long n, int act, float slope, float* gin,
+                    cudaStream_t stream);
+int og_channel_sum(const float* x, long long P, int C, double* scratch, float* out, int n_out, int accumulate,
+                   cudaStream_t stream);
+int og_upsample2x_bwd(const float* gu, int N, int H, int W, int C, float* gx, cudaStream_t stream);
+int og_reflect_pad_fwd(const float* x, int N, int H, int W, int C, float* xp, cudaStream_t stream);
+int og_reflect_pad_bwd(const float* gpad, int N, int H, int W, int C, float* gx, cudaStream_t stream);
+int og_copy_channels(const float* src, int sstride, int soff, float* dst, int dstride, int doff, int nch, long long P,
+                     int accumulate, cudaStream_t stream);
+int og_broadcast_channels(const float* c, int B, int Cc, float* dst, int dstride, int doff, long long pix_per_img,
+                          cudaStream_t stream);
+int og_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
+int og_glu_fwd(const float* x, long long P, int Ch, float* out, cudaStream_t stream);
+int og_glu_bwd(const float* x, const float* g, long long P, int Ch, float* gx, cudaStream_t stream);
+int og_reparam_fwd(const float* x, int xs, const float* eps, int B, int D, float* c, int cs, cudaStream_t stream);
+int og_reparam_bwd(const float* x, int xs, const float* eps, const float* gc, int gcs, int B, int D, float* gx,
+                   cudaStream_t stream);
+int og_bce(const float* p, long long n, float target, float weight, float* loss_accum, float* gp, cudaStream_t stream);
+int og_kl(const float* x, int xs, int B, int D, float weight, float* loss_accum, float* gx, cudaStream_t stream);
+int og_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long long n, double lr, double b1, double b2,
+                double eps, int step, float gscale, float decay, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBJGAN_B200_H */

@@ -1,0 +1,556 @@
+// Word- and object-level attention of GlobalAttention.py plus the mask-paint of miscc/utils.py,
+// as fused bandwidth-bound kernels.  All "ref:" paths are under /root/reference/image_generation/.
+//
+//   og_words_proj*        conv1x1 of the word embeddings (ref: GlobalAttention.py:97-100, 151-154)
+//   og_att_general_*      GlobalAttentionGeneral / ATT_NET    (ref: GlobalAttention.py:83-122)
+//   og_bu_att_*           GlobalBUAttentionGeneral / BT_ATT_NET (ref: GlobalAttention.py:136-181)
+//   og_paint_max_*        pprocess_bt_attns                   (ref: miscc/utils.py:401-413)
+//   og_func_attention_fwd func_attention (DAMSM)              (ref: GlobalAttention.py:32-70)
+//
+// The grid attention streams h_code once (4*C bytes / query), writes the context once and the
+// attention map once: algorithmic bytes 4*Q*(2C + L) per image.
+#include "common.cuh"
+
+constexpr int LMAX = 32;   // max caption length handled in registers (reference uses 12..18)
+constexpr int ATT_Q = 128; // queries per block
+
+// src[b][c][l] = sum_k W[c][k] * words[b][k][l]
+__global__ void words_proj_kernel(const float* __restrict__ words, const float* __restrict__ W, int idf, int cdf,
+                                  int L, float* __restrict__ src) {
+  const int b = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < idf * L; i += gridDim.x * blockDim.x) {
+    int c = i / L, l = i - c * L;
+    const float* wr = W + c * cdf;
+    const float* wd = words + (long long)b * cdf * L + l;
+    float acc = 0.f;
+    for (int k = 0; k < cdf; ++k) acc = fmaf(__ldg(wr + k), __ldg(wd + (long long)k * L), acc);
+    src[((long long)b * idf + c) * L + l] = acc;
+  }
+}
+// gW[c][k] += sum_b sum_l gsrc[b][c][l] * words[b][k][l];   gwords[b][k][l] = sum_c W[c][k] * gsrc[b][c][l]
+__global__ void words_proj_bwd_w_kernel(const float* __restrict__ words, const float* __restrict__ gsrc, int B,
+                                        int idf, int cdf, int L, float* __restrict__ gW, int accumulate) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < idf * cdf; i += gridDim.x * blockDim.x) {
+    int c = i / cdf, k = i - c * cdf;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float* gs = gsrc + ((long long)b * idf + c) * L;
+      const float* wd = words + ((long long)b * cdf + k) * L;
+      for (int l = 0; l < L; ++l) acc = fmaf(gs[l], wd[l], acc);
+    }
+    gW[i] = accumulate ? gW[i] + acc : acc;
+  }
+}
+__global__ void words_proj_bwd_x_kernel(const float* __restrict__ W, const float* __restrict__ gsrc, int idf, int cdf,
+                                        int L, float* __restrict__ gwords) {
+  const int b = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cdf * L; i += gridDim.x * blockDim.x) {
+    int k = i / L, l = i - k * L;
+    float acc = 0.f;
+    for (int c = 0; c < idf; ++c) acc = fmaf(W[c * cdf + k], gsrc[((long long)b * idf + c) * L + l], acc);
+    gwords[(long long)b * cdf * L + i] = acc;
+  }
+}
+
+OG_API int og_words_proj(const float* words, const float* W, int B, int idf, int cdf, int L, float* src,
+                         cudaStream_t stream) {
+  if (B == 0) return 0;
+  dim3 grid(og_cdiv(idf * L, 128), B);
+  words_proj_kernel<<<grid, 128, 0, stream>>>(words, W, idf, cdf, L, src);
+  OG_RETURN_LAST_ERROR();
+}
+OG_API int og_words_proj_bwd(const float* words, const float* W, const float* gsrc, int B, int idf, int cdf, int L,
+                             float* gW, int accumulate, float* gwords, cudaStream_t stream) {
+  if (gW) words_proj_bwd_w_kernel<<<og_cdiv(idf * cdf, 128), 128, 0, stream>>>(words, gsrc, B, idf, cdf, L, gW, accumulate);
+  if (gwords && B > 0) {
+    dim3 grid(og_cdiv(cdf * L, 128), B);
+    words_proj_bwd_x_kernel<<<grid, 128, 0, stream>>>(W, gsrc, idf, cdf, L, gwords);
+  }
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid attention forward.  h: [B][Q][cs] (NHWC, idf real channels, row stride cs), src: [B][idf][L],
+// mask: [B][L] bytes (1 = padding word) or null.  wc: [B][Q][cs] (pad lanes zeroed), attn: [B][L][Q].
+// Mask quirk (ref: GlobalAttention.py:108): row (b, q) uses the caption mask of sample (b*Q + q) mod B.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_Q) att_general_fwd_kernel(const float* __restrict__ h,
+                                                                const float* __restrict__ src,
+                                                                const unsigned char* __restrict__ mask, int B, int Q,
+                                                                int idf, int cs, int L, float* __restrict__ wc,
+                                                                float* __restrict__ attn) {
+  extern __shared__ float smem[];
+  const int pitch = cs + 1;
+  float* tile = smem;                    // [ATT_Q][pitch]
+  float* ssrc = smem + ATT_Q * pitch;    // [idf][L]
+  const int b = blockIdx.y, q0 = blockIdx.x * ATT_Q, t = threadIdx.x;
+  const int nq = min(ATT_Q, Q - q0);
+  for (int i = t; i < idf * L; i += ATT_Q) ssrc[i] = src[(long long)b * idf * L + i];
+  const float* hb = h + ((long long)b * Q + q0) * cs;
+  for (int i = t; i < nq * cs / 4; i += ATT_Q) {
+    float4 v = ldg4(hb + i * 4);
+    int r = (i * 4) / cs, c = (i * 4) - r * cs;
+    float* d = tile + r * pitch + c;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  if (t < nq) {
+    float s[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) s[l] = 0.f;
+    float* row = tile + t * pitch;
+    for (int c = 0; c < idf; ++c) {
+      float hv = row[c];
+      const float* sr = ssrc + c * L;
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l)
+        if (l < L) s[l] = fmaf(hv, sr[l], s[l]);
+    }
+    const int q = q0 + t;
+    float mx = -INFINITY;
+    if (mask) {
+      const unsigned char* mr = mask + (((long long)b * Q + q) % B) * L;
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l)
+        if (l < L && mr[l]) s[l] = -INFINITY;
+    }
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < L) mx = fmaxf(mx, s[l]);
+    float sum = 0.f;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < L) {
+        s[l] = expf(s[l] - mx);
+        sum += s[l];
+      }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < L) {
+        s[l] *= inv;
+        attn[((long long)b * L + l) * Q + q] = s[l];
+      }
+    for (int c = 0; c < cs; ++c) {
+      float acc = 0.f;
+      if (c < idf) {
+        const float* sr = ssrc + c * L;
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l)
+          if (l < L) acc = fmaf(sr[l], s[l], acc);
+      }
+      row[c] = acc;
+    }
+  }
+  __syncthreads();
+  float* wb = wc + ((long long)b * Q + q0) * cs;
+  for (int i = t; i < nq * cs / 4; i += ATT_Q) {
+    int r = (i * 4) / cs, c = (i * 4) - r * cs;
+    const float* d = tile + r * pitch + c;
+    st4(wb + i * 4, make_float4(d[0], d[1], d[2], d[3]));
+  }
+}
+
+OG_API int og_att_general_fwd(const float* h, const float* src, const unsigned char* mask, int B, int Q, int idf,
+                              int cs, int L, float* wc, float* attn, cudaStream_t stream) {
+  if (L > LMAX || cs % 4 || idf > cs) return (int)cudaErrorInvalidValue;
+  if (B == 0 || Q == 0) return 0;
+  size_t sm = sizeof(float) * (ATT_Q * (cs + 1) + idf * L);
+  OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  dim3 grid(og_cdiv(Q, ATT_Q), B);
+  att_general_fwd_kernel<<<grid, ATT_Q, sm, stream>>>(h, src, mask, B, Q, idf, cs, L, wc, attn);
+  OG_RETURN_LAST_ERROR();
+}
+
+// backward: g_h [B][Q][cs], g_src [B][idf][L] (accumulated atomically; zeroed by the launcher).
+// g_attn ([B][L][Q]) may be null (the attention maps are only visualised in training).
+__global__ void __launch_bounds__(ATT_Q) att_general_bwd_kernel(const float* __restrict__ h,
+                                                                const float* __restrict__ src,
+                                                                const float* __restrict__ attn,
+                                                                const float* __restrict__ g_wc,
+                                                                const float* __restrict__ g_attn, int B, int Q,
+                                                                int idf, int cs, int L, float* __restrict__ g_h,
+                                                                float* __restrict__ g_src) {
+  extern __shared__ float smem[];
+  const int pitch = cs + 1;
+  float* th = smem;                         // [ATT_Q][pitch]  h rows, later g_h rows
+  float* tg = th + ATT_Q * pitch;           // [ATT_Q][pitch]  g_wc rows
+  float* sA = tg + ATT_Q * pitch;           // [ATT_Q][L]
+  float* sG = sA + ATT_Q * L;               // [ATT_Q][L]     gS
+  float* ssrc = sG + ATT_Q * L;             // [idf][L]
+  const int b = blockIdx.y, q0 = blockIdx.x * ATT_Q, t = threadIdx.x;
+  const int nq = min(ATT_Q, Q - q0);
+  for (int i = t; i < idf * L; i += ATT_Q) ssrc[i] = src[(long long)b * idf * L + i];
+  const float* hb = h + ((long long)b * Q + q0) * cs;
+  const float* gb = g_wc + ((long long)b * Q + q0) * cs;
+  for (int i = t; i < nq * cs / 4; i += ATT_Q) {
+    int r = (i * 4) / cs, c = (i * 4) - r * cs;
+    float4 v = ldg4(hb + i * 4), w = ldg4(gb + i * 4);
+    float* d = th + r * pitch + c;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    float* e = tg + r * pitch + c;
+    e[0] = w.x; e[1] = w.y; e[2] = w.z; e[3] = w.w;
+  }
+  __syncthreads();
+  float gS[LMAX];
+  float hrow_keep = 0.f;
+  (void)hrow_keep;
+  if (t < nq) {
+    const int q = q0 + t;
+    float A[LMAX], gA[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      A[l] = 0.f;
+      gA[l] = 0.f;
+      if (l < L) {
+        A[l] = attn[((long long)b * L + l) * Q + q];
+        if (g_attn) gA[l] = g_attn[((long long)b * L + l) * Q + q];
+      }
+    }
+    const float* grow = tg + t * pitch;
+    for (int c = 0; c < idf; ++c) {
+      float gv = grow[c];
+      const float* sr = ssrc + c * L;
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l)
+        if (l < L) gA[l] = fmaf(gv, sr[l], gA[l]);
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < L) dot = fmaf(gA[l], A[l], dot);
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      gS[l] = 0.f;
+      if (l < L) {
+        gS[l] = A[l] * (gA[l] - dot);
+        sA[t * L + l] = A[l];
+        sG[t * L + l] = gS[l];
+      }
+    }
+  } else {
+    for (int l = 0; l < L; ++l) {
+      sA[t * L + l] = 0.f;
+      sG[t * L + l] = 0.f;
+    }
+    for (int c = 0; c < cs; ++c) {
+      th[t * pitch + c] = 0.f;
+      tg[t * pitch + c] = 0.f;
+    }
+  }
+  __syncthreads();
+  // block-partial g_src[c][l] = sum_t h[t][c] * gS[t][l] + g_wc[t][c] * A[t][l]
+  for (int i = t; i < idf * L; i += ATT_Q) {
+    int c = i / L, l = i - c * L;
+    float acc = 0.f;
+    for (int r = 0; r < ATT_Q; ++r)
+      acc = fmaf(th[r * pitch + c], sG[r * L + l], fmaf(tg[r * pitch + c], sA[r * L + l], acc));
+    atomicAdd(g_src + (long long)b * idf * L + i, acc);
+  }
+  __syncthreads();
+  if (t < nq) {
+    float* row = th + t * pitch;
+    for (int c = 0; c < cs; ++c) {
+      float acc = 0.f;
+      if (c < idf) {
+        const float* sr = ssrc + c * L;
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l)
+          if (l < L) acc = fmaf(gS[l], sr[l], acc);
+      }
+      row[c] = acc;
+    }
+  }
+  __syncthreads();
+  float* ob = g_h + ((long long)b * Q + q0) * cs;
+  for (int i = t; i < nq * cs / 4; i += ATT_Q) {
+    int r = (i * 4) / cs, c = (i * 4) - r * cs;
+    const float* d = th + r * pitch + c;
+    st4(ob + i * 4, make_float4(d[0], d[1], d[2], d[3]));
+  }
+}
+
+OG_API int og_att_general_bwd(const float* h, const float* src, const float* attn, const float* g_wc,
+                              const float* g_attn, int B, int Q, int idf, int cs, int L, float* g_h, float* g_src,
+                              cudaStream_t stream) {
+  if (L > LMAX || cs % 4 || idf > cs) return (int)cudaErrorInvalidValue;
+  OG_CHECK(cudaMemsetAsync(g_src, 0, sizeof(float) * (size_t)B * idf * L, stream));
+  if (B == 0 || Q == 0) return 0;
+  size_t sm = sizeof(float) * (2 * ATT_Q * (cs + 1) + 2 * ATT_Q * L + idf * L);
+  OG_CHECK(cudaFuncSetAttribute(att_general_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  dim3 grid(og_cdiv(Q, ATT_Q), B);
+  att_general_bwd_kernel<<<grid, ATT_Q, sm, stream>>>(h, src, attn, g_wc, g_attn, B, Q, idf, cs, L, g_h, g_src);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// bottom-up (object) attention: one block per sample.
+// labels [B][E][R] (E = 50 GloVe dims), glove [B][E][L], src [B][idf][L], mask [B][L] bytes or null
+// -> wc [B][idf][R], attn [B][L][R].   Cosine normalisation when `norm` (cfg.TRAIN.BUATTN_NORM).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bu_att_fwd_kernel(const float* __restrict__ labels,
+                                                         const float* __restrict__ glove,
+                                                         const float* __restrict__ src,
+                                                         const unsigned char* __restrict__ mask, int B, int E, int R,
+                                                         int L, int idf, int norm, float eps, float* __restrict__ wc,
+                                                         float* __restrict__ attn) {
+  extern __shared__ float smem[];
+  float* S = smem;          // [R][L]
+  float* nl = S + R * L;    // [R]
+  float* ng = nl + R;       // [L]
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* lb = labels + (long long)b * E * R;
+  const float* gb = glove + (long long)b * E * L;
+  for (int r = t; r < R; r += 128) {
+    float a = 0.f;
+    for (int e = 0; e < E; ++e) a = fmaf(lb[e * R + r], lb[e * R + r], a);
+    nl[r] = sqrtf(a);
+  }
+  for (int l = t; l < L; l += 128) {
+    float a = 0.f;
+    for (int e = 0; e < E; ++e) a = fmaf(gb[e * L + l], gb[e * L + l], a);
+    ng[l] = sqrtf(a);
+  }
+  __syncthreads();
+  for (int i = t; i < R * L; i += 128) {
+    int r = i / L, l = i - r * L;
+    float a = 0.f;
+    for (int e = 0; e < E; ++e) a = fmaf(lb[e * R + r], gb[e * L + l], a);
+    if (norm) a = a / fmaxf(nl[r] * ng[l], eps);
+    if (mask && mask[(((long long)b * R + r) % B) * L + l]) a = -INFINITY;
+    S[i] = a;
+  }
+  __syncthreads();
+  for (int r = t; r < R; r += 128) {
+    float mx = -INFINITY;
+    for (int l = 0; l < L; ++l) mx = fmaxf(mx, S[r * L + l]);
+    float sum = 0.f;
+    for (int l = 0; l < L; ++l) {
+      float e = expf(S[r * L + l] - mx);
+      S[r * L + l] = e;
+      sum += e;
+    }
+    float inv = 1.f / sum;
+    for (int l = 0; l < L; ++l) {
+      float a = S[r * L + l] * inv;
+      S[r * L + l] = a;
+      attn[((long long)b * L + l) * R + r] = a;
+    }
+  }
+  __syncthreads();
+  const float* sb = src + (long long)b * idf * L;
+  for (int i = t; i < idf * R; i += 128) {
+    int c = i / R, r = i - c * R;
+    float a = 0.f;
+    for (int l = 0; l < L; ++l) a = fmaf(sb[c * L + l], S[r * L + l], a);
+    wc[(long long)b * idf * R + i] = a;
+  }
+}
+OG_API int og_bu_att_fwd(const float* labels, const float* glove, const float* src, const unsigned char* mask, int B,
+                         int E, int R, int L, int idf, int norm, float eps, float* wc, float* attn,
+                         cudaStream_t stream) {
+  if (B == 0 || R == 0) return 0;
+  size_t sm = sizeof(float) * (R * L + R + L);
+  bu_att_fwd_kernel<<<B, 128, sm, stream>>>(labels, glove, src, mask, B, E, R, L, idf, norm, eps, wc, attn);
+  OG_RETURN_LAST_ERROR();
+}
+// the attention weights depend only on constants (labels, GloVe), so the only gradient path is
+// g_src[b][c][l] = sum_r g_wc[b][c][r] * attn[b][l][r]
+__global__ void bu_att_bwd_kernel(const float* __restrict__ attn, const float* __restrict__ g_wc, int R, int L,
+                                  int idf, float* __restrict__ g_src) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < idf * L; i += blockDim.x) {
+    int c = i / L, l = i - c * L;
+    float a = 0.f;
+    for (int r = 0; r < R; ++r)
+      a = fmaf(g_wc[((long long)b * idf + c) * R + r], attn[((long long)b * L + l) * R + r], a);
+    g_src[(long long)b * idf * L + i] = a;
+  }
+}
+OG_API int og_bu_att_bwd(const float* attn, const float* g_wc, int B, int R, int L, int idf, float* g_src,
+                         cudaStream_t stream) {
+  if (B == 0) return 0;
+  bu_att_bwd_kernel<<<B, 128, 0, stream>>>(attn, g_wc, R, L, idf, g_src);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// mask paint: out[b][p][doff + k] = max_{r < R} f[b][k][r] * m[b][r][p]
+// f [B][num][R], m [B][Rtot][P] (first R roi slots used), out NHWC rows of stride dstride.
+// ---------------------------------------------------------------------------------------------
+constexpr int PAINT_PIX = 64;
+__global__ void __launch_bounds__(256) paint_max_fwd_kernel(const float* __restrict__ f,
+                                                            const float* __restrict__ m, int num, int R, int Rtot,
+                                                            long long P, float* __restrict__ out, int dstride,
+                                                            int doff) {
+  extern __shared__ float smem[];
+  float* sf = smem;             // [num][R]
+  float* sm = smem + num * R;   // [R][PAINT_PIX]
+  const int b = blockIdx.y, t = threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * PAINT_PIX;
+  const int np = (int)min((long long)PAINT_PIX, P - p0);
+  for (int i = t; i < num * R; i += 256) sf[i] = f[(long long)b * num * R + i];
+  for (int i = t; i < R * PAINT_PIX; i += 256) {
+    int r = i / PAINT_PIX, j = i - r * PAINT_PIX;
+    sm[i] = j < np ? m[((long long)b * Rtot + r) * P + p0 + j] : 0.f;
+  }
+  __syncthreads();
+  for (int i = t; i < np * num; i += 256) {
+    int j = i / num, k = i - j * num;
+    float v = sf[k * R] * sm[j];
+    for (int r = 1; r < R; ++r) v = fmaxf(v, sf[k * R + r] * sm[r * PAINT_PIX + j]);
+    out[((long long)b * P + p0 + j) * dstride + doff + k] = v;
+  }
+}
+OG_API int og_paint_max_fwd(const float* f, const float* m, int B, int num, int R, int Rtot, long long P, float* out,
+                            int dstride, int doff, cudaStream_t stream) {
+  if (B == 0 || P == 0) return 0;
+  size_t sm = sizeof(float) * (num * R + R * PAINT_PIX);
+  dim3 grid(og_cdiv(P, PAINT_PIX), B);
+  paint_max_fwd_kernel<<<grid, 256, sm, stream>>>(f, m, num, R, Rtot, P, out, dstride, doff);
+  OG_RETURN_LAST_ERROR();
+}
+// g_f[b][k][r] += sum_p g[b][p][goff + k] * m[b][r][p] * [r == argmax_r f*m]   (first maximal r)
+__global__ void __launch_bounds__(256) paint_max_bwd_kernel(const float* __restrict__ f,
+                                                            const float* __restrict__ m,
+                                                            const float* __restrict__ g, int gstride, int goff,
+                                                            int num, int R, int Rtot, long long P,
+                                                            float* __restrict__ g_f) {
+  extern __shared__ float smem[];
+  float* sf = smem;                   // [num][R]
+  float* sm = sf + num * R;           // [R][PAINT_PIX]
+  float* sacc = sm + R * PAINT_PIX;   // [num][R]
+  const int b = blockIdx.y, t = threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * PAINT_PIX;
+  const int np = (int)min((long long)PAINT_PIX, P - p0);
+  for (int i = t; i < num * R; i += 256) {
+    sf[i] = f[(long long)b * num * R + i];
+    sacc[i] = 0.f;
+  }
+  for (int i = t; i < R * PAINT_PIX; i += 256) {
+    int r = i / PAINT_PIX, j = i - r * PAINT_PIX;
+    sm[i] = j < np ? m[((long long)b * Rtot + r) * P + p0 + j] : 0.f;
+  }
+  __syncthreads();
+  for (int i = t; i < np * num; i += 256) {
+    int j = i / num, k = i - j * num;
+    float best = sf[k * R] * sm[j];
+    int br = 0;
+    for (int r = 1; r < R; ++r) {
+      float v = sf[k * R + r] * sm[r * PAINT_PIX + j];
+      if (v > best) {
+        best = v;
+        br = r;
+      }
+    }
+    float mv = sm[br * PAINT_PIX + j];
+    if (mv != 0.f) atomicAdd(&sacc[k * R + br], g[((long long)b * P + p0 + j) * gstride + goff + k] * mv);
+  }
+  __syncthreads();
+  for (int i = t; i < num * R; i += 256)
+    if (sacc[i] != 0.f) atomicAdd(g_f + (long long)b * num * R + i, sacc[i]);
+}
+OG_API int og_paint_max_bwd(const float* f, const float* m, const float* g, int gstride, int goff, int B, int num,
+                            int R, int Rtot, long long P, float* g_f, cudaStream_t stream) {
+  OG_CHECK(cudaMemsetAsync(g_f, 0, sizeof(float) * (size_t)B * num * R, stream));
+  if (B == 0 || P == 0) return 0;
+  size_t sm = sizeof(float) * (2 * num * R + R * PAINT_PIX);
+  dim3 grid(og_cdiv(P, PAINT_PIX), B);
+  paint_max_bwd_kernel<<<grid, 256, sm, stream>>>(f, m, g, gstride, goff, num, R, Rtot, P, g_f);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// func_attention forward (DAMSM): one block per (image, caption) pair.
+// query [B][ndf][Lq], context [B][ndf][S] (NCHW feature map flattened) -> wc [B][ndf][Lq], attn [B][Lq][S]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) func_attention_fwd_kernel(const float* __restrict__ query,
+                                                                 const float* __restrict__ ctx, int ndf, int Lq,
+                                                                 int S, float gamma1, float* __restrict__ wc,
+                                                                 float* __restrict__ attn) {
+  extern __shared__ float smem[];
+  float* sq = smem;              // [ndf][Lq]
+  float* sp = smem + ndf * Lq;   // [S][Lq]  scores / probabilities
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const float* qb = query + (long long)b * ndf * Lq;
+  const float* cb = ctx + (long long)b * ndf * S;
+  for (int i = t; i < ndf * Lq; i += 256) sq[i] = qb[i];
+  __syncthreads();
+  // phase 1+2: scores per region, softmax over the words (ref: GlobalAttention.py:49-53)
+  for (int s = t; s < S; s += 256) {
+    float acc[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) acc[l] = 0.f;
+    for (int c = 0; c < ndf; ++c) {
+      float cv = __ldg(cb + (long long)c * S + s);
+      const float* qr = sq + c * Lq;
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l)
+        if (l < Lq) acc[l] = fmaf(cv, qr[l], acc[l]);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < Lq) mx = fmaxf(mx, acc[l]);
+    float sum = 0.f;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < Lq) {
+        acc[l] = expf(acc[l] - mx);
+        sum += acc[l];
+      }
+    float inv = 1.f / sum;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < Lq) sp[s * Lq + l] = acc[l] * inv;
+  }
+  __syncthreads();
+  // phase 3: per word, softmax over the regions of gamma1 * p (ref: GlobalAttention.py:57-62)
+  for (int l = warp; l < Lq; l += 8) {
+    float mx = -INFINITY;
+    for (int s = lane; s < S; s += 32) mx = fmaxf(mx, sp[s * Lq + l] * gamma1);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s = lane; s < S; s += 32) {
+      float e = expf(sp[s * Lq + l] * gamma1 - mx);
+      sp[s * Lq + l] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    float inv = 1.f / sum;
+    for (int s = lane; s < S; s += 32) {
+      float a = sp[s * Lq + l] * inv;
+      sp[s * Lq + l] = a;
+      attn[((long long)b * Lq + l) * S + s] = a;
+    }
+  }
+  __syncthreads();
+  // phase 4: weighted context (ref: GlobalAttention.py:66-68); warp per channel, lanes over regions
+  for (int c = warp; c < ndf; c += 8) {
+    float acc[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) acc[l] = 0.f;
+    for (int s = lane; s < S; s += 32) {
+      float cv = __ldg(cb + (long long)c * S + s);
+      const float* pr = sp + s * Lq;
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l)
+        if (l < Lq) acc[l] = fmaf(cv, pr[l], acc[l]);
+    }
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < Lq) {
+        float v = warp_sum(acc[l]);
+        if (lane == 0) wc[((long long)b * ndf + c) * Lq + l] = v;
+      }
+  }
+}
+OG_API int og_func_attention_fwd(const float* query, const float* ctx, int B, int ndf, int Lq, int S, float gamma1,
+                                 float* wc, float* attn, cudaStream_t stream) {
+  if (Lq > LMAX) return (int)cudaErrorInvalidValue;
+  if (B == 0) return 0;
+  size_t sm = sizeof(float) * ((size_t)ndf * Lq + (size_t)S * Lq);
+  OG_CHECK(cudaFuncSetAttribute(func_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  func_attention_fwd_kernel<<<B, 256, sm, stream>>>(query, ctx, ndf, Lq, S, gamma1, wc, attn);
+  OG_RETURN_LAST_ERROR();
+}

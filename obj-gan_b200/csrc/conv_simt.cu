@@ -1,0 +1,467 @@
+// Implicit-GEMM convolution on the CUDA cores (exact fp32 FMA arithmetic), NHWC activations.
+//
+// This is the general-purpose contraction kernel of the library: every conv / transposed conv /
+// linear layer of G_NET and the PAT_D_NETs (reference image_generation/model.py:36-49, 63-81,
+// 486-518, 589-617, 708-719, 999-1048) can run through it, in forward (fprop), input-gradient
+// (dgrad == fprop in OG_TRANSPOSED addressing with re-packed weights) and weight-gradient (wgrad).
+// The tcgen05 path (conv_tc.cu) takes over the shapes that dominate the step; this kernel stays as
+// the exact-fp32 path for small / odd shapes and as the on-device cross-check.
+//
+// GEMM view (fprop): rows m = (n, oh, ow) output pixels, cols = output channels (padded to 4),
+// reduction k = (kh, kw, ci) with ci padded to 8.  A is gathered on the fly from the NHWC input
+// with the addressing mode (zero pad / reflection pad / nearest-2x-upsample-then-zero-pad /
+// transposed); B is a pre-packed [(kh,kw,ci)][co] matrix (og_pack_weights).
+#include "common.cuh"
+
+struct ConvArgs {
+  const float* x;  // source NHWC
+  int N, H, W, C;  // source dims (C % 8 == 0)
+  long long xsn, xsh, xsw;
+  const float* w;  // packed [(KH*KW*C)][K]
+  float* y;        // result NHWC, channels K (K % 4 == 0)
+  int OH, OW, K;
+  long long ysn, ysh, ysw;
+  int KH, KW, stride, pad, mode;
+  const float* bias;  // [K] or null
+  int act;
+  float slope;
+};
+
+__device__ __forceinline__ int src_coord(int mode, int o, int k, int stride, int pad, int Hs) {
+  if (mode == OG_PAD_ZERO) {
+    int i = o * stride + k - pad;
+    return (i < 0 || i >= Hs) ? -1 : i;
+  } else if (mode == OG_PAD_REFLECT) {
+    int i = o * stride + k - pad;
+    if (i < 0) i = -i;
+    if (i >= Hs) i = 2 * Hs - 2 - i;
+    return i;
+  } else if (mode == OG_UPSAMPLE2X) {
+    int u = o + k - pad;
+    return (u < 0 || u >= 2 * Hs) ? -1 : (u >> 1);
+  } else {  // OG_TRANSPOSED: rows are input pixels of the forward conv, source is the output gradient
+    int t = o + pad - k;
+    if (t < 0 || (t % stride) != 0) return -1;
+    int i = t / stride;
+    return i >= Hs ? -1 : i;
+  }
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == OG_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == OG_ACT_TANH) return tanhf(v);
+  if (act == OG_ACT_SIGMOID) return og_sigmoid(v);
+  return v;
+}
+
+constexpr int BM = 128, BK = 8, BMP = BM + 4;
+
+template <int TN>
+__device__ __forceinline__ void mma_tile(const float (*As)[BMP], const float* Bs, int bnp, float (&acc)[8][TN], int tx,
+                                         int ty) {
+#pragma unroll
+  for (int k = 0; k < BK; ++k) {
+    float a[8], b[TN];
+    float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+    float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+    a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    const float* brow = Bs + k * bnp;
+    if (TN == 8) {
+      float4 b0 = *reinterpret_cast<const float4*>(brow + tx * 4);
+      float4 b1 = *reinterpret_cast<const float4*>(brow + 64 + tx * 4);
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+      b[TN - 4] = b1.x; b[TN - 3] = b1.y; b[TN - 2] = b1.z; b[TN - 1] = b1.w;
+    } else if (TN == 4) {
+      float4 b0 = *reinterpret_cast<const float4*>(brow + tx * 4);
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+    } else {
+      float2 b0 = *reinterpret_cast<const float2*>(brow + tx * 2);
+      b[0] = b0.x; b[1] = b0.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
+// column of accumulator j for thread tx
+template <int TN>
+__device__ __forceinline__ int acc_col(int tx, int j) {
+  if (TN == 8) return j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4);
+  if (TN == 4) return tx * 4 + j;
+  return tx * 2 + j;
+}
+__device__ __forceinline__ int acc_row(int ty, int i) { return i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4); }
+
+template <int TN>
+__global__ void __launch_bounds__(256) conv_gemm_kernel(ConvArgs a) {
+  constexpr int BN = 16 * TN;
+  __shared__ __align__(16) float As[2][BK][BMP];
+  __shared__ __align__(16) float Bs[2][BK * BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long long M = (long long)a.N * a.OH * a.OW;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int cchunks = a.C / BK;
+  const int nk_total = a.KH * a.KW * cchunks;
+  // split-K range
+  const int per = (nk_total + gridDim.z - 1) / gridDim.z;
+  const int kt_beg = blockIdx.z * per;
+  const int kt_end = min(nk_total, kt_beg + per);
+  if (kt_beg >= kt_end) return;
+
+  // A-load role: one float4 per thread
+  const int ar = tid >> 1, ah = tid & 1;
+  const long long am = m0 + ar;
+  const bool am_ok = am < M;
+  int an = 0, aoh = 0, aow = 0;
+  if (am_ok) {
+    an = (int)(am / ((long long)a.OH * a.OW));
+    int rem = (int)(am - (long long)an * a.OH * a.OW);
+    aoh = rem / a.OW;
+    aow = rem - aoh * a.OW;
+  }
+  // B-load role
+  constexpr int COLS4 = BN / 4;
+  const int bk = tid / COLS4, bc4 = tid % COLS4;
+  const bool b_ok = (bk < BK) && (n0 + bc4 * 4 < a.K);
+
+  int tap = kt_beg / cchunks;
+  int cc = kt_beg - tap * cchunks;
+  const float* aptr = nullptr;
+  auto set_tap = [&](int t) {
+    aptr = nullptr;
+    if (!am_ok) return;
+    int kh = t / a.KW, kw = t - kh * a.KW;
+    int ih = src_coord(a.mode, aoh, kh, a.stride, a.pad, a.H);
+    int iw = src_coord(a.mode, aow, kw, a.stride, a.pad, a.W);
+    if (ih < 0 || iw < 0) return;
+    aptr = a.x + an * a.xsn + ih * a.xsh + iw * a.xsw + ah * 4;
+  };
+  set_tap(tap);
+
+  float4 ra, rb;
+  auto gload = [&](int kt) {
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = ra;
+    if (aptr) ra = ldg4(aptr + cc * BK);
+    if (b_ok) rb = ldg4(a.w + (long long)(kt * BK + bk) * a.K + n0 + bc4 * 4);
+  };
+  auto sstore = [&](int buf) {
+    As[buf][ah * 4 + 0][ar] = ra.x;
+    As[buf][ah * 4 + 1][ar] = ra.y;
+    As[buf][ah * 4 + 2][ar] = ra.z;
+    As[buf][ah * 4 + 3][ar] = ra.w;
+    if (bk < BK) *reinterpret_cast<float4*>(&Bs[buf][bk * BN + bc4 * 4]) = rb;
+  };
+  auto advance = [&]() {
+    if (++cc == cchunks) {
+      cc = 0;
+      ++tap;
+      if (tap < a.KH * a.KW) set_tap(tap);
+    }
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  gload(kt_beg);
+  sstore(0);
+  advance();
+  __syncthreads();
+  int cur = 0;
+  for (int kt = kt_beg; kt < kt_end; ++kt) {
+    const bool more = kt + 1 < kt_end;
+    if (more) gload(kt + 1);
+    mma_tile<TN>(As[cur], Bs[cur], BN, acc, tx, ty);
+    if (more) {
+      sstore(cur ^ 1);
+      advance();
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+
+  // epilogue
+  const bool atomic = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    long long m = m0 + acc_row(ty, i);
+    if (m >= M) continue;
+    int n = (int)(m / ((long long)a.OH * a.OW));
+    int rem = (int)(m - (long long)n * a.OH * a.OW);
+    int oh = rem / a.OW, ow = rem - oh * a.OW;
+    float* yrow = a.y + n * a.ysn + oh * a.ysh + ow * a.ysw;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int c = n0 + acc_col<TN>(tx, j);
+      if (c >= a.K) continue;
+      float v = acc[i][j];
+      if (atomic) {
+        atomicAdd(yrow + c, v);
+      } else {
+        if (a.bias) v += __ldg(a.bias + c);
+        yrow[c] = apply_act(v, a.act, a.slope);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dW[(kh,kw,ci)][co] += sum over output pixels m of  x[src(m,kh,kw)][ci] * g[m][co]
+// ---------------------------------------------------------------------------------------------
+struct WgradArgs {
+  const float* x;  // forward input NHWC
+  int N, H, W, C;
+  long long xsn, xsh, xsw;
+  const float* g;  // output gradient NHWC, K channels
+  int OH, OW, K;
+  long long gsn, gsh, gsw;
+  float* dw;  // packed [(KH*KW*C)][K], accumulated with atomicAdd
+  int KH, KW, stride, pad, mode;
+  int pix_per_split;  // multiple of 8
+};
+
+template <int TN>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
+  constexpr int BN = 16 * TN;
+  __shared__ __align__(16) float As[2][BK][BMP];
+  __shared__ __align__(16) float Bs[2][BK * BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int R = a.KH * a.KW * a.C;
+  const int r0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const long long M = (long long)a.N * a.OH * a.OW;
+  const long long mbeg = (long long)blockIdx.z * a.pix_per_split;
+  const long long mend = min(M, mbeg + a.pix_per_split);
+  if (mbeg >= mend) return;
+  const int nk = (int)((mend - mbeg + BK - 1) / BK);
+
+  // A-load role: pixel pj of the chunk, rows q*4..q*4+3 of the tile
+  const int pj = tid >> 5, q = tid & 31;
+  const int r = r0 + q * 4;
+  const bool r_ok = r < R;
+  int kh = 0, kw = 0, ci = 0;
+  if (r_ok) {
+    int tap = r / a.C;
+    ci = r - tap * a.C;
+    kh = tap / a.KW;
+    kw = tap - kh * a.KW;
+  }
+  constexpr int COLS4 = BN / 4;
+  const int bp = tid / COLS4, bc4 = tid % COLS4;
+  const bool b_ok = (bp < BK) && (n0 + bc4 * 4 < a.K);
+  const long long ohow = (long long)a.OH * a.OW;
+
+  float4 ra, rb;
+  auto gload = [&](int kt) {
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = ra;
+    long long m = mbeg + (long long)kt * BK + pj;
+    if (r_ok && m < mend) {
+      int n = (int)(m / ohow);
+      int rem = (int)(m - n * ohow);
+      int oh = rem / a.OW, ow = rem - oh * a.OW;
+      int ih = src_coord(a.mode, oh, kh, a.stride, a.pad, a.H);
+      int iw = src_coord(a.mode, ow, kw, a.stride, a.pad, a.W);
+      if (ih >= 0 && iw >= 0) ra = ldg4(a.x + n * a.xsn + ih * a.xsh + iw * a.xsw + ci);
+    }
+    long long mb = mbeg + (long long)kt * BK + bp;
+    if (b_ok && mb < mend) {
+      int n = (int)(mb / ohow);
+      int rem = (int)(mb - n * ohow);
+      int oh = rem / a.OW, ow = rem - oh * a.OW;
+      rb = ldg4(a.g + n * a.gsn + oh * a.gsh + ow * a.gsw + n0 + bc4 * 4);
+    }
+  };
+  auto sstore = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][pj][q * 4]) = ra;
+    if (bp < BK) *reinterpret_cast<float4*>(&Bs[buf][bp * BN + bc4 * 4]) = rb;
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int cur = 0;
+  for (int kt = 0; kt < nk; ++kt) {
+    const bool more = kt + 1 < nk;
+    if (more) gload(kt + 1);
+    mma_tile<TN>(As[cur], Bs[cur], BN, acc, tx, ty);
+    if (more) sstore(cur ^ 1);
+    __syncthreads();
+    cur ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int rr = r0 + acc_row(ty, i);
+    if (rr >= R) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int c = n0 + acc_col<TN>(tx, j);
+      if (c >= a.K) continue;
+      atomicAdd(a.dw + (long long)rr * a.K + c, acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight (re)packing between the reference's OIHW parameter layout (state_dict shapes)
+// and the kernel-native K-major matrices.
+//   co_map(co) = co < split ? co : co + (splitp - split)   (GLU halves each padded to splitp)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, int Co, int Ci, int KH, int KW, int Cip, int Kp,
+                                    int split, int splitp, int transposed, float* __restrict__ out,
+                                    float* __restrict__ out_lo) {
+  long long total = (long long)Co * Ci * KH * KW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int kw = (int)(i % KW);
+    long long t = i / KW;
+    int kh = (int)(t % KH);
+    t /= KH;
+    int ci = (int)(t % Ci);
+    int co = (int)(t / Ci);
+    int cm = (split > 0 && co >= split) ? co + (splitp - split) : co;
+    long long o;
+    if (!transposed)
+      o = ((long long)(kh * KW + kw) * Cip + ci) * Kp + cm;
+    else
+      o = ((long long)(kh * KW + kw) * Kp + cm) * Cip + ci;
+    float v = w[i];
+    if (out_lo) {  // tf32 hi/lo split for the 3xTF32 tensor-core path
+      float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      out[o] = hi;
+      out_lo[o] = v - hi;
+    } else {
+      out[o] = v;
+    }
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Co, int Ci, int KH, int KW, int Cip, int Kp,
+                                    int split, int splitp, float* __restrict__ grad, int accumulate) {
+  long long total = (long long)Co * Ci * KH * KW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int kw = (int)(i % KW);
+    long long t = i / KW;
+    int kh = (int)(t % KH);
+    t /= KH;
+    int ci = (int)(t % Ci);
+    int co = (int)(t / Ci);
+    int cm = (split > 0 && co >= split) ? co + (splitp - split) : co;
+    float v = dw[((long long)(kh * KW + kw) * Cip + ci) * Kp + cm];
+    grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+static int pick_splits(long long tiles, int nk, int want_ctas) {
+  if (tiles >= want_ctas) return 1;
+  int s = (int)((want_ctas + tiles - 1) / tiles);
+  int maxs = nk / 16;  // keep at least 16 k-steps per split
+  if (s > maxs) s = maxs;
+  return s < 1 ? 1 : s;
+}
+
+OG_API int og_conv2d_simt(const float* x, int N, int H, int W, int C, long long xsn, long long xsh, long long xsw,
+                          const float* wpacked, float* y, int OH, int OW, int K, long long ysn, long long ysh,
+                          long long ysw, int KH, int KW, int stride, int pad, int mode, const float* bias, int act,
+                          float slope, int allow_splitk, cudaStream_t stream) {
+  if (C % 8 || K % 4) return (int)cudaErrorInvalidValue;
+  ConvArgs a{x, N, H, W, C, xsn, xsh, xsw, wpacked, y, OH, OW, K, ysn, ysh, ysw, KH, KW, stride, pad, mode, bias, act, slope};
+  long long M = (long long)N * OH * OW;
+  if (M == 0) return 0;
+  int TN = K > 64 ? 8 : (K > 32 ? 4 : 2);
+  int BN = 16 * TN;
+  dim3 grid(og_cdiv(M, BM), og_cdiv(K, BN), 1);
+  int nk = KH * KW * (C / 8);
+  if (allow_splitk && !bias && act == OG_ACT_NONE) {
+    int s = pick_splits((long long)grid.x * grid.y, nk, 296);
+    if (s > 1) {
+      // split-K accumulates with atomicAdd into a zeroed result
+      for (int n = 0; n < N; ++n)
+        for (int h = 0; h < OH; ++h)
+          if (ysw == K && ysh == (long long)OW * K) {
+            break;
+          }
+      if (ysw == K && ysh == (long long)OW * K && ysn == (long long)OH * OW * K) {
+        OG_CHECK(cudaMemsetAsync(y, 0, sizeof(float) * M * K, stream));
+        grid.z = s;
+      }
+    }
+  }
+  if (TN == 8)
+    conv_gemm_kernel<8><<<grid, 256, 0, stream>>>(a);
+  else if (TN == 4)
+    conv_gemm_kernel<4><<<grid, 256, 0, stream>>>(a);
+  else
+    conv_gemm_kernel<2><<<grid, 256, 0, stream>>>(a);
+  OG_RETURN_LAST_ERROR();
+}
+
+OG_API int og_conv2d_wgrad_simt(const float* x, int N, int H, int W, int C, long long xsn, long long xsh,
+                                long long xsw, const float* g, int OH, int OW, int K, long long gsn, long long gsh,
+                                long long gsw, float* dw_packed, int KH, int KW, int stride, int pad, int mode,
+                                cudaStream_t stream) {
+  if (C % 8 || K % 4) return (int)cudaErrorInvalidValue;
+  long long M = (long long)N * OH * OW;
+  int R = KH * KW * C;
+  OG_CHECK(cudaMemsetAsync(dw_packed, 0, sizeof(float) * (long long)R * K, stream));
+  if (M == 0) return 0;
+  int TN = K > 64 ? 8 : (K > 32 ? 4 : 2);
+  int BN = 16 * TN;
+  dim3 grid(og_cdiv(R, BM), og_cdiv(K, BN), 1);
+  long long tiles = (long long)grid.x * grid.y;
+  long long splits = (592 + tiles - 1) / tiles;
+  long long maxs = (M + 127) / 128;
+  if (splits > maxs) splits = maxs;
+  if (splits < 1) splits = 1;
+  long long pps = (M + splits - 1) / splits;
+  pps = (pps + 7) / 8 * 8;
+  grid.z = og_cdiv(M, pps);
+  WgradArgs a{x, N, H, W, C, xsn, xsh, xsw, g, OH, OW, K, gsn, gsh, gsw, dw_packed, KH, KW, stride, pad, mode, (int)pps};
+  if (TN == 8)
+    conv_wgrad_kernel<8><<<grid, 256, 0, stream>>>(a);
+  else if (TN == 4)
+    conv_wgrad_kernel<4><<<grid, 256, 0, stream>>>(a);
+  else
+    conv_wgrad_kernel<2><<<grid, 256, 0, stream>>>(a);
+  OG_RETURN_LAST_ERROR();
+}
+
+OG_API int og_pack_weights(const float* w_oihw, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split,
+                           int splitp, int transposed, float* out, float* out_lo, cudaStream_t stream) {
+  long long n = (long long)KH * KW * Cip * Kp;
+  OG_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * n, stream));
+  if (out_lo) OG_CHECK(cudaMemsetAsync(out_lo, 0, sizeof(float) * n, stream));
+  long long total = (long long)Co * Ci * KH * KW;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weights_kernel<<<blocks, 256, 0, stream>>>(w_oihw, Co, Ci, KH, KW, Cip, Kp, split, splitp, transposed, out,
+                                                  out_lo);
+  OG_RETURN_LAST_ERROR();
+}
+
+OG_API int og_unpack_wgrad(const float* dw_packed, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split,
+                           int splitp, float* grad_oihw, int accumulate, cudaStream_t stream) {
+  long long total = (long long)Co * Ci * KH * KW;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unpack_wgrad_kernel<<<blocks, 256, 0, stream>>>(dw_packed, Co, Ci, KH, KW, Cip, Kp, split, splitp, grad_oihw,
+                                                  accumulate);
+  OG_RETURN_LAST_ERROR();
+}

@@ -1,0 +1,456 @@
+// Bandwidth-bound helper kernels: layout conversion at the module boundary, activation / padding /
+// upsampling adjoints, channel concat, losses (BCE, KL), CA_NET reparametrisation, fused Adam + EMA.
+// Reference semantics cited per kernel (paths under /root/reference/image_generation/).
+#include "common.cuh"
+
+static int eblocks(long long total, int per = 256) {
+  long long b = (total + per - 1) / per;
+  long long cap = 148LL * 32;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW <-> NHWC(+channel padding).  Public tensors are NCHW fp32 like the reference's; kernels run NHWC.
+// ---------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, int HW, int Cp, float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xn = x + (long long)n * C * HW;
+  float* yn = y + (long long)n * HW * Cp;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int c = c0 + j, p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? xn[(long long)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int p = p0 + j, c = c0 + threadIdx.x;
+    if (p < HW && c < Cp) yn[(long long)p * Cp + c] = tile[threadIdx.x][j];
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ y, int C, int HW, int Cp, float* __restrict__ x) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* yn = y + (long long)n * HW * Cp;
+  float* xn = x + (long long)n * C * HW;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int p = p0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (p < HW && c < Cp) ? yn[(long long)p * Cp + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int c = c0 + j, p = p0 + threadIdx.x;
+    if (c < C && p < HW) xn[(long long)c * HW + p] = tile[threadIdx.x][j];
+  }
+}
+
+OG_API int og_nchw_to_nhwc(const float* x, int N, int C, int H, int W, int Cp, float* y, cudaStream_t stream) {
+  if (N == 0) return 0;
+  dim3 grid(og_cdiv((long long)H * W, 32), og_cdiv(Cp, 32), N), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, stream>>>(x, C, H * W, Cp, y);
+  OG_RETURN_LAST_ERROR();
+}
+OG_API int og_nhwc_to_nchw(const float* y, int N, int C, int H, int W, int Cp, float* x, cudaStream_t stream) {
+  if (N == 0) return 0;
+  dim3 grid(og_cdiv((long long)H * W, 32), og_cdiv(Cp, 32), N), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, stream>>>(y, C, H * W, Cp, x);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient through a conv-epilogue activation, from the saved OUTPUT (LeakyReLU / tanh / sigmoid)
+// ---------------------------------------------------------------------------------------------
+__global__ void act_backward_kernel(const float* __restrict__ out, const float* __restrict__ g, long long n4, int act,
+                                    float slope, float* __restrict__ gin) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 o = ldg4(out + i * 4), gg = ldg4(g + i * 4), r;
+    if (act == OG_ACT_LRELU) {
+      r.x = o.x > 0.f ? gg.x : gg.x * slope; r.y = o.y > 0.f ? gg.y : gg.y * slope;
+      r.z = o.z > 0.f ? gg.z : gg.z * slope; r.w = o.w > 0.f ? gg.w : gg.w * slope;
+    } else if (act == OG_ACT_TANH) {
+      r.x = gg.x * (1.f - o.x * o.x); r.y = gg.y * (1.f - o.y * o.y);
+      r.z = gg.z * (1.f - o.z * o.z); r.w = gg.w * (1.f - o.w * o.w);
+    } else if (act == OG_ACT_SIGMOID) {
+      r.x = gg.x * o.x * (1.f - o.x); r.y = gg.y * o.y * (1.f - o.y);
+      r.z = gg.z * o.z * (1.f - o.z); r.w = gg.w * o.w * (1.f - o.w);
+    } else {
+      r = gg;
+    }
+    st4(gin + i * 4, r);
+  }
+}
+OG_API int og_act_backward(const float* out, const float* g, long long n, int act, float slope, float* gin,
+                           cudaStream_t stream) {
+  if (n % 4) return (int)cudaErrorInvalidValue;
+  if (n == 0) return 0;
+  act_backward_kernel<<<eblocks(n / 4), 256, 0, stream>>>(out, g, n / 4, act, slope, gin);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-channel sum over pixels (conv bias gradient).  fp64 partials, one atomic per (block, channel).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ x, int C, long long P,
+                                                          int pix_per_block, double* __restrict__ acc) {
+  const int c4 = blockIdx.x * 32 + threadIdx.x;
+  const int C4 = C >> 2;
+  const long long p0 = (long long)blockIdx.y * pix_per_block, p1 = min(P, p0 + pix_per_block);
+  double s[4] = {0, 0, 0, 0};
+  if (c4 < C4)
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+      float4 v = ldg4(x + p * C + c4 * 4);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+  __shared__ double sh[8][32][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sh[threadIdx.y][threadIdx.x][i] = s[i];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 128) {
+    int cx = t >> 2, k = t & 3;
+    double a = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += sh[j][cx][k];
+    int cc4 = blockIdx.x * 32 + cx;
+    if (cc4 < C4) atomicAdd(&acc[cc4 * 4 + k], a);
+  }
+}
+__global__ void store_sum_kernel(const double* __restrict__ acc, int n, float* out, int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = accumulate ? out[i] + (float)acc[i] : (float)acc[i];
+}
+OG_API int og_channel_sum(const float* x, long long P, int C, double* scratch, float* out, int n_out, int accumulate,
+                          cudaStream_t stream) {
+  if (C % 4) return (int)cudaErrorInvalidValue;
+  OG_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * C, stream));
+  int cg = og_cdiv(C / 4, 32);
+  long long chunks = 148LL * 8 / cg + 1;
+  long long ppb = (P + chunks - 1) / chunks;
+  if (ppb < 64) ppb = 64;
+  dim3 grid(cg, og_cdiv(P, ppb)), block(32, 8);
+  if (P > 0) channel_sum_kernel<<<grid, block, 0, stream>>>(x, C, P, (int)ppb, scratch);
+  store_sum_kernel<<<og_cdiv(n_out, 256), 256, 0, stream>>>(scratch, n_out, out, accumulate);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// adjoint of nn.Upsample(scale_factor=2, mode='nearest') (model.py:45): sum of the 4 children
+// ---------------------------------------------------------------------------------------------
+__global__ void upsample2x_bwd_kernel(const float* __restrict__ gu, int H, int W, int C4, long long total,
+                                      float* __restrict__ gx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    long long t = i / C4;
+    int w = (int)(t % W);
+    t /= W;
+    int h = (int)(t % H);
+    long long n = t / H;
+    const float* b = gu + (((n * 2 * H + 2 * h) * 2 * W + 2 * w) * C4 + c) * 4;
+    long long rs = (long long)2 * W * C4 * 4;
+    float4 a = ldg4(b), b1 = ldg4(b + C4 * 4), c0 = ldg4(b + rs), c1 = ldg4(b + rs + C4 * 4);
+    st4(gx + i * 4, make_float4(a.x + b1.x + c0.x + c1.x, a.y + b1.y + c0.y + c1.y, a.z + b1.z + c0.z + c1.z,
+                                a.w + b1.w + c0.w + c1.w));
+  }
+}
+OG_API int og_upsample2x_bwd(const float* gu, int N, int H, int W, int C, float* gx, cudaStream_t stream) {
+  if (C % 4) return (int)cudaErrorInvalidValue;
+  long long total = (long long)N * H * W * (C / 4);
+  if (total == 0) return 0;
+  upsample2x_bwd_kernel<<<eblocks(total), 256, 0, stream>>>(gu, H, W, C / 4, total, gx);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// nn.ReflectionPad2d(1) (model.py:67, 72, 600): forward materialisation and adjoint (fold).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int refl(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+__global__ void reflect_pad_fwd_kernel(const float* __restrict__ x, int H, int W, int C4, long long total,
+                                       float* __restrict__ xp) {
+  const int Hp = H + 2, Wp = W + 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    long long t = i / C4;
+    int w = (int)(t % Wp);
+    t /= Wp;
+    int h = (int)(t % Hp);
+    long long n = t / Hp;
+    int sh = refl(h - 1, H), sw = refl(w - 1, W);
+    st4(xp + i * 4, ldg4(x + (((n * H + sh) * W + sw) * C4 + c) * 4));
+  }
+}
+OG_API int og_reflect_pad_fwd(const float* x, int N, int H, int W, int C, float* xp, cudaStream_t stream) {
+  if (C % 4) return (int)cudaErrorInvalidValue;
+  long long total = (long long)N * (H + 2) * (W + 2) * (C / 4);
+  if (total == 0) return 0;
+  reflect_pad_fwd_kernel<<<eblocks(total), 256, 0, stream>>>(x, H, W, C / 4, total, xp);
+  OG_RETURN_LAST_ERROR();
+}
+
+__global__ void reflect_pad_bwd_kernel(const float* __restrict__ gp, int H, int W, int C4, long long total,
+                                       float* __restrict__ gx) {
+  const int Wp = W + 2, Hp = H + 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    long long t = i / C4;
+    int w = (int)(t % W);
+    t /= W;
+    int h = (int)(t % H);
+    long long n = t / H;
+    // padded rows/cols that read input row h: h+1 always; row 0 if h == 1; row H+1 if h == H-2
+    int hs[3], nh = 0, ws[3], nw = 0;
+    hs[nh++] = h + 1;
+    if (h == 1) hs[nh++] = 0;
+    if (h == H - 2) hs[nh++] = H + 1;
+    ws[nw++] = w + 1;
+    if (w == 1) ws[nw++] = 0;
+    if (w == W - 2) ws[nw++] = W + 1;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ih = 0; ih < nh; ++ih)
+      for (int iw = 0; iw < nw; ++iw) {
+        float4 v = ldg4(gp + (((n * Hp + hs[ih]) * Wp + ws[iw]) * C4 + c) * 4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+    st4(gx + i * 4, a);
+  }
+}
+OG_API int og_reflect_pad_bwd(const float* gpad, int N, int H, int W, int C, float* gx, cudaStream_t stream) {
+  if (C % 4) return (int)cudaErrorInvalidValue;
+  long long total = (long long)N * H * W * (C / 4);
+  if (total == 0) return 0;
+  reflect_pad_bwd_kernel<<<eblocks(total), 256, 0, stream>>>(gpad, H, W, C / 4, total, gx);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// channel-slice copy (torch.cat along channels and its adjoint), optional accumulate
+// ---------------------------------------------------------------------------------------------
+__global__ void copy_channels_kernel(const float* __restrict__ src, int sstride, int soff, float* __restrict__ dst,
+                                     int dstride, int doff, int nch, long long P, int accumulate) {
+  long long total = P * nch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / nch;
+    int c = (int)(i - p * nch);
+    float v = src[p * sstride + soff + c];
+    float* d = dst + p * dstride + doff + c;
+    *d = accumulate ? *d + v : v;
+  }
+}
+OG_API int og_copy_channels(const float* src, int sstride, int soff, float* dst, int dstride, int doff, int nch,
+                            long long P, int accumulate, cudaStream_t stream) {
+  if (P * nch == 0) return 0;
+  copy_channels_kernel<<<eblocks(P * nch), 256, 0, stream>>>(src, sstride, soff, dst, dstride, doff, nch, P, accumulate);
+  OG_RETURN_LAST_ERROR();
+}
+
+// c_code (B, Cc) broadcast over each image's pixels into a channel slice (D_GET_LOGITS, model.py:1037-1041)
+__global__ void broadcast_channels_kernel(const float* __restrict__ c, int Cc, float* __restrict__ dst, int dstride,
+                                          int doff, long long pix_per_img, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / Cc;
+    int k = (int)(i - p * Cc);
+    long long b = p / pix_per_img;
+    dst[p * dstride + doff + k] = c[b * Cc + k];
+  }
+}
+OG_API int og_broadcast_channels(const float* c, int B, int Cc, float* dst, int dstride, int doff,
+                                 long long pix_per_img, cudaStream_t stream) {
+  long long total = (long long)B * pix_per_img * Cc;
+  if (total == 0) return 0;
+  broadcast_channels_kernel<<<eblocks(total), 256, 0, stream>>>(c, Cc, dst, dstride, doff, pix_per_img, total);
+  OG_RETURN_LAST_ERROR();
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
+                           long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 x = ldg4(a + i * 4), y = ldg4(b + i * 4);
+    st4(o + i * 4, make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w));
+  }
+}
+OG_API int og_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream) {
+  if (n % 4) return (int)cudaErrorInvalidValue;
+  if (n == 0) return 0;
+  add_kernel<<<eblocks(n / 4), 256, 0, stream>>>(a, b, out, n / 4);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// GLU without normalisation (CA_NET, model.py:464-468): rows of 2*Ch channels -> Ch
+// ---------------------------------------------------------------------------------------------
+__global__ void glu_fwd_kernel(const float* __restrict__ x, int Ch, long long total, float* __restrict__ o) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / Ch;
+    int c = (int)(i - p * Ch);
+    o[i] = x[p * 2 * Ch + c] * og_sigmoid(x[p * 2 * Ch + Ch + c]);
+  }
+}
+__global__ void glu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, int Ch, long long total,
+                               float* __restrict__ gx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / Ch;
+    int c = (int)(i - p * Ch);
+    float a = x[p * 2 * Ch + c], s = og_sigmoid(x[p * 2 * Ch + Ch + c]), gg = g[i];
+    gx[p * 2 * Ch + c] = gg * s;
+    gx[p * 2 * Ch + Ch + c] = gg * a * s * (1.f - s);
+  }
+}
+OG_API int og_glu_fwd(const float* x, long long P, int Ch, float* out, cudaStream_t stream) {
+  if (P * Ch == 0) return 0;
+  glu_fwd_kernel<<<eblocks(P * Ch), 256, 0, stream>>>(x, Ch, P * Ch, out);
+  OG_RETURN_LAST_ERROR();
+}
+OG_API int og_glu_bwd(const float* x, const float* g, long long P, int Ch, float* gx, cudaStream_t stream) {
+  if (P * Ch == 0) return 0;
+  glu_bwd_kernel<<<eblocks(P * Ch), 256, 0, stream>>>(x, g, Ch, P * Ch, gx);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// CA_NET reparametrisation (model.py:470-478):  c = eps * exp(0.5 * logvar) + mu
+// x rows hold [mu (D) | logvar (D)] (row stride xs); eps, c are (B, D) dense.
+// ---------------------------------------------------------------------------------------------
+__global__ void reparam_fwd_kernel(const float* __restrict__ x, int xs, const float* __restrict__ eps, int D,
+                                   long long total, float* __restrict__ c, int cs) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long b = i / D;
+    int k = (int)(i - b * D);
+    c[b * cs + k] = eps[i] * expf(0.5f * x[b * xs + D + k]) + x[b * xs + k];
+  }
+}
+__global__ void reparam_bwd_kernel(const float* __restrict__ x, int xs, const float* __restrict__ eps,
+                                   const float* __restrict__ gc, int gcs, int D, long long total,
+                                   float* __restrict__ gx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long b = i / D;
+    int k = (int)(i - b * D);
+    float g = gc[b * gcs + k];
+    gx[b * xs + k] += g;
+    gx[b * xs + D + k] += g * eps[i] * 0.5f * expf(0.5f * x[b * xs + D + k]);
+  }
+}
+OG_API int og_reparam_fwd(const float* x, int xs, const float* eps, int B, int D, float* c, int cs,
+                          cudaStream_t stream) {
+  reparam_fwd_kernel<<<eblocks((long long)B * D), 256, 0, stream>>>(x, xs, eps, D, (long long)B * D, c, cs);
+  OG_RETURN_LAST_ERROR();
+}
+// accumulates into gx (caller zero-fills or pre-loads it with the KL gradient)
+OG_API int og_reparam_bwd(const float* x, int xs, const float* eps, const float* gc, int gcs, int B, int D, float* gx,
+                          cudaStream_t stream) {
+  reparam_bwd_kernel<<<eblocks((long long)B * D), 256, 0, stream>>>(x, xs, eps, gc, gcs, D, (long long)B * D, gx);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// losses.  Each kernel adds  weight * mean(loss)  into *loss_accum (device scalar) and writes the
+// gradient of that weighted mean w.r.t. its input.
+// nn.BCELoss (miscc/losses.py:178-208, 378-393): log terms clamped at -100, backward
+// (p - t) / max(p (1 - p), 1e-12) like PyTorch.
+// ---------------------------------------------------------------------------------------------
+__global__ void bce_kernel(const float* __restrict__ p, long long n, float target, float weight, float* loss_accum,
+                           float* __restrict__ gp) {
+  float local = 0.f;
+  const float inv = 1.f / (float)n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = p[i];
+    float l1 = fmaxf(logf(v), -100.f), l0 = fmaxf(logf(1.f - v), -100.f);
+    local += -(target * l1 + (1.f - target) * l0);
+    if (gp) gp[i] = weight * inv * (v - target) / fmaxf(v * (1.f - v), 1e-12f);
+  }
+  local = warp_sum(local);
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) s += sh[i];
+    atomicAdd(loss_accum, weight * inv * s);
+  }
+}
+OG_API int og_bce(const float* p, long long n, float target, float weight, float* loss_accum, float* gp,
+                  cudaStream_t stream) {
+  if (n == 0) return 0;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 64) blocks = 64;
+  bce_kernel<<<blocks, 256, 0, stream>>>(p, n, target, weight, loss_accum, gp);
+  OG_RETURN_LAST_ERROR();
+}
+
+// KL_loss (miscc/losses.py:533-537): -0.5 * mean(1 + logvar - mu^2 - exp(logvar)); x rows = [mu | logvar]
+__global__ void kl_kernel(const float* __restrict__ x, int xs, int B, int D, float weight, float* loss_accum,
+                          float* __restrict__ gx) {
+  float local = 0.f;
+  const long long n = (long long)B * D;
+  const float inv = 1.f / (float)n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long b = i / D;
+    int k = (int)(i - b * D);
+    float mu = x[b * xs + k], lv = x[b * xs + D + k], e = expf(lv);
+    local += 1.f + lv - mu * mu - e;
+    if (gx) {
+      gx[b * xs + k] = weight * inv * mu;
+      gx[b * xs + D + k] = weight * inv * (-0.5f) * (1.f - e);
+    }
+  }
+  local = warp_sum(local);
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) s += sh[i];
+    atomicAdd(loss_accum, -0.5f * weight * inv * s);
+  }
+}
+OG_API int og_kl(const float* x, int xs, int B, int D, float weight, float* loss_accum, float* gx,
+                 cudaStream_t stream) {
+  kl_kernel<<<8, 256, 0, stream>>>(x, xs, B, D, weight, loss_accum, gx);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused Adam (+ gradient pre-scale for data-parallel averaging, + EMA of the generator weights)
+// torch.optim.Adam(lr, betas=(0.5, 0.999)) as used in trainer.py:197-224; EMA trainer.py:461-462.
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, float* __restrict__ avg, long long n, float lr, float b1,
+                                float b2, float eps, float bc1, float sqrt_bc2, float gscale, float decay) {
+  const float step_size = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gg = g[i] * gscale;
+    float mm = m[i] * b1 + (1.f - b1) * gg;
+    float vv = v[i] * b2 + (1.f - b2) * gg * gg;
+    m[i] = mm;
+    v[i] = vv;
+    float denom = sqrtf(vv) / sqrt_bc2 + eps;
+    float pp = p[i] - step_size * (mm / denom);
+    p[i] = pp;
+    if (avg) avg[i] = avg[i] * decay + (1.f - decay) * pp;
+  }
+}
+OG_API int og_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long long n, double lr, double b1,
+                       double b2, double eps, int step, float gscale, float decay, cudaStream_t stream) {
+  if (n == 0) return 0;
+  // bias corrections in double on the host, like torch.optim.Adam's python scalars
+  double bc1 = 1.0 - pow(b1, (double)step);
+  double sqrt_bc2 = sqrt(1.0 - pow(b2, (double)step));
+  adam_ema_kernel<<<eblocks(n), 256, 0, stream>>>(p, g, m, v, avg, n, (float)lr, (float)b1, (float)b2, (float)eps,
+                                                   (float)bc1, (float)sqrt_bc2, gscale, decay);
+  OG_RETURN_LAST_ERROR();
+}

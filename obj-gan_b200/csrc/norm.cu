@@ -1,0 +1,354 @@
+// InstanceNorm2d / BatchNorm{1,2}d (train mode) with fused activation, forward and backward, NHWC.
+//
+// Reference semantics (image_generation/model.py): nn.InstanceNorm2d defaults (no affine, eps 1e-5, biased
+// variance; model.py:70, 602, 1198) and nn.BatchNorm2d/1d in train mode (batch statistics, biased variance
+// for normalisation, running stats with momentum 0.1 and the unbiased variance; model.py:47, 497, 992,
+// 1011).  The activation that always follows is fused into the apply pass: GLU (model.py:19-27),
+// LeakyReLU(0.2) or nothing (+ optional residual add, model.py:76-81).
+//
+// All kernels are HBM-bandwidth bound: one read of the conv output for the statistics, one read + one
+// write for the apply.  Statistics are accumulated in fp64 (sum, sum of squares) so that the one-pass
+// variance does not lose digits; the finalised mean / rstd are fp32.
+//
+// Layout: contiguous NHWC, rows = pixels, C % 4 == 0.  "groups" = N for instance norm, 1 for batch norm;
+// each group covers P pixels (H*W, resp. N*H*W).
+#include "common.cuh"
+
+// grid: (ceil(C4/32), chunks, groups)   block: (32, 8)
+__global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ x, int C, long long P,
+                                                         int pix_per_block, double* __restrict__ stats) {
+  const int c4 = blockIdx.x * 32 + threadIdx.x;
+  const int C4 = C >> 2;
+  const long long g = blockIdx.z;
+  const long long p0 = (long long)blockIdx.y * pix_per_block;
+  const long long p1 = min(P, p0 + pix_per_block);
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (c4 < C4) {
+    const float* base = x + (g * P) * C + c4 * 4;
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+      float4 v = ldg4(base + p * C);
+      s[0] += v.x; q[0] += (double)v.x * v.x;
+      s[1] += v.y; q[1] += (double)v.y * v.y;
+      s[2] += v.z; q[2] += (double)v.z * v.z;
+      s[3] += v.w; q[3] += (double)v.w * v.w;
+    }
+  }
+  __shared__ double sh[8][32][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sh[threadIdx.y][threadIdx.x][i] = s[i];
+    sh[threadIdx.y][threadIdx.x][4 + i] = q[i];
+  }
+  __syncthreads();
+  // 256 threads reduce 32 x 8 values over the 8 pixel lanes
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  const int cx = t >> 3, k = t & 7;
+  double acc = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc += sh[j][cx][k];
+  const int cc4 = blockIdx.x * 32 + cx;
+  if (cc4 < C4) {
+    int ch = cc4 * 4 + (k & 3);
+    atomicAdd(&stats[(g * C + ch) * 2 + (k >> 2)], acc);
+  }
+}
+
+// mean / rstd from (sum, sumsq); optional BatchNorm running-stat update.
+__global__ void norm_finalize_kernel(const double* __restrict__ stats, int groups, int C, double count, float eps,
+                                     float* __restrict__ mean, float* __restrict__ rstd, float* running_mean,
+                                     float* running_var, float momentum, int real_c,
+                                     long long* num_batches_tracked) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * C) return;
+  if (i == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  double m = stats[i * 2] / count;
+  double var = stats[i * 2 + 1] / count - m * m;
+  if (var < 0) var = 0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean && groups == 1 && i < real_c) {
+    double unbiased = count > 1 ? var * count / (count - 1.0) : var;
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * (float)m;
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unbiased;
+  }
+}
+
+// forward apply.  y: conv output [G*P][Cy];  out: [G*P][Co] where Co = Cy (none / lrelu) or Cy/2 (GLU).
+// gamma/beta (BatchNorm affine) may be null (InstanceNorm).  res (same shape as out) is added when non-null.
+template <int ACT>
+__global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict__ y, int Cy, long long P,
+                                                         long long total_pix, const float* __restrict__ mean,
+                                                         const float* __restrict__ rstd,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta,
+                                                         const float* __restrict__ res, float slope,
+                                                         float* __restrict__ out) {
+  const int Co = (ACT == OG_NA_GLU) ? Cy / 2 : Cy;
+  const int Co4 = Co >> 2;
+  const long long total = total_pix * Co4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / Co4;
+    int c = (int)(i - p * Co4) * 4;
+    long long g = p / P;
+    const float* mrow = mean + g * Cy;
+    const float* rrow = rstd + g * Cy;
+    float4 v = ldg4(y + p * Cy + c);
+    float4 m = ldg4(mrow + c), r = ldg4(rrow + c);
+    float4 ga = gamma ? ldg4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 be = beta ? ldg4(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a;
+    a.x = (v.x - m.x) * r.x * ga.x + be.x;
+    a.y = (v.y - m.y) * r.y * ga.y + be.y;
+    a.z = (v.z - m.z) * r.z * ga.z + be.z;
+    a.w = (v.w - m.w) * r.w * ga.w + be.w;
+    float4 o;
+    if (ACT == OG_NA_GLU) {
+      float4 v2 = ldg4(y + p * Cy + Co + c);
+      float4 m2 = ldg4(mrow + Co + c), r2 = ldg4(rrow + Co + c);
+      float4 ga2 = gamma ? ldg4(gamma + Co + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+      float4 be2 = beta ? ldg4(beta + Co + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      o.x = a.x * og_sigmoid((v2.x - m2.x) * r2.x * ga2.x + be2.x);
+      o.y = a.y * og_sigmoid((v2.y - m2.y) * r2.y * ga2.y + be2.y);
+      o.z = a.z * og_sigmoid((v2.z - m2.z) * r2.z * ga2.z + be2.z);
+      o.w = a.w * og_sigmoid((v2.w - m2.w) * r2.w * ga2.w + be2.w);
+    } else if (ACT == OG_NA_LRELU) {
+      o.x = a.x > 0.f ? a.x : a.x * slope;
+      o.y = a.y > 0.f ? a.y : a.y * slope;
+      o.z = a.z > 0.f ? a.z : a.z * slope;
+      o.w = a.w > 0.f ? a.w : a.w * slope;
+    } else {
+      o = a;
+    }
+    if (res) {
+      float4 rr = ldg4(res + p * Co + c);
+      o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+    }
+    st4(out + p * Co + c, o);
+  }
+}
+
+// gradient of the fused activation w.r.t. the normalised (+affine) values n, for 4 channels.
+// Returns dn for the "a" half (and dn2 for the gate half when GLU).
+template <int ACT>
+__device__ __forceinline__ void act_grad4(const float* __restrict__ y, const float* __restrict__ g, long long p,
+                                          int Cy, int c, const float* mrow, const float* rrow,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          float slope, float4& xh, float4& dn, float4& xh2, float4& dn2) {
+  const int Co = (ACT == OG_NA_GLU) ? Cy / 2 : Cy;
+  float4 v = ldg4(y + p * Cy + c);
+  float4 m = ldg4(mrow + c), r = ldg4(rrow + c);
+  float4 go = ldg4(g + p * Co + c);
+  xh.x = (v.x - m.x) * r.x; xh.y = (v.y - m.y) * r.y; xh.z = (v.z - m.z) * r.z; xh.w = (v.w - m.w) * r.w;
+  float4 ga = gamma ? ldg4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 be = beta ? ldg4(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 n;
+  n.x = xh.x * ga.x + be.x; n.y = xh.y * ga.y + be.y; n.z = xh.z * ga.z + be.z; n.w = xh.w * ga.w + be.w;
+  if (ACT == OG_NA_GLU) {
+    float4 v2 = ldg4(y + p * Cy + Co + c);
+    float4 m2 = ldg4(mrow + Co + c), r2 = ldg4(rrow + Co + c);
+    xh2.x = (v2.x - m2.x) * r2.x; xh2.y = (v2.y - m2.y) * r2.y; xh2.z = (v2.z - m2.z) * r2.z; xh2.w = (v2.w - m2.w) * r2.w;
+    float4 ga2 = gamma ? ldg4(gamma + Co + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 be2 = beta ? ldg4(beta + Co + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float sx = og_sigmoid(xh2.x * ga2.x + be2.x), sy = og_sigmoid(xh2.y * ga2.y + be2.y);
+    float sz = og_sigmoid(xh2.z * ga2.z + be2.z), sw = og_sigmoid(xh2.w * ga2.w + be2.w);
+    dn.x = go.x * sx; dn.y = go.y * sy; dn.z = go.z * sz; dn.w = go.w * sw;
+    dn2.x = go.x * n.x * sx * (1.f - sx); dn2.y = go.y * n.y * sy * (1.f - sy);
+    dn2.z = go.z * n.z * sz * (1.f - sz); dn2.w = go.w * n.w * sw * (1.f - sw);
+  } else if (ACT == OG_NA_LRELU) {
+    dn.x = n.x > 0.f ? go.x : go.x * slope; dn.y = n.y > 0.f ? go.y : go.y * slope;
+    dn.z = n.z > 0.f ? go.z : go.z * slope; dn.w = n.w > 0.f ? go.w : go.w * slope;
+  } else {
+    dn = go;
+  }
+}
+
+// backward reduce: per (group, channel of y):  bstats[.,0] = sum dn,  bstats[.,1] = sum dn * xhat   (fp64)
+// grid: (ceil(Co4/32), chunks, groups)  block (32, 8)
+template <int ACT>
+__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __restrict__ y,
+                                                              const float* __restrict__ g, int Cy, long long P,
+                                                              int pix_per_block, const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float slope,
+                                                              double* __restrict__ bstats) {
+  const int Co = (ACT == OG_NA_GLU) ? Cy / 2 : Cy;
+  const int Co4 = Co >> 2;
+  const int c4 = blockIdx.x * 32 + threadIdx.x;
+  const long long grp = blockIdx.z;
+  const long long p0 = (long long)blockIdx.y * pix_per_block;
+  const long long p1 = min(P, p0 + pix_per_block);
+  constexpr int NV = (ACT == OG_NA_GLU) ? 16 : 8;
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0;
+  if (c4 < Co4) {
+    const float* mrow = mean + grp * Cy;
+    const float* rrow = rstd + grp * Cy;
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+      float4 xh, dn, xh2, dn2;
+      act_grad4<ACT>(y, g, grp * P + p, Cy, c4 * 4, mrow, rrow, gamma, beta, slope, xh, dn, xh2, dn2);
+      acc[0] += dn.x; acc[1] += dn.y; acc[2] += dn.z; acc[3] += dn.w;
+      acc[4] += (double)dn.x * xh.x; acc[5] += (double)dn.y * xh.y;
+      acc[6] += (double)dn.z * xh.z; acc[7] += (double)dn.w * xh.w;
+      if (ACT == OG_NA_GLU) {
+        acc[NV - 8] += dn2.x; acc[NV - 7] += dn2.y; acc[NV - 6] += dn2.z; acc[NV - 5] += dn2.w;
+        acc[NV - 4] += (double)dn2.x * xh2.x; acc[NV - 3] += (double)dn2.y * xh2.y;
+        acc[NV - 2] += (double)dn2.z * xh2.z; acc[NV - 1] += (double)dn2.w * xh2.w;
+      }
+    }
+  }
+  __shared__ double sh[8][32][NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sh[threadIdx.y][threadIdx.x][i] = acc[i];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  for (int item = t; item < 32 * NV; item += 256) {
+    int cx = item / NV, k = item % NV;
+    double a = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += sh[j][cx][k];
+    int cc4 = blockIdx.x * 32 + cx;
+    if (cc4 < Co4) {
+      int half = k >> 3;            // 0: "a" half, 1: gate half (GLU only)
+      int kk = k & 7;
+      int ch = half * Co + cc4 * 4 + (kk & 3);
+      atomicAdd(&bstats[(grp * Cy + ch) * 2 + (kk >> 2)], a);
+    }
+  }
+}
+
+// backward apply: dy = rstd * gamma * (dn - S1/cnt - xhat * S2/cnt)
+template <int ACT>
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __restrict__ y,
+                                                             const float* __restrict__ g, int Cy, long long P,
+                                                             long long total_pix, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float slope,
+                                                             const double* __restrict__ bstats, double inv_count,
+                                                             float* __restrict__ dy) {
+  const int Co = (ACT == OG_NA_GLU) ? Cy / 2 : Cy;
+  const int Co4 = Co >> 2;
+  const long long total = total_pix * Co4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / Co4;
+    int c = (int)(i - p * Co4) * 4;
+    long long grp = p / P;
+    const float* mrow = mean + grp * Cy;
+    const float* rrow = rstd + grp * Cy;
+    float4 xh, dn, xh2, dn2;
+    act_grad4<ACT>(y, g, p, Cy, c, mrow, rrow, gamma, beta, slope, xh, dn, xh2, dn2);
+    {
+      const double* bs = bstats + (grp * Cy + c) * 2;
+      float4 r = ldg4(rrow + c);
+      float4 ga = gamma ? ldg4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+      float4 o;
+      o.x = r.x * ga.x * (dn.x - (float)(bs[0] * inv_count) - xh.x * (float)(bs[1] * inv_count));
+      o.y = r.y * ga.y * (dn.y - (float)(bs[2] * inv_count) - xh.y * (float)(bs[3] * inv_count));
+      o.z = r.z * ga.z * (dn.z - (float)(bs[4] * inv_count) - xh.z * (float)(bs[5] * inv_count));
+      o.w = r.w * ga.w * (dn.w - (float)(bs[6] * inv_count) - xh.w * (float)(bs[7] * inv_count));
+      st4(dy + p * Cy + c, o);
+    }
+    if (ACT == OG_NA_GLU) {
+      const double* bs = bstats + (grp * Cy + Co + c) * 2;
+      float4 r = ldg4(rrow + Co + c);
+      float4 ga = gamma ? ldg4(gamma + Co + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+      float4 o;
+      o.x = r.x * ga.x * (dn2.x - (float)(bs[0] * inv_count) - xh2.x * (float)(bs[1] * inv_count));
+      o.y = r.y * ga.y * (dn2.y - (float)(bs[2] * inv_count) - xh2.y * (float)(bs[3] * inv_count));
+      o.z = r.z * ga.z * (dn2.z - (float)(bs[4] * inv_count) - xh2.z * (float)(bs[5] * inv_count));
+      o.w = r.w * ga.w * (dn2.w - (float)(bs[6] * inv_count) - xh2.w * (float)(bs[7] * inv_count));
+      st4(dy + p * Cy + Co + c, o);
+    }
+  }
+}
+
+// dgamma = S2, dbeta = S1 for batch norm (groups == 1): copy fp64 sums to fp32 parameter-gradient vectors
+__global__ void norm_param_grad_kernel(const double* __restrict__ bstats, int C, float* dgamma, float* dbeta,
+                                       int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  float db = (float)bstats[i * 2], dg = (float)bstats[i * 2 + 1];
+  dgamma[i] = accumulate ? dgamma[i] + dg : dg;
+  dbeta[i] = accumulate ? dbeta[i] + db : db;
+}
+
+static int elem_blocks(long long total) {
+  long long b = (total + 255) / 256;
+  long long cap = 148LL * 32;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+static int pix_chunk(long long P, int cgroups, int groups) {
+  // aim for >= ~4 blocks per SM overall, at least 64 pixels per block
+  long long want = 148LL * 8;
+  long long chunks = want / ((long long)cgroups * groups) + 1;
+  long long ppb = (P + chunks - 1) / chunks;
+  if (ppb < 64) ppb = 64;
+  return (int)ppb;
+}
+
+// stats: fp64 [groups][C][2] (zeroed here); mean/rstd: fp32 [groups][C]
+OG_API int og_norm_stats(const float* x, int groups, long long P, int C, float eps, double* stats, float* mean,
+                         float* rstd, float* running_mean, float* running_var, float momentum, int real_c,
+                         long long* num_batches_tracked, cudaStream_t stream) {
+  if (C % 4) return (int)cudaErrorInvalidValue;
+  OG_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * C, stream));
+  int cg = og_cdiv(C / 4, 32);
+  int ppb = pix_chunk(P, cg, groups);
+  dim3 grid(cg, og_cdiv(P, ppb), groups), block(32, 8);
+  norm_stats_kernel<<<grid, block, 0, stream>>>(x, C, P, ppb, stats);
+  norm_finalize_kernel<<<og_cdiv((long long)groups * C, 256), 256, 0, stream>>>(stats, groups, C, (double)P, eps, mean, rstd,
+                                                                     running_mean, running_var, momentum, real_c,
+                                                                     num_batches_tracked);
+  OG_RETURN_LAST_ERROR();
+}
+
+OG_API int og_norm_apply(const float* y, int groups, long long P, int Cy, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, const float* res, int act, float slope, float* out,
+                         cudaStream_t stream) {
+  long long tp = (long long)groups * P;
+  int Co = act == OG_NA_GLU ? Cy / 2 : Cy;
+  if (Cy % 4 || Co % 4) return (int)cudaErrorInvalidValue;
+  int blocks = elem_blocks(tp * (Co / 4));
+  if (act == OG_NA_GLU)
+    norm_apply_kernel<OG_NA_GLU><<<blocks, 256, 0, stream>>>(y, Cy, P, tp, mean, rstd, gamma, beta, res, slope, out);
+  else if (act == OG_NA_LRELU)
+    norm_apply_kernel<OG_NA_LRELU><<<blocks, 256, 0, stream>>>(y, Cy, P, tp, mean, rstd, gamma, beta, res, slope, out);
+  else
+    norm_apply_kernel<OG_NA_NONE><<<blocks, 256, 0, stream>>>(y, Cy, P, tp, mean, rstd, gamma, beta, res, slope, out);
+  OG_RETURN_LAST_ERROR();
+}
+
+// g: gradient w.r.t. the fused output ([groups*P][Co]); dy: gradient w.r.t. the conv output y.
+// bstats: fp64 scratch [groups][Cy][2].  dgamma/dbeta optional (batch norm).
+OG_API int og_norm_backward(const float* y, const float* g, int groups, long long P, int Cy, const float* mean,
+                            const float* rstd, const float* gamma, const float* beta, int act, float slope,
+                            double* bstats, float* dy, float* dgamma, float* dbeta, int accumulate_param_grads,
+                            cudaStream_t stream) {
+  long long tp = (long long)groups * P;
+  int Co = act == OG_NA_GLU ? Cy / 2 : Cy;
+  if (Cy % 4 || Co % 4) return (int)cudaErrorInvalidValue;
+  OG_CHECK(cudaMemsetAsync(bstats, 0, sizeof(double) * 2 * groups * Cy, stream));
+  int cg = og_cdiv(Co / 4, 32);
+  int ppb = pix_chunk(P, cg, groups);
+  dim3 grid(cg, og_cdiv(P, ppb), groups), block(32, 8);
+  int blocks = elem_blocks(tp * (Co / 4));
+  double inv = 1.0 / (double)P;
+#define OG_LAUNCH_BWD(A)                                                                                           \
+  norm_bwd_reduce_kernel<A><<<grid, block, 0, stream>>>(y, g, Cy, P, ppb, mean, rstd, gamma, beta, slope, bstats); \
+  norm_bwd_apply_kernel<A><<<blocks, 256, 0, stream>>>(y, g, Cy, P, tp, mean, rstd, gamma, beta, slope, bstats, inv, dy);
+  if (act == OG_NA_GLU) {
+    OG_LAUNCH_BWD(OG_NA_GLU)
+  } else if (act == OG_NA_LRELU) {
+    OG_LAUNCH_BWD(OG_NA_LRELU)
+  } else {
+    OG_LAUNCH_BWD(OG_NA_NONE)
+  }
+#undef OG_LAUNCH_BWD
+  if (dgamma && groups == 1)
+    norm_param_grad_kernel<<<og_cdiv(Cy, 256), 256, 0, stream>>>(bstats, Cy, dgamma, dbeta, accumulate_param_grads);
+  OG_RETURN_LAST_ERROR();
+}

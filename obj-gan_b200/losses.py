@@ -1,0 +1,64 @@
+"""Loss functions of the hot path with the reference's names and argument order
+(reference: image_generation/miscc/losses.py:163-211 ``patD_loss``, 364-399 patch-D part of ``G_loss``,
+533-537 ``KL_loss``).  BCE / KL values and their gradients come from the fused kernels ``og_bce`` / ``og_kl``.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .config import cfg
+
+
+def _heads(net):
+    net = net.module if hasattr(net, "module") else net
+    return net.COND_DNET, net.UNCOND_DNET
+
+
+def patD_loss(netPatD, real_imgs, fake_imgs, conditions):
+    """ref: miscc/losses.py:163-211 -- two body forwards (separate BatchNorm statistics), COND head on
+    (real, fake, wrong = real[:B-1] x cond[1:]), UNCOND head on (real, fake)."""
+    real_features = netPatD(real_imgs)
+    fake_features = netPatD(fake_imgs.detach())
+    cond, uncond = _heads(netPatD)
+    ul, tl = cfg.TRAIN.SMOOTH.UNCOND_LAMBDA, cfg.TRAIN.SMOOTH.TXT_LAMBDA
+    batch_size = real_features.size(0)
+    cond_real = cond(real_features, conditions)
+    cond_fake = cond(fake_features, conditions)
+    cond_wrong = cond(real_features[:(batch_size - 1)], conditions[1:batch_size])
+    if uncond is not None:
+        real_logits = uncond(real_features)
+        fake_logits = uncond(fake_features)
+        # errD = (u_real*UL + c_real*TL)/2 + (u_fake*UL + (c_fake + c_wrong)*TL)/3, folded into the weights
+        return (ops.bce(real_logits, 1.0, ul / 2.0) + ops.bce(cond_real, 1.0, tl / 2.0)
+                + ops.bce(fake_logits, 0.0, ul / 3.0) + ops.bce(cond_fake, 0.0, tl / 3.0)
+                + ops.bce(cond_wrong, 0.0, tl / 3.0))
+    return ops.bce(cond_real, 1.0, tl) + ops.bce(cond_fake, 0.0, tl / 2.0) + ops.bce(cond_wrong, 0.0, tl / 2.0)
+
+
+def G_loss_pat(netsPatD, fake_imgs, sent_emb):
+    """Patch-discriminator terms of ``G_loss`` (ref: miscc/losses.py:372-399)."""
+    ul, tl = cfg.TRAIN.SMOOTH.UNCOND_LAMBDA, cfg.TRAIN.SMOOTH.TXT_LAMBDA
+    total, per = None, []
+    for i in range(len(netsPatD)):
+        features = netsPatD[i](fake_imgs[i])
+        cond, uncond = _heads(netsPatD[i])
+        cond_err = ops.bce(cond(features, sent_emb), 1.0, tl if uncond is not None else 1.0)
+        loss = cond_err
+        if uncond is not None:
+            loss = loss + ops.bce(uncond(features), 1.0, ul)
+        per.append(loss)
+        total = loss if total is None else total + loss
+    return total, per
+
+
+def KL_loss(mu, logvar):
+    """ref: miscc/losses.py:533-537.  ``mu`` / ``logvar`` are the column views G_NET returns; the fused
+    kernel runs on their shared row buffer."""
+    base = mu._base if mu._base is not None else None
+    if base is not None and logvar._base is base and base.dim() == 2:
+        return ops.kl_rows(base, mu.shape[1], 1.0)
+    d = mu.shape[1]
+    rows = torch.zeros(mu.shape[0], ops.cpad(2 * d), device=mu.device)
+    rows = torch.cat((mu, logvar, rows[:, 2 * d:]), 1)
+    return ops.kl_rows(rows, d, 1.0)

@@ -1,0 +1,681 @@
+"""Autograd-aware Python operators over the C ABI of libobjgan_b200.so.
+
+PyTorch is plumbing here: device memory (``torch.empty``), the autograd tape and streams.  Every
+arithmetic step is a kernel of this repo's library, reached through ``lib.call`` (ctypes); there is no
+torch / cuDNN / cuBLAS compute path and no CPU fallback -- CPU tensors raise.
+
+Internal activation layout: NHWC fp32, shape (N, H, W, Cp) with Cp = channels rounded up to 8 and the
+pad lanes kept at exactly zero.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lib as _lib
+from .lib import (ACT_LRELU, ACT_NONE, ACT_SIGMOID, ACT_TANH, NA_GLU, NA_LRELU, NA_NONE, PAD_REFLECT, PAD_ZERO,
+                  TRANSPOSED, UPSAMPLE2X)
+
+LRELU_SLOPE = 0.2
+NORM_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def cpad(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda and not _lib.DRY_RUN:
+            raise RuntimeError("objgan_b200 kernels need CUDA tensors (no CPU fallback)")
+        if t.dtype not in (torch.float32, torch.uint8, torch.float64, torch.int64):
+            raise RuntimeError(f"unsupported dtype {t.dtype}")
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _call(name, *args):
+    if _lib.DRY_RUN:  # host-logic tracing only (tests): kernels are NOT executed, outputs stay uninitialised
+        _lib.get().launches += 1
+        return
+    _lib.get().call(name, *args, _lib.stream())
+
+
+# weights change only through the optimiser / load_state_dict; both bump this epoch so cached packed copies
+# are rebuilt.  In-place torch ops on a Parameter are caught through Tensor._version.
+_param_epoch = [0]
+
+
+def bump_param_epoch():
+    _param_epoch[0] += 1
+
+
+class PackedWeights:
+    """Cache of kernel-native copies (fprop and dgrad operand) of one OIHW parameter."""
+
+    def __init__(self):
+        self.key = None
+        self.f = None
+        self.t = None
+
+    def get(self, w, cip, kp, split, splitp, need_t):
+        key = (w.data_ptr(), w._version, _param_epoch[0], cip, kp, split)
+        if key != self.key:
+            self.key, self.f, self.t = key, None, None
+        co, ci, kh, kw = w.shape
+        if self.f is None:
+            self.f = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float32)
+            _call("og_pack_weights", _p(w), co, ci, kh, kw, cip, kp, split, splitp, 0, _p(self.f), 0)
+        if need_t and self.t is None:
+            self.t = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float32)
+            _call("og_pack_weights", _p(w), co, ci, kh, kw, cip, kp, split, splitp, 1, _p(self.t), 0)
+        return self.f, self.t
+
+
+def _out_hw(h, w, kh, kw, stride, pad, mode):
+    if mode == UPSAMPLE2X:
+        return 2 * h, 2 * w
+    if mode == PAD_REFLECT:
+        return (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    return (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+
+
+def _conv_raw(x, wp, n, h, w, c, oh, ow, k, kh, kw, stride, pad, mode, bias, act, splitk=True):
+    y = torch.empty((n, oh, ow, k), device=x.device, dtype=torch.float32)
+    _call("og_conv2d_simt", _p(x), n, h, w, c, h * w * c, w * c, c, _p(wp), _p(y), oh, ow, k, oh * ow * k, ow * k, k,
+          kh, kw, stride, pad, mode, _p(bias), act, LRELU_SLOPE, 1 if splitk else 0)
+    return y
+
+
+class _Conv2d(torch.autograd.Function):
+    """y = act(conv(x, W) + b) on NHWC tensors; W, b are the reference's OIHW / (Co,) parameters."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cache, stride, pad, mode, act, split):
+        _chk(x, weight, bias)
+        x = x.contiguous()
+        n, h, w, c = x.shape
+        co, ci, kh, kw = weight.shape
+        assert c == cpad(ci), (c, ci)
+        if split:
+            assert co == 2 * split
+            splitp = cpad(split)
+            kp = 2 * splitp
+        else:
+            splitp, kp = 0, cpad(co)
+        need_t = ctx.needs_input_grad[0]
+        wf, _ = cache.get(weight, c, kp, split, splitp, False)
+        oh, ow = _out_hw(h, w, kh, kw, stride, pad, mode)
+        bias_p = None
+        if bias is not None:
+            if kp == co:
+                bias_p = bias.detach()
+            else:
+                assert not split
+                bias_p = torch.zeros(kp, device=x.device, dtype=torch.float32)
+                bias_p[:co] = bias.detach()
+        y = _conv_raw(x, wf, n, h, w, c, oh, ow, kp, kh, kw, stride, pad, mode, bias_p, act,
+                      splitk=(bias is None and act == ACT_NONE))
+        ctx.cfg = (stride, pad, mode, act, split, splitp, kp, need_t)
+        ctx.cache = cache
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, y = ctx.saved_tensors
+        stride, pad, mode, act, split, splitp, kp, _ = ctx.cfg
+        n, h, w, c = x.shape
+        co, ci, kh, kw = weight.shape
+        g = g.contiguous()
+        oh, ow = g.shape[1], g.shape[2]
+        if act != ACT_NONE:
+            gp = torch.empty_like(g)
+            _call("og_act_backward", _p(y), _p(g), g.numel(), act, LRELU_SLOPE, _p(gp))
+            g = gp
+        gx = gw = gb = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            scratch = torch.empty(kp, device=g.device, dtype=torch.float64)
+            gb = torch.empty(co, device=g.device, dtype=torch.float32)
+            _call("og_channel_sum", _p(g), n * oh * ow, kp, _p(scratch), _p(gb), co, 0)
+        if ctx.needs_input_grad[0]:
+            _, wt = ctx.cache.get(weight, c, kp, split, splitp, True)
+            if mode == PAD_ZERO:
+                gx = _conv_raw(g, wt, n, oh, ow, kp, h, w, c, kh, kw, stride, pad, TRANSPOSED, None, ACT_NONE)
+            elif mode == PAD_REFLECT:
+                assert stride == 1 and pad == 1
+                gpad = _conv_raw(g, wt, n, oh, ow, kp, h + 2, w + 2, c, kh, kw, 1, 0, TRANSPOSED, None, ACT_NONE)
+                gx = torch.empty_like(x)
+                _call("og_reflect_pad_bwd", _p(gpad), n, h, w, c, _p(gx))
+            else:  # UPSAMPLE2X
+                gu = _conv_raw(g, wt, n, oh, ow, kp, 2 * h, 2 * w, c, kh, kw, 1, pad, TRANSPOSED, None, ACT_NONE)
+                gx = torch.empty_like(x)
+                _call("og_upsample2x_bwd", _p(gu), n, h, w, c, _p(gx))
+        if ctx.needs_input_grad[1]:
+            dwp = torch.empty(kh * kw * c * kp, device=g.device, dtype=torch.float32)
+            _call("og_conv2d_wgrad_simt", _p(x), n, h, w, c, h * w * c, w * c, c, _p(g), oh, ow, kp, oh * ow * kp,
+                  ow * kp, kp, _p(dwp), kh, kw, stride, pad, mode)
+            gw = torch.empty_like(weight)
+            _call("og_unpack_wgrad", _p(dwp), co, ci, kh, kw, c, kp, split, splitp, _p(gw), 0)
+        return gx, gw, gb, None, None, None, None, None, None
+
+
+def conv2d(x, weight, bias, cache, *, stride=1, pad=1, mode=PAD_ZERO, act=ACT_NONE, split=0):
+    return _Conv2d.apply(x, weight, bias, cache, stride, pad, mode, act, split)
+
+
+# --------------------------------------------------------------------------------------------------
+class _NormAct(torch.autograd.Function):
+    """InstanceNorm2d (groups = N) or train-mode BatchNorm (groups = 1) + fused activation (+ residual)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, res, bn_buffers, instance, act):
+        _chk(y, gamma, beta, res)
+        y = y.contiguous()
+        n, h, w, cy = y.shape
+        groups = n if instance else 1
+        P = h * w if instance else n * h * w
+        dev = y.device
+        stats = torch.empty(groups * cy * 2, device=dev, dtype=torch.float64)
+        mean = torch.empty(groups * cy, device=dev, dtype=torch.float32)
+        rstd = torch.empty(groups * cy, device=dev, dtype=torch.float32)
+        rm = rv = nbt = None
+        if bn_buffers is not None:
+            rm, rv, nbt = bn_buffers
+            assert gamma.numel() == cy, "BatchNorm layers of this model never need channel padding"
+        _call("og_norm_stats", _p(y), groups, P, cy, NORM_EPS, _p(stats), _p(mean), _p(rstd), _p(rm), _p(rv),
+              BN_MOMENTUM, cy, _p(nbt))
+        co = cy // 2 if act == NA_GLU else cy
+        out = torch.empty((n, h, w, co), device=dev, dtype=torch.float32)
+        if res is not None:
+            res = res.contiguous()
+            assert res.shape == out.shape
+        _call("og_norm_apply", _p(y), groups, P, cy, _p(mean), _p(rstd), _p(gamma), _p(beta), _p(res), act,
+              LRELU_SLOPE, _p(out))
+        ctx.cfg = (groups, P, cy, act, res is not None)
+        ctx.save_for_backward(y, mean, rstd, gamma, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, mean, rstd, gamma, beta = ctx.saved_tensors
+        groups, P, cy, act, has_res = ctx.cfg
+        g = g.contiguous()
+        bstats = torch.empty(groups * cy * 2, device=g.device, dtype=torch.float64)
+        dy = torch.empty_like(y)
+        dgamma = dbeta = None
+        if gamma is not None:
+            dgamma = torch.empty_like(gamma)
+            dbeta = torch.empty_like(beta)
+        _call("og_norm_backward", _p(y), _p(g), groups, P, cy, _p(mean), _p(rstd), _p(gamma), _p(beta), act,
+              LRELU_SLOPE, _p(bstats), _p(dy), _p(dgamma), _p(dbeta), 0)
+        return dy, dgamma, dbeta, (g if has_res else None), None, None, None
+
+
+def instance_norm_act(y, act, res=None):
+    return _NormAct.apply(y, None, None, res, None, True, act)
+
+
+def batch_norm_act(y, gamma, beta, buffers, act):
+    return _NormAct.apply(y, gamma, beta, None, buffers, False, act)
+
+
+# --------------------------------------------------------------------------------------------------
+class _ToNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cp):
+        _chk(x)
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        y = torch.empty((n, h, w, cp), device=x.device, dtype=torch.float32)
+        _call("og_nchw_to_nhwc", _p(x), n, c, h, w, cp, _p(y))
+        ctx.c = c
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        n, h, w, cp = g.shape
+        gx = torch.empty((n, ctx.c, h, w), device=g.device, dtype=torch.float32)
+        _call("og_nhwc_to_nchw", _p(g), n, ctx.c, h, w, cp, _p(gx))
+        return gx, None
+
+
+class _ToNCHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, c):
+        _chk(y)
+        y = y.contiguous()
+        n, h, w, cp = y.shape
+        x = torch.empty((n, c, h, w), device=y.device, dtype=torch.float32)
+        _call("og_nhwc_to_nchw", _p(y), n, c, h, w, cp, _p(x))
+        ctx.cp = cp
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        n, c, h, w = g.shape
+        gy = torch.empty((n, h, w, ctx.cp), device=g.device, dtype=torch.float32)
+        _call("og_nchw_to_nhwc", _p(g), n, c, h, w, ctx.cp, _p(gy))
+        return gy, None
+
+
+def to_nhwc(x, cp=None):
+    return _ToNHWC.apply(x, cpad(x.shape[1]) if cp is None else cp)
+
+
+def to_nchw(y, c):
+    return _ToNCHW.apply(y, c)
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        _chk(a, b)
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a)
+        _call("og_add", _p(a), _p(b), _p(out), a.numel())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+class _CatChannels(torch.autograd.Function):
+    """torch.cat along channels for NHWC tensors with padded lanes: copies the first reals[i] channels of
+    each input back to back and zero-fills the tail up to cpad(sum(reals))."""
+
+    @staticmethod
+    def forward(ctx, reals, *xs):
+        _chk(*xs)
+        xs = [x.contiguous() for x in xs]
+        n, h, w, _ = xs[0].shape
+        tot = sum(reals)
+        cp = cpad(tot)
+        out = torch.empty((n, h, w, cp), device=xs[0].device, dtype=torch.float32)
+        if cp != tot:
+            out.zero_()
+        off = 0
+        P = n * h * w
+        for x, r in zip(xs, reals):
+            _call("og_copy_channels", _p(x), x.shape[3], 0, _p(out), cp, off, r, P, 0)
+            off += r
+        ctx.reals = reals
+        ctx.cps = [x.shape[3] for x in xs]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        n, h, w, cp = g.shape
+        P = n * h * w
+        outs, off = [], 0
+        for i, (r, c) in enumerate(zip(ctx.reals, ctx.cps)):
+            if ctx.needs_input_grad[1 + i]:
+                gi = torch.empty((n, h, w, c), device=g.device, dtype=torch.float32)
+                if c != r:
+                    gi.zero_()
+                _call("og_copy_channels", _p(g), cp, off, _p(gi), c, 0, r, P, 0)
+                outs.append(gi)
+            else:
+                outs.append(None)
+            off += r
+        return (None, *outs)
+
+
+def cat_channels(xs, reals):
+    return _CatChannels.apply(tuple(reals), *xs)
+
+
+class _BroadcastCat(torch.autograd.Function):
+    """D_GET_LOGITS conditioning: cat(h, c_code broadcast over the grid) along channels (no grad to c_code,
+    which is the detached sentence embedding in every caller: miscc/losses.py:169-190, 375-377)."""
+
+    @staticmethod
+    def forward(ctx, h, c_code):
+        _chk(h, c_code)
+        h, c_code = h.contiguous(), c_code.contiguous()
+        n, hh, ww, ch = h.shape
+        cc = c_code.shape[1]
+        cp = cpad(ch + cc)
+        out = torch.empty((n, hh, ww, cp), device=h.device, dtype=torch.float32)
+        if cp != ch + cc:
+            out.zero_()
+        P = n * hh * ww
+        _call("og_copy_channels", _p(h), ch, 0, _p(out), cp, 0, ch, P, 0)
+        _call("og_broadcast_channels", _p(c_code), n, cc, _p(out), cp, ch, hh * ww)
+        ctx.ch = ch
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        n, hh, ww, cp = g.shape
+        gh = torch.empty((n, hh, ww, ctx.ch), device=g.device, dtype=torch.float32)
+        _call("og_copy_channels", _p(g), cp, 0, _p(gh), ctx.ch, 0, ctx.ch, n * hh * ww, 0)
+        return gh, None
+
+
+def broadcast_cat(h, c_code):
+    return _BroadcastCat.apply(h, c_code)
+
+
+class _GLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _chk(x)
+        x = x.contiguous()
+        ch = x.shape[-1] // 2
+        P = x.numel() // (2 * ch)
+        out = torch.empty((*x.shape[:-1], ch), device=x.device, dtype=torch.float32)
+        _call("og_glu_fwd", _p(x), P, ch, _p(out))
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        ch = x.shape[-1] // 2
+        gx = torch.empty_like(x)
+        _call("og_glu_bwd", _p(x), _p(g.contiguous()), x.numel() // (2 * ch), ch, _p(gx))
+        return gx
+
+
+def glu(x):
+    return _GLU.apply(x)
+
+
+class _Reparam(torch.autograd.Function):
+    """c = eps * exp(0.5 * logvar) + mu with x rows = [mu (D) | logvar (D) | pad]; c rows padded to cpad(D)."""
+
+    @staticmethod
+    def forward(ctx, x, eps, d):
+        _chk(x, eps)
+        x, eps = x.contiguous(), eps.contiguous()
+        b = x.shape[0]
+        cs = cpad(d)
+        c = torch.zeros((b, cs), device=x.device, dtype=torch.float32)
+        _call("og_reparam_fwd", _p(x), x.shape[1], _p(eps), b, d, _p(c), cs)
+        ctx.d = d
+        ctx.save_for_backward(x, eps)
+        return c
+
+    @staticmethod
+    def backward(ctx, gc):
+        x, eps = ctx.saved_tensors
+        gc = gc.contiguous()
+        gx = torch.zeros_like(x)
+        _call("og_reparam_bwd", _p(x), x.shape[1], _p(eps), _p(gc), gc.shape[1], x.shape[0], ctx.d, _p(gx))
+        return gx, None, None
+
+
+def reparam(x, eps, d):
+    return _Reparam.apply(x, eps, d)
+
+
+# --------------------------------------------------------------------------------------------------
+# losses: scalar = weight * mean(...)
+# --------------------------------------------------------------------------------------------------
+class _BCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, target, weight):
+        _chk(p)
+        p = p.contiguous()
+        loss = torch.zeros((), device=p.device, dtype=torch.float32)
+        gp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        _call("og_bce", _p(p), p.numel(), float(target), float(weight), _p(loss), _p(gp))
+        ctx.save_for_backward(gp)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (gp,) = ctx.saved_tensors
+        return gp * g, None, None
+
+
+def bce(p, target, weight=1.0):
+    """weight * nn.BCELoss()(p, full_like(p, target))."""
+    return _BCE.apply(p, target, weight)
+
+
+class _KL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, d, weight):
+        _chk(x)
+        x = x.contiguous()
+        loss = torch.zeros((), device=x.device, dtype=torch.float32)
+        gx = torch.zeros_like(x)
+        _call("og_kl", _p(x), x.shape[1], x.shape[0], d, float(weight), _p(loss), _p(gx))
+        ctx.save_for_backward(gx)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (gx,) = ctx.saved_tensors
+        return gx * g, None, None
+
+
+def kl_rows(x, d, weight=1.0):
+    return _KL.apply(x, d, weight)
+
+
+# --------------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------------
+def mask_bytes(mask):
+    if mask is None:
+        return None
+    return mask.to(torch.uint8).contiguous()
+
+
+class _WordsProj(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, words, w):
+        _chk(words, w)
+        words = words.contiguous()
+        b, cdf, l = words.shape
+        idf = w.shape[0]
+        src = torch.empty((b, idf, l), device=words.device, dtype=torch.float32)
+        _call("og_words_proj", _p(words), _p(w), b, idf, cdf, l, _p(src))
+        ctx.save_for_backward(words, w)
+        return src
+
+    @staticmethod
+    def backward(ctx, g):
+        words, w = ctx.saved_tensors
+        g = g.contiguous()
+        b, cdf, l = words.shape
+        idf = w.shape[0]
+        gw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        gwords = torch.empty_like(words) if ctx.needs_input_grad[0] else None
+        _call("og_words_proj_bwd", _p(words), _p(w), _p(g), b, idf, cdf, l, _p(gw), 0, _p(gwords))
+        return gwords, gw
+
+
+def words_proj(words, w):
+    return _WordsProj.apply(words, w)
+
+
+class _AttGeneral(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, src, mask_u8, idf):
+        _chk(h, src, mask_u8)
+        h, src = h.contiguous(), src.contiguous()
+        b, ih, iw, cs = h.shape
+        l = src.shape[2]
+        q = ih * iw
+        wc = torch.empty_like(h)
+        attn = torch.empty((b, l, ih, iw), device=h.device, dtype=torch.float32)
+        _call("og_att_general_fwd", _p(h), _p(src), _p(mask_u8), b, q, idf, cs, l, _p(wc), _p(attn))
+        ctx.idf = idf
+        ctx.save_for_backward(h, src, attn)
+        ctx.mark_non_differentiable(attn)  # visualisation only (trainer.py:390 discards it)
+        return wc, attn
+
+    @staticmethod
+    def backward(ctx, g_wc, _g_attn):
+        h, src, attn = ctx.saved_tensors
+        b, ih, iw, cs = h.shape
+        l = src.shape[2]
+        g_h = torch.empty_like(h)
+        g_src = torch.empty_like(src)
+        _call("og_att_general_bwd", _p(h), _p(src), _p(attn), _p(g_wc.contiguous()), 0, b, ih * iw, ctx.idf, cs, l,
+              _p(g_h), _p(g_src))
+        return g_h, g_src, None, None
+
+
+def att_general(h, src, mask_u8, idf):
+    return _AttGeneral.apply(h, src, mask_u8, idf)
+
+
+class _BuAtt(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, labels, glove, src, mask_u8, norm):
+        _chk(labels, glove, src, mask_u8)
+        labels, glove, src = labels.contiguous(), glove.contiguous(), src.contiguous()
+        b, e, r = labels.shape
+        l = glove.shape[2]
+        idf = src.shape[1]
+        wc = torch.empty((b, idf, r), device=src.device, dtype=torch.float32)
+        attn = torch.empty((b, l, r), device=src.device, dtype=torch.float32)
+        _call("og_bu_att_fwd", _p(labels), _p(glove), _p(src), _p(mask_u8), b, e, r, l, idf, 1 if norm else 0, 1e-8,
+              _p(wc), _p(attn))
+        ctx.save_for_backward(attn)
+        ctx.dims = (b, r, l, idf)
+        ctx.mark_non_differentiable(attn)
+        return wc, attn
+
+    @staticmethod
+    def backward(ctx, g_wc, _g):
+        (attn,) = ctx.saved_tensors
+        b, r, l, idf = ctx.dims
+        g_src = torch.empty((b, idf, l), device=attn.device, dtype=torch.float32)
+        _call("og_bu_att_bwd", _p(attn), _p(g_wc.contiguous()), b, r, l, idf, _p(g_src))
+        return None, None, g_src, None, None
+
+
+def bu_att(labels, glove, src, mask_u8, norm=True):
+    return _BuAtt.apply(labels, glove, src, mask_u8, norm)
+
+
+class _PaintMax(torch.autograd.Function):
+    """pprocess_bt_attns: out[b, y, x, k] = max_r f[b, k, r] * m[b, r, y, x]; f (B, num, R), m (B, Rtot, ih, iw)."""
+
+    @staticmethod
+    def forward(ctx, f, m):
+        _chk(f, m)
+        f, m = f.contiguous(), m.contiguous()
+        b, num, r = f.shape
+        _, rtot, ih, iw = m.shape
+        cp = cpad(num)
+        out = torch.empty((b, ih, iw, cp), device=f.device, dtype=torch.float32)
+        if cp != num:
+            out.zero_()
+        _call("og_paint_max_fwd", _p(f), _p(m), b, num, r, rtot, ih * iw, _p(out), cp, 0)
+        ctx.save_for_backward(f, m)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f, m = ctx.saved_tensors
+        g = g.contiguous()
+        b, num, r = f.shape
+        _, rtot, ih, iw = m.shape
+        g_f = torch.empty_like(f)
+        _call("og_paint_max_bwd", _p(f), _p(m), _p(g), g.shape[3], 0, b, num, r, rtot, ih * iw, _p(g_f))
+        return g_f, None
+
+
+def paint_max(f, m):
+    return _PaintMax.apply(f, m)
+
+
+def func_attention(query, context, gamma1):
+    """DAMSM attention, forward only (reference: GlobalAttention.py:32-70)."""
+    _chk(query, context)
+    query, context = query.contiguous(), context.contiguous()
+    b, ndf, lq = query.shape
+    ih, iw = context.shape[2:]
+    wc = torch.empty((b, ndf, lq), device=query.device, dtype=torch.float32)
+    attn = torch.empty((b, lq, ih, iw), device=query.device, dtype=torch.float32)
+    _call("og_func_attention_fwd", _p(query), _p(context), b, ndf, lq, ih * iw, float(gamma1), _p(wc), _p(attn))
+    return wc, attn
+
+
+# --------------------------------------------------------------------------------------------------
+# ROIAlign (NCHW like the reference op)
+# --------------------------------------------------------------------------------------------------
+class _RoIAlign(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, rois, ah, aw, scale):
+        _chk(features, rois)
+        features, rois = features.contiguous(), rois.contiguous()
+        assert rois.shape[1] == 5
+        b, c, h, w = features.shape
+        r = rois.shape[0]
+        out = torch.zeros((r, c, ah, aw), device=features.device, dtype=torch.float32)
+        _call("ROIAlignForwardLaucher", _p(features), float(scale), r, h, w, c, ah, aw, _p(rois), _p(out))
+        ctx.cfg = (b, c, h, w, ah, aw, scale)
+        ctx.save_for_backward(rois)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (rois,) = ctx.saved_tensors
+        b, c, h, w, ah, aw, scale = ctx.cfg
+        gin = torch.zeros((b, c, h, w), device=g.device, dtype=torch.float32)
+        _call("ROIAlignBackwardLaucher", _p(g.contiguous()), float(scale), b, rois.shape[0], h, w, c, ah, aw, _p(rois),
+              _p(gin))
+        return gin, None, None, None, None
+
+
+def roi_align(features, rois, ah, aw, scale):
+    return _RoIAlign.apply(features, rois, ah, aw, scale)
+
+
+class _RoIAlignAvg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, rois, ah, aw, scale):
+        _chk(features, rois)
+        features, rois = features.contiguous(), rois.contiguous()
+        assert rois.shape[1] == 5
+        b, c, h, w = features.shape
+        r = rois.shape[0]
+        out = torch.empty((r, c, ah, aw), device=features.device, dtype=torch.float32)
+        _call("og_roi_align_avg_fwd", _p(features), h, w, c, _p(rois), r, ah, aw, float(scale), _p(out))
+        ctx.cfg = (b, c, h, w, ah, aw, scale)
+        ctx.save_for_backward(rois)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (rois,) = ctx.saved_tensors
+        b, c, h, w, ah, aw, scale = ctx.cfg
+        gin = torch.zeros((b, c, h, w), device=g.device, dtype=torch.float32)
+        _call("og_roi_align_avg_bwd", _p(g.contiguous()), h, w, c, _p(rois), rois.shape[0], ah, aw, float(scale),
+              _p(gin))
+        return gin, None, None, None, None
+
+
+def roi_align_avg(features, rois, ah, aw, scale):
+    return _RoIAlignAvg.apply(features, rois, ah, aw, scale)
+
+
+# --------------------------------------------------------------------------------------------------
+def adam_ema_(p, g, m, v, avg, step, *, lr=2e-4, b1=0.5, b2=0.999, eps=1e-8, gscale=1.0, decay=0.999):
+    """Fused Adam (+EMA) over flat fp32 buffers, in place."""
+    _chk(p, g, m, v, avg)
+    _call("og_adam_ema", _p(p), _p(g), _p(m), _p(v), _p(avg), p.numel(), float(lr), float(b1), float(b2), float(eps),
+          int(step), float(gscale), float(decay))
+    bump_param_epoch()

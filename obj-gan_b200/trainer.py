@@ -1,0 +1,194 @@
+"""Step-A of ``condGANTrainer.train`` on the B200 kernels: G forward -> three PatD updates -> G update
+(PatD terms + KL) -> EMA, with the reference's ordering and optimiser settings
+(reference: image_generation/trainer.py:388-406 and 444-462; ``define_optimizers`` 197-224).
+
+What is different from the reference by design (B200-first, results identical):
+  * each network's parameters / gradients / Adam moments live in one flat fp32 buffer, so the optimiser is
+    one fused kernel per network (``og_adam_ema``) and the data-parallel exchange is one NCCL all-reduce per
+    network over its gradient bucket (one process per GPU instead of nn.DataParallel, trainer.py:136-152);
+  * during the G update the discriminators' parameters do not require grad, which skips the weight-gradient
+    GEMMs the reference computes and throws away (miscc/losses.py:372-399 + trainer.py:449-459);
+  * no per-step ``.item()`` / ``.cpu()`` synchronisation: losses stay on the device.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import losses, model, ops
+from .config import cfg
+
+ALIGN = 64  # floats; keeps every parameter view 256-byte aligned inside its bucket
+
+
+class FlatBucket:
+    """Parameters of one network as views of a single flat buffer (+ matching grad / Adam state)."""
+
+    def __init__(self, module: torch.nn.Module, ema: bool = False):
+        self.module = module
+        self.params = [p for p in module.parameters()]
+        dev = self.params[0].device
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.numel = total
+        self.flat = torch.zeros(total, device=dev)
+        self.grad = torch.zeros(total, device=dev)
+        self.m = torch.zeros(total, device=dev)
+        self.v = torch.zeros(total, device=dev)
+        for p, o in zip(self.params, offs):
+            n = p.numel()
+            self.flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + n].view(p.shape)
+            p.grad = self.grad[o:o + n].view(p.shape)
+        self.avg = self.flat.clone() if ema else None
+        self.offsets = offs
+        self.step = 0
+        ops.bump_param_epoch()
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def requires_grad_(self, flag: bool):
+        for p in self.params:
+            p.requires_grad_(flag)
+
+    def adam(self, lr, gscale=1.0):
+        self.step += 1
+        ops.adam_ema_(self.flat, self.grad, self.m, self.v, self.avg, self.step, lr=lr, b1=0.5, b2=0.999, eps=1e-8,
+                      gscale=gscale, decay=0.999)
+
+    def ema_state_dict(self):
+        """EMA weights keyed like ``module.state_dict()`` (what the reference saves as netG_epoch_%d.pth,
+        trainer.py:251-256)."""
+        sd = {k: v.clone() for k, v in self.module.state_dict().items()}
+        names = [n for n, _ in self.module.named_parameters()]
+        for n, p, o in zip(names, self.params, self.offsets):
+            sd[n] = self.avg[o:o + p.numel()].view(p.shape).clone()
+        return sd
+
+
+class StepATrainer:
+    """Owns G_NET + PAT_D_NET64/128/256 and runs Step-A steps on one GPU (one rank of a DP group)."""
+
+    def __init__(self, num_classes=80, device="cuda", process_group=None, seed=None):
+        if seed is not None:
+            torch.manual_seed(seed)
+        self.device = torch.device(device)
+        self.netG = model.G_NET(num_classes)
+        self.netsPatD = [model.PAT_D_NET64(), model.PAT_D_NET128(), model.PAT_D_NET256()][:cfg.TREE.BRANCH_NUM]
+        self.netG.apply(model.weights_init)
+        for d in self.netsPatD:
+            d.apply(model.weights_init)
+        self.netG.to(self.device)
+        for d in self.netsPatD:
+            d.to(self.device)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._flatten()
+
+    def _flatten(self):
+        self.bG = FlatBucket(self.netG, ema=True)
+        self.bD = [FlatBucket(d) for d in self.netsPatD]
+
+    def load_reference_state(self, g_sd, d_sds):
+        """Load reference-format state_dicts (strict) and rebuild the flat buckets."""
+        self.netG.load_state_dict({k: v.to(self.device) for k, v in g_sd.items()}, strict=True)
+        for d, sd in zip(self.netsPatD, d_sds):
+            d.load_state_dict({k: v.to(self.device) for k, v in sd.items()}, strict=True)
+        self._flatten()
+
+    def broadcast_parameters(self):
+        """Identical initial weights on every rank (the reference's DataParallel replicates from GPU0)."""
+        if self.world > 1:
+            for b in [self.bG, *self.bD]:
+                dist.broadcast(b.flat, src=0, group=self.pg)
+            self.bG.avg.copy_(self.bG.flat)
+            for m in [self.netG, *self.netsPatD]:
+                for buf in m.buffers():
+                    dist.broadcast(buf, src=0, group=self.pg)
+            ops.bump_param_epoch()
+
+    def _allreduce(self, bucket):
+        if self.world > 1:
+            return dist.all_reduce(bucket.grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        return None
+
+    def to_device(self, inp: dict) -> dict:
+        """Host (pinned) batch -> device tensors; non_blocking so copies overlap with queued kernels."""
+        out = {}
+        for k, v in inp.items():
+            if torch.is_tensor(v):
+                out[k] = v.to(self.device, non_blocking=True)
+            elif isinstance(v, (list, tuple)):
+                out[k] = [t.to(self.device, non_blocking=True) for t in v]
+            else:
+                out[k] = v
+        for k in ("rois", "fm_rois"):  # float64 host arrays in the reference; the hot path never reads them on device
+            pass
+        return out
+
+    def generate(self, inp):
+        g = self.netG
+        g.ca_net.eps_override = inp.get("eps")
+        return g(inp["z"], inp["sent_emb"], inp["words_embs"], inp["glove_words_embs"], inp["slabels_feat"],
+                 inp["mask"], inp["hmaps"], inp["rois"], inp["fm_rois"], inp["num_rois"], inp["bt_masks"],
+                 inp["fm_bt_masks"], inp["glb_max_num_roi"])
+
+    def step(self, inp: dict) -> dict:
+        """One Step-A step on device-resident inputs.  Returns losses as device scalars."""
+        lr_d, lr_g = cfg.TRAIN.DISCRIMINATOR_LR, cfg.TRAIN.GENERATOR_LR
+        gs = 1.0 / self.world
+        sent = inp["sent_emb"]
+        # (2) generate fake images
+        self.bG.requires_grad_(True)
+        fake_imgs, _bt_c, _att, _bt_att, mu, logvar = self.generate(inp)
+        out = {}
+        # (3-1) update the patch discriminators
+        works = []
+        for i, (d, b) in enumerate(zip(self.netsPatD, self.bD)):
+            b.requires_grad_(True)
+            b.zero_grad()
+            err = losses.patD_loss(d, inp["imgs"][i], fake_imgs[i], sent)
+            err.backward()
+            works.append(self._allreduce(b))
+            out[f"errPatD{i}"] = err.detach()
+        for w, b in zip(works, self.bD):
+            if w is not None:
+                w.wait()
+            b.adam(lr_d, gs)
+        # (4) update G through the updated discriminators (their weight gradients are not needed)
+        for b in self.bD:
+            b.requires_grad_(False)
+        self.bG.zero_grad()
+        err_g, _ = losses.G_loss_pat(self.netsPatD, fake_imgs, sent)
+        kl = losses.KL_loss(mu, logvar)
+        total = err_g + kl
+        total.backward()
+        w = self._allreduce(self.bG)
+        if w is not None:
+            w.wait()
+        self.bG.adam(lr_g, gs)  # fused Adam + EMA (trainer.py:460-462)
+        out["errG"] = err_g.detach()
+        out["kl"] = kl.detach()
+        out["fake_imgs"] = [f.detach() for f in fake_imgs]
+        return out
+
+    def step_from_host(self, host_inp: dict) -> float:
+        """The public end-to-end call: pinned host batch in, scalar generator loss out (forces the
+        device->host read of the step's result)."""
+        out = self.step(self.to_device(host_inp))
+        return float((out["errG"] + out["kl"]).item())
+
+
+def pin(inp: dict) -> dict:
+    out = {}
+    for k, v in inp.items():
+        if torch.is_tensor(v):
+            out[k] = v.pin_memory() if torch.cuda.is_available() else v
+        elif isinstance(v, (list, tuple)):
+            out[k] = [t.pin_memory() if torch.cuda.is_available() else t for t in v]
+        else:
+            out[k] = v
+    return out

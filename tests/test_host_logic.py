@@ -1,0 +1,81 @@
+"""CPU tests of the host-side logic (no kernels run: lib.DRY_RUN skips the launches, outputs are
+uninitialised).  Checks shapes, autograd wiring, flat-bucket plumbing and state_dict compatibility."""
+import pytest
+import torch
+
+import refimport
+from objgan_b200 import lib, model, synth, trainer
+from objgan_b200.config import cfg
+
+
+@pytest.fixture()
+def dry():
+    lib.DRY_RUN = True
+    yield
+    lib.DRY_RUN = False
+
+
+def test_step_a_wiring(dry):
+    t = trainer.StepATrainer(device="cpu", seed=0)
+    inp = synth.make_inputs(2, parity=True)
+    n0 = lib.get().launches
+    out = t.step(inp)
+    assert lib.get().launches - n0 > 300
+    assert [tuple(f.shape) for f in out["fake_imgs"]] == [(2, 3, 64, 64), (2, 3, 128, 128), (2, 3, 256, 256)]
+    assert t.bG.step == 1 and all(b.step == 1 for b in t.bD)
+    # every parameter is a view of its bucket and received a gradient view
+    for b in [t.bG, *t.bD]:
+        for p, o in zip(b.params, b.offsets):
+            assert p.data.data_ptr() == b.flat[o:].data_ptr()
+            assert p.grad.data_ptr() == b.grad[o:].data_ptr()
+
+
+def test_module_signatures(dry):
+    g = model.G_NET(80)
+    inp = synth.make_inputs(2, parity=True)
+    fake, btc, att, btatt, mu, logvar = g(inp["z"], inp["sent_emb"], inp["words_embs"], inp["glove_words_embs"],
+                                          inp["slabels_feat"], inp["mask"], inp["hmaps"], inp["rois"], inp["fm_rois"],
+                                          inp["num_rois"], inp["bt_masks"], inp["fm_bt_masks"], inp["glb_max_num_roi"])
+    assert mu.shape == (2, 100) and logvar.shape == (2, 100)
+    assert [tuple(a.shape) for a in att] == [(2, 18, 64, 64), (2, 18, 128, 128)]
+    assert [tuple(a.shape) for a in btatt] == [(2, 18, 64, 64), (2, 18, 128, 128)]
+    assert [tuple(a.shape) for a in btc] == [(2, inp["glb_max_num_roi"], 48)] * 2
+    d = model.PAT_D_NET128()
+    f = d(fake[1])
+    assert f.size(0) == 2 and tuple(f.size()) == (2, 768, 8, 8)
+    assert tuple(d.COND_DNET(f, inp["sent_emb"]).shape) == (2, 1, 3, 3)
+    assert tuple(d.UNCOND_DNET(f[:1]).shape) == (1, 1, 3, 3)
+    # standalone drop-in modules on NCHW tensors
+    a = model.ATT_NET(48, 256)
+    a.applyMask(inp["mask"])
+    wc, am = a(torch.randn(2, 48, 16, 16), inp["words_embs"])
+    assert tuple(wc.shape) == (2, 48, 16, 16) and tuple(am.shape) == (2, 18, 16, 16)
+    out = model.pprocess_bt_attns(torch.randn(2, 48, 5, 1), 16, 16, torch.rand(2, 5, 16, 16))
+    assert tuple(out.shape) == (2, 48, 16, 16)
+    r = model.RoIAlignAvg(5, 5, 1.0 / 16)(torch.randn(2, 16, 32, 32), torch.zeros(20, 5))
+    assert tuple(r.shape) == (20, 16, 5, 5)
+
+
+@pytest.mark.skipif(not refimport.available(), reason="/root/reference not mounted")
+def test_state_dict_keys_match_reference():
+    ref = refimport.load()
+    pairs = [(ref.model.G_NET(80), model.G_NET(80)), (ref.model.PAT_D_NET64(), model.PAT_D_NET64()),
+             (ref.model.PAT_D_NET256(), model.PAT_D_NET256())]
+    for r, m in pairs:
+        rs, ms = r.state_dict(), m.state_dict()
+        assert list(rs.keys()) == list(ms.keys())
+        for k in rs:
+            assert rs[k].shape == ms[k].shape and rs[k].dtype == ms[k].dtype, k
+        m.load_state_dict(rs, strict=True)
+        assert [n for n, _ in r.named_parameters()] == [n for n, _ in m.named_parameters()]
+
+
+def test_state_dict_keys_golden():
+    """Same check against the key list committed under tests/golden (works without the reference)."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "state_dict_keys.json")
+    gold = json.load(open(path))
+    for name, cls in (("G_NET", lambda: model.G_NET(80)), ("PAT_D_NET64", model.PAT_D_NET64)):
+        sd = cls().state_dict()
+        assert [[k, list(v.shape)] for k, v in sd.items()] == gold[name]
