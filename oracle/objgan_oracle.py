@@ -309,7 +309,7 @@ def roi_align_forward_np(feat, rois, ah, aw, scale):
     feat (B,C,H,W) f32, rois (R,5) f32 [batch, x1, y1, x2, y2] -> (R, C, ah, aw) f32.
     Reproduces the C promotion rules: float products for the scaled corners, ``+ 1.`` and
     ``/ (ah - 1.)`` evaluated in double then narrowed to float, float sample coordinates,
-    double bilinear weights, result narrowed to float."""
+    mixed float/double bilinear products (see the inline comment), double sum narrowed to float."""
     f32, f64 = np.float32, np.float64
     feat = np.ascontiguousarray(feat, dtype=f32)
     rois = np.ascontiguousarray(rois, dtype=f32)
@@ -332,10 +332,15 @@ def roi_align_forward_np(feat, rois, ah, aw, scale):
                     continue
                 hs = int(min(f32(math.floor(h)), f32(H - 2)))
                 ws = int(min(f32(math.floor(w)), f32(W - 2)))
-                hr, wr = f64(f32(h - f32(hs))), f64(f32(w - f32(ws)))
+                hr32, wr32 = f32(h - f32(hs)), f32(w - f32(ws))
+                hr, wr = f64(hr32), f64(wr32)
                 ul, ur = feat[b, :, hs, ws].astype(f64), feat[b, :, hs, ws + 1].astype(f64)
-                dl, dr = feat[b, :, hs + 1, ws].astype(f64), feat[b, :, hs + 1, ws + 1].astype(f64)
-                v = ul * (1.0 - hr) * (1.0 - wr) + ur * (1.0 - hr) * wr + dl * hr * (1.0 - wr) + dr * hr * wr
+                dl32, dr32 = feat[b, :, hs + 1, ws], feat[b, :, hs + 1, ws + 1]
+                # C typing of "bottom[i] * h_ratio * ..." (roi_align.c:131-134): float * float stays float until a
+                # double operand ("1. - w_ratio") appears; the four terms are then summed in double.
+                t3 = (dl32 * hr32).astype(f32).astype(f64) * (1.0 - wr)
+                t4 = ((dr32 * hr32).astype(f32) * wr32).astype(f32).astype(f64)
+                v = ul * (1.0 - hr) * (1.0 - wr) + ur * (1.0 - hr) * wr + t3 + t4
                 out[n, :, ph, pw] = v.astype(f32)
     return out
 

@@ -1,0 +1,106 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own code (imported read-only from /root/reference,
+so this script only works in the build container).  The fixtures pin oracle/objgan_oracle.py and the CUDA path
+on machines where the reference is absent (the GPU box).
+
+Weights are not stored: both sides rebuild them from a seed with objgan_b200.model's own constructors (CPU) and
+load them into the reference modules with load_state_dict(strict=True).
+
+    python tests/golden/make_golden.py
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(HERE))
+import refimport  # noqa: E402
+from objgan_b200 import model, synth  # noqa: E402
+
+SEED_W, SEED_IN = 101, 202
+
+
+def build_weights(seed=SEED_W):
+    torch.manual_seed(seed)
+    g = model.G_NET(80)
+    g.apply(model.weights_init)
+    ds = [model.PAT_D_NET64(), model.PAT_D_NET128(), model.PAT_D_NET256()]
+    for d in ds:
+        d.apply(model.weights_init)
+    return g.state_dict(), [d.state_dict() for d in ds]
+
+
+def sub(t, s):
+    return t[..., ::s, ::s].contiguous().numpy()
+
+
+def main():
+    ref = refimport.load()
+    g_sd, d_sds = build_weights()
+    # ---- G_NET forward, B=2, ragged captions / roi counts ------------------------------------
+    g = ref.model.G_NET(80)
+    g.load_state_dict(g_sd, strict=True)
+    inp = synth.make_inputs(2, seed=SEED_IN, parity=True)
+    torch.manual_seed(0)
+    out = g(inp["z"], inp["sent_emb"], inp["words_embs"], inp["glove_words_embs"], inp["slabels_feat"], inp["mask"],
+            inp["hmaps"], inp["rois"], inp["fm_rois"], inp["num_rois"], inp["bt_masks"], inp["fm_bt_masks"],
+            inp["glb_max_num_roi"])
+    torch.manual_seed(0)
+    eps = torch.FloatTensor(2, 100).normal_()     # the draw CA_NET.reparametrize made (model.py:473-477)
+    fake = [f.detach() for f in out[0]]
+    np.savez_compressed(os.path.join(HERE, "g_forward.npz"), eps=eps.numpy(), fake64=fake[0].numpy(),
+                        fake128=sub(fake[1], 4), fake256=sub(fake[2], 8), att1=sub(out[2][0].detach(), 4),
+                        att2=sub(out[2][1].detach(), 8), bt_att1=sub(out[3][0].detach(), 4),
+                        bt_c1=out[1][0].detach().numpy(), bt_c2=out[1][1].detach().numpy(), mu=out[4].detach().numpy(),
+                        logvar=out[5].detach().numpy(),
+                        bn_rm=g.state_dict()["h_net3_main.upsample.2.running_mean"].numpy())
+    # ---- patD_loss value + gradient norms ------------------------------------------------------
+    d = ref.model.PAT_D_NET64()
+    d.load_state_dict(d_sds[0], strict=True)
+    gen = torch.Generator().manual_seed(7)
+    real = torch.rand(4, 3, 64, 64, generator=gen) * 2 - 1
+    fk = torch.rand(4, 3, 64, 64, generator=gen) * 2 - 1
+    cond = torch.rand(4, 256, generator=gen)
+    err = ref.losses.patD_loss(d, real, fk, cond)
+    err.backward()
+    names = [n for n, _ in d.named_parameters()]
+    np.savez_compressed(os.path.join(HERE, "pat_d_loss.npz"), err=float(err),
+                        grad_norms=np.array([p.grad.norm().item() for p in d.parameters()]),
+                        grad_first=np.stack([p.grad.reshape(-1)[:4].numpy() for p in d.parameters()
+                                             if p.numel() >= 4]),
+                        names=np.array(names))
+    # ---- attention modules -----------------------------------------------------------------------
+    torch.manual_seed(5)
+    att = ref.GlobalAttention.GlobalAttentionGeneral(48, 256)
+    W = torch.randn(48, 256, 1, 1, generator=torch.Generator().manual_seed(1)) * 0.1
+    att.conv_context.weight.data.copy_(W)
+    gen = torch.Generator().manual_seed(9)
+    h, words = torch.randn(3, 48, 8, 8, generator=gen), torch.randn(3, 256, 18, generator=gen)
+    mask = torch.arange(18).view(1, 18) >= torch.tensor([18, 11, 6]).view(3, 1)
+    att.applyMask(mask)
+    wc, a = att(h, words)
+    q, ctx = torch.randn(3, 256, 14, generator=gen), torch.randn(3, 256, 17, 17, generator=gen)
+    fw, fa = ref.GlobalAttention.func_attention(q, ctx, 4.0)
+    np.savez_compressed(os.path.join(HERE, "attention.npz"), wc=wc.detach().numpy(), attn=a.detach().numpy(),
+                        func_wc=fw.numpy(), func_attn=fa.numpy())
+    # ---- ROIAlign from the reference C source compiled verbatim (oracle/_ref) -----------------------
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libroi_align_ref_cpu.so"))
+    rng = np.random.RandomState(3)
+    feat = rng.randn(2, 5, 16, 16).astype(np.float32)
+    xy = rng.uniform(-4, 230, (12, 2))
+    wh = rng.uniform(1, 128, (12, 2))
+    rois = np.hstack((np.repeat(np.arange(2), 6).reshape(-1, 1), xy, xy + wh)).astype(np.float32)
+    outp = np.zeros((12, 5, 6, 6), dtype=np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.ROIAlignForwardCpu(feat.ctypes.data_as(fp), ctypes.c_float(1.0 / 16), 12, 16, 16, 5, 6, 6,
+                           rois.ctypes.data_as(fp), outp.ctypes.data_as(fp))
+    np.savez_compressed(os.path.join(HERE, "roi_align.npz"), feat=feat, rois=rois, out=outp)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

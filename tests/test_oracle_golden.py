@@ -1,0 +1,166 @@
+"""CPU tests: the oracle against the committed golden fixtures (produced by the reference's own code via
+tests/golden/make_golden.py), the three ROIAlign restatements against each other, and the C ABI surface."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from objgan_b200 import lib, model, synth
+from oracle import objgan_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden")
+sys.path.insert(0, GOLD)
+import make_golden  # noqa: E402  (only its seed constants and build_weights are used here)
+
+
+def _close(a, b, tol=1e-4):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max()), np.abs(a - b).max()
+
+
+def test_g_forward_golden():
+    gold = np.load(os.path.join(GOLD, "g_forward.npz"))
+    g_sd, _ = make_golden.build_weights()
+    inp = synth.make_inputs(2, seed=make_golden.SEED_IN, parity=True)
+    inp["eps"] = torch.from_numpy(gold["eps"])
+    sd = {k: v.clone() for k, v in g_sd.items()}
+    with torch.no_grad():
+        fake, btc, att, btatt, mu, logvar = O.g_net_forward(sd, inp)
+    _close(fake[0].numpy(), gold["fake64"])
+    _close(fake[1][..., ::4, ::4].numpy(), gold["fake128"])
+    _close(fake[2][..., ::8, ::8].numpy(), gold["fake256"])
+    _close(att[0][..., ::4, ::4].numpy(), gold["att1"])
+    _close(att[1][..., ::8, ::8].numpy(), gold["att2"])
+    _close(btatt[0][..., ::4, ::4].numpy(), gold["bt_att1"])
+    _close(btc[0].numpy(), gold["bt_c1"])
+    _close(btc[1].numpy(), gold["bt_c2"])
+    _close(mu.numpy(), gold["mu"])
+    _close(logvar.numpy(), gold["logvar"])
+    _close(sd["h_net3_main.upsample.2.running_mean"].numpy(), gold["bn_rm"])
+
+
+def test_pat_d_loss_golden():
+    gold = np.load(os.path.join(GOLD, "pat_d_loss.npz"))
+    _, d_sds = make_golden.build_weights()
+    sd = {k: v.clone() for k, v in d_sds[0].items()}
+    gen = torch.Generator().manual_seed(7)
+    real = torch.rand(4, 3, 64, 64, generator=gen) * 2 - 1
+    fk = torch.rand(4, 3, 64, 64, generator=gen) * 2 - 1
+    cond = torch.rand(4, 256, generator=gen)
+    keys = O.trainable_keys(sd)
+    assert keys == list(gold["names"])
+    live, leaves = O._with_grad(sd, keys)
+    err = O.pat_d_loss(live, real, fk, cond)
+    grads = torch.autograd.grad(err, [leaves[k] for k in keys])
+    assert abs(float(err) - float(gold["err"])) < 1e-5
+    _close(np.array([g.norm().item() for g in grads]), gold["grad_norms"], 1e-3)
+
+
+def test_attention_golden():
+    gold = np.load(os.path.join(GOLD, "attention.npz"))
+    W = torch.randn(48, 256, 1, 1, generator=torch.Generator().manual_seed(1)) * 0.1
+    gen = torch.Generator().manual_seed(9)
+    h, words = torch.randn(3, 48, 8, 8, generator=gen), torch.randn(3, 256, 18, generator=gen)
+    mask = torch.arange(18).view(1, 18) >= torch.tensor([18, 11, 6]).view(3, 1)
+    wc, a = O.global_attention_general(h, words, W, mask)
+    _close(wc.numpy(), gold["wc"])
+    _close(a.numpy(), gold["attn"])
+    q, ctx = torch.randn(3, 256, 14, generator=gen), torch.randn(3, 256, 17, 17, generator=gen)
+    fw, fa = O.func_attention(q, ctx, 4.0)
+    _close(fw.numpy(), gold["func_wc"])
+    _close(fa.numpy(), gold["func_attn"])
+
+
+def _c_oracle():
+    so = os.path.join(ROOT, "oracle", "_ref", "libroi_align_oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_ref/libroi_align_oracle.so"])
+    return ctypes.CDLL(so)
+
+
+def test_roi_align_restatements_bit_exact():
+    """numpy oracle == C oracle == golden output of the reference's roi_align.c, bit for bit."""
+    gold = np.load(os.path.join(GOLD, "roi_align.npz"))
+    feat, rois, want = gold["feat"], gold["rois"], gold["out"]
+    got_np = O.roi_align_forward_np(feat, rois, 6, 6, 1.0 / 16)
+    assert np.array_equal(got_np, want)
+    c = _c_oracle()
+    fp = ctypes.POINTER(ctypes.c_float)
+    out = np.zeros_like(want)
+    c.og_oracle_roi_align_forward(feat.ctypes.data_as(fp), ctypes.c_float(1.0 / 16), rois.shape[0], 16, 16, 5, 6, 6,
+                                  rois.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert np.array_equal(out, want)
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libroi_align_ref_cpu.so")
+    if os.path.exists(ref_so):  # the reference source compiled verbatim, when it was built here
+        r = ctypes.CDLL(ref_so)
+        rng = np.random.RandomState(11)
+        feat2 = rng.randn(3, 4, 32, 32).astype(np.float32)
+        xy = rng.uniform(-8, 480, (30, 2))
+        rois2 = np.hstack((np.repeat(np.arange(3), 10).reshape(-1, 1), xy, xy + rng.uniform(0, 200, (30, 2))))
+        rois2 = rois2.astype(np.float32)
+        a = np.zeros((30, 4, 6, 6), dtype=np.float32)
+        b = np.zeros_like(a)
+        r.ROIAlignForwardCpu(feat2.ctypes.data_as(fp), ctypes.c_float(1.0 / 16), 30, 32, 32, 4, 6, 6,
+                             rois2.ctypes.data_as(fp), a.ctypes.data_as(fp))
+        c.og_oracle_roi_align_forward(feat2.ctypes.data_as(fp), ctypes.c_float(1.0 / 16), 30, 32, 32, 4, 6, 6,
+                                      rois2.ctypes.data_as(fp), b.ctypes.data_as(fp))
+        assert np.array_equal(a, b)
+        assert np.array_equal(O.roi_align_forward_np(feat2, rois2, 6, 6, 1.0 / 16), a)
+    # backward restatements agree (numpy vs C, both float64 accumulation)
+    g = np.random.RandomState(2).randn(*want.shape).astype(np.float32)
+    gb_np = O.roi_align_backward_np(g, rois, feat.shape, 6, 6, 1.0 / 16)
+    gb_c = np.zeros(feat.shape, dtype=np.float64)
+    c.og_oracle_roi_align_backward(g.ctypes.data_as(fp), ctypes.c_float(1.0 / 16), rois.shape[0], 16, 16, 5, 6, 6,
+                                   rois.ctypes.data_as(fp), gb_c.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    np.testing.assert_allclose(gb_c.astype(np.float32), gb_np, rtol=1e-6, atol=1e-7)
+
+
+def test_get_rois_blob():
+    fm = np.zeros((2, 10, 6))
+    fm[:, :, :4] = np.random.RandomState(0).uniform(0, 30, (2, 10, 4))
+    blob = O.get_rois_blob_np(fm)
+    assert blob.shape == (20, 5) and blob.dtype == np.float32
+    assert (blob[:10, 0] == 0).all() and (blob[10:, 0] == 1).all()
+    np.testing.assert_allclose(blob[:, 3], (fm[:, :, 0] + fm[:, :, 2]).reshape(-1).astype(np.float32))
+    # host helper of the product mirrors miscc/utils.py:365-399
+    xyxy = fm.copy()
+    xyxy[:, :, 2:4] += xyxy[:, :, 0:2]
+    blob2 = model._get_rois_blob(xyxy.reshape(20, 6)[:, :4], np.array([1] * 20))
+    assert np.array_equal(blob, blob2)
+
+
+def test_cabi_exports_every_declared_symbol():
+    """The shared library loads (no GPU needed) and exports everything include/objgan_b200.h declares."""
+    L = lib.get()
+    protos = lib.parse_header()
+    assert len(protos) >= 37
+    out = subprocess.check_output(["nm", "-D", "--defined-only", lib.LIB_PATH], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = sorted(set(protos) - exported)
+    assert not missing, missing
+    for name in protos:
+        assert name in L.fn
+    # the reference's FFI names are present verbatim (roi_align_kernel.h:13-27)
+    assert {"ROIAlignForwardLaucher", "ROIAlignBackwardLaucher"} <= exported
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are rejected (the product path has no CPU or library fallback)."""
+    from objgan_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.to_nhwc(torch.zeros(1, 8, 4, 4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "obj-gan_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), fn
