@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- G+D training-step throughput (Step-A of trainer.py) on N B200s.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1   # the reference algorithm on the host CPU cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...  # data parallel, one rank per GPU
+
+Prints ONE JSON line (rank 0).  A "step" = one Step-A pass (G forward, 3 PatD updates, G update + EMA) over a
+synthetic COCO-shaped batch of 16 images per GPU at 256x256 (BASELINE.json configs[1]; weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "G+D training-step images/sec @256x256 (Step-A: G fwd+bwd, 3 PatD updates, G update through 3 PatD + KL)"
+UNIT = "images/s"
+GMAC_PER_IMG_STEP_A = 330.0  # SURVEY.md 8d / BASELINE.md section 2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active")
+                                                          for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def dist_setup(n):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def max_over_ranks(ms, world):
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed(fn, steps, world):
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    barrier(world)
+    return max_over_ranks(ms, world)
+
+
+def conv_roofline(hbm, bf16_tf, src):
+    """Dominant kernel: the stage-3 HmapResBlock first conv (194->388, 3x3 reflect, 128x128, B=16): 11.1 GMAC/img
+    (SURVEY.md 8d).  Timed alone with CUDA events on the launching stream; operands (210 MB in, 420 MB out) exceed
+    the 126 MB L2, so every iteration is HBM-cold."""
+    from objgan_b200 import model
+    from objgan_b200.lib import PAD_REFLECT
+    B, C, H = 16, 194, 128
+    m = model.Conv2dP(C, 2 * C, 3, 1, 1, mode=PAD_REFLECT, split=C).cuda()
+    x = torch.randn(B, H, H, 200, device="cuda")
+    x[..., 194:] = 0
+    with torch.no_grad():
+        for _ in range(3):
+            m(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 5
+        e0.record()
+        for _ in range(n):
+            m(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = 2.0 * B * H * H * (9 * C) * (2 * C)          # algorithmic, unpadded
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = bf16_tf / 2.0                                   # tf32 dense = half the bf16 rate (nominal 1.1 vs 2.25 PF)
+    return {"bound": "tensor", "kernel": "conv_gemm_kernel<8> (res-block conv1 194->388 @128x128, B=16)",
+            "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+            "traffic": None, "ms_per_launch": round(ms, 3),
+            "peak_source": f"{src} bf16 cuBLAS burst / 2 (tf32:bf16 nominal ratio); kernel computes in fp32 on CUDA cores"}
+
+
+def attn_roofline(hbm, src):
+    """GlobalAttentionGeneral forward, Q=16384 regions x L=18 words, C=48, B=16: algorithmic bytes 4*Q*(2C+L) per image
+    = 7.47 MB."""
+    from objgan_b200 import ops
+    B, Q, C, L = 16, 16384, 48, 18
+    h = torch.randn(B, 128, 128, C, device="cuda")
+    srcw = torch.randn(B, C, L, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+    times = []
+    for i in range(8):
+        flush.zero_()                                       # evict L2 (256 MB > 126 MB)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.att_general(h, srcw, None, C)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    byts = 4.0 * Q * (2 * C + L) * B
+    ach = byts / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "att_general_fwd_kernel (Q=16384, L=18, C=48, B=16)", "achieved": round(ach, 1),
+            "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None, "ms_per_launch": round(ms, 4),
+            "peak_source": f"{src} copy bandwidth"}
+
+
+def cpu_step_a(batch, steps, warmup, seed=1234):
+    """Reference algorithm (oracle port) on the host cores: Step-A at batch `batch`."""
+    from objgan_b200 import model, synth
+    from oracle import objgan_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(seed)
+    g = model.G_NET(80)
+    ds = [model.PAT_D_NET64(), model.PAT_D_NET128(), model.PAT_D_NET256()]
+    state = O.StepAState(g.state_dict(), [d.state_dict() for d in ds])
+    inp = synth.make_inputs(batch, seed=seed, parity=False)
+    for _ in range(warmup):
+        O.step_a(state, inp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.step_a(state, inp)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 2
+    ips, spstep = cpu_step_a(B, args.steps, args.warmup)
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(ips, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(spstep * 1e3, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "step_a_b16_256 (BASELINE configs[1]); CPU arm runs a bounded sample of it: batch 2 per step",
+                   "global_batch": B, "words": 18, "rois": 10},
+        "cpu_baseline": {"value": round(ips, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} Step-A steps at batch {B} (oracle/objgan_oracle.py, torch CPU fp32, "
+                                   f"{cores} threads)"},
+        "e2e": {"value": round(ips, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    from objgan_b200 import lib, synth, trainer
+    world, rank, local = dist_setup(args.gpus)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun"
+    hbm, bf16_tf, bf16_sus, src = peaks()
+    B = args.batch_per_gpu
+    tr = trainer.StepATrainer(device=f"cuda:{local}", seed=1234)
+    tr.broadcast_parameters()
+    host = trainer.pin(synth.make_inputs(B, seed=1234 + rank, parity=False))
+    host.pop("eps")  # CA_NET draws its own noise on the device, like the reference
+    dev = tr.to_device(host)
+    torch.cuda.synchronize()
+    h2d = synth.input_bytes(host)
+
+    for _ in range(args.warmup):
+        tr.step(dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.get().launches
+    ms = timed(lambda: tr.step(dev), args.steps, world)
+    launches = lib.get().launches - n0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # end-to-end through the public call: pinned host batch -> device every step, loss read back every step
+    tr.step_from_host(host)
+    ms_e2e = timed(lambda: tr.step_from_host(host), args.steps, world)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return
+    roof = conv_roofline(hbm, bf16_tf, src)
+    roof_att = attn_roofline(hbm, src)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, sps = cpu_step_a(2, 1, 0)
+        cpu = {"value": round(ips, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"1 Step-A step at batch 2 ({sps:.1f} s) of oracle/objgan_oracle.py, torch CPU fp32, all host threads"}
+    step_tflops = 2 * GMAC_PER_IMG_STEP_A * 1e9 * value / 1e12
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "step_a_b16_256 (BASELINE configs[1]: full G_NET 64/128/256 + 3 patch Ds, batch 16/GPU)",
+                   "global_batch": world * B, "words": 18, "rois": 10, "parallelism": f"dp{world}",
+                   "l2": "inputs (0.47 GB/step) and activations (>10 GB) exceed the 126 MB L2; no explicit flush"},
+        "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_attention": roof_att,
+        "algorithmic_tflops": round(step_tflops, 2),
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.impl == "b200":
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,7 +66,32 @@ int og_conv2d_wgrad_simt(const float* x, int N, int H, int W, int C, long long x
 int og_pack_weights(const float* w_oihw, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split, int splitp,
                     int transposed, float* out, float* out_lo, cudaStream_t stream);
 int og_unpack_wgrad(const float* dw_packed, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split, int splitp,
-                    float* grad_oihw, int accumulate, cudaStream_t stream);
+                    float* grad_oihw, int accumulate, int transposed, cudaStream_t stream);
+
+/* Tensor-core path (tcgen05.mma kind::tf32, TMEM accumulators, TMA operand staging) for the stride-1
+ * contractions that dominate the step (HmapResBlock / upBlock / jointConv forward and input gradients).
+ * og_prep_split writes the tf32 hi/lo parts of an activation tensor (pad=1 also materialises the
+ * nn.ReflectionPad2d(1) halo, ref: model.py:67; s2d=1 writes the four space-to-depth phase blocks used by the
+ * stride-2 convs of the discriminators and by the adjoint of the 2x upsampling); og_conv2d_tc computes
+ *     y[n, osy*h+opy, osx*w+opx, :] = act(bias + sum_t x[n+dn_t, h+dh_t, w+dw_t, :] * W[widx_t])   (x OOB = 0)
+ * with taps = ntaps host quadruples (dh, dw, dn, widx); nsplit = 3 is the error-compensated 3xTF32 product
+ * (fp32-level accuracy), nsplit = 1 a single TF32 product. */
+int og_prep_split(const float* x, int N, int H, int W, int C, int pad, int s2d, float* xh, float* xl,
+                  cudaStream_t stream);
+int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH, int SW, int C, const float* wh,
+                 const float* wl, int ntaps_w, int Kw, float* y, int OH, int OW, int K, long long ysn, long long ysh,
+                 long long ysw, int OHf, int OWf, int osy, int osx, int opy, int opx, const int* taps_host, int ntaps,
+                 int nsplit, const float* bias, int act, float slope, cudaStream_t stream);
+/* dw[tap][co][ci] += sum over pixels of G_copy[n,h,w,co] * X_copy[n,h+dh,w,ci]; operands are the channel-planar
+ * hi/lo copies written by og_prep_split_planar ([copy][c][n][h][w], row pitch rounded up to 4 floats; pad=1 adds
+ * the reflection halo; copies = w-shifted and/or space-to-depth phase versions, because a TMA box must start
+ * 16-byte aligned in its innermost dimension, so a tap's w offset selects a copy instead of shifting the box).
+ * entries_host: nentries quadruples (g copy, dh, x copy, output tap). */
+int og_prep_split_planar(const float* x, int N, int H, int W, int C, int pad, int nshift, int origin, int s2d,
+                         float* th, float* tl, cudaStream_t stream);
+int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int OH, int OW, int Kp, int gvariants, const float* xh,
+                       const float* xl, int SH, int SW, int C, int xvariants, float* dw, int ntaps_out,
+                       const int* entries_host, int nentries, int nsplit, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * InstanceNorm2d / BatchNorm (train mode) + fused GLU / LeakyReLU / residual

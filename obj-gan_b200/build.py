@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose and out:
                 print(out, file=sys.stderr)
     if jobs or not os.path.exists(LIB):
-        run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"])
+        run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
     return LIB
 
 

@@ -340,9 +340,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Co, int Ci,
       o = ((long long)(kh * KW + kw) * Kp + cm) * Cip + ci;
     float v = w[i];
     if (out_lo) {  // tf32 hi/lo split for the 3xTF32 tensor-core path
-      float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      uint32_t uh, ul;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(uh) : "f"(v));
+      float hi = __uint_as_float(uh);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul) : "f"(v - hi));
       out[o] = hi;
-      out_lo[o] = v - hi;
+      out_lo[o] = __uint_as_float(ul);
     } else {
       out[o] = v;
     }
@@ -350,7 +353,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Co, int Ci,
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Co, int Ci, int KH, int KW, int Cip, int Kp,
-                                    int split, int splitp, float* __restrict__ grad, int accumulate) {
+                                    int split, int splitp, float* __restrict__ grad, int accumulate,
+                                    int transposed) {
   long long total = (long long)Co * Ci * KH * KW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -361,7 +365,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Co, int Ci
     int ci = (int)(t % Ci);
     int co = (int)(t / Ci);
     int cm = (split > 0 && co >= split) ? co + (splitp - split) : co;
-    float v = dw[((long long)(kh * KW + kw) * Cip + ci) * Kp + cm];
+    float v = transposed ? dw[((long long)(kh * KW + kw) * Kp + cm) * Cip + ci]
+                         : dw[((long long)(kh * KW + kw) * Cip + ci) * Kp + cm];
     grad[i] = accumulate ? grad[i] + v : v;
   }
 }
@@ -457,11 +462,11 @@ OG_API int og_pack_weights(const float* w_oihw, int Co, int Ci, int KH, int KW, 
 }
 
 OG_API int og_unpack_wgrad(const float* dw_packed, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split,
-                           int splitp, float* grad_oihw, int accumulate, cudaStream_t stream) {
+                           int splitp, float* grad_oihw, int accumulate, int transposed, cudaStream_t stream) {
   long long total = (long long)Co * Ci * KH * KW;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   unpack_wgrad_kernel<<<blocks, 256, 0, stream>>>(dw_packed, Co, Ci, KH, KW, Cip, Kp, split, splitp, grad_oihw,
-                                                  accumulate);
+                                                  accumulate, transposed);
   OG_RETURN_LAST_ERROR();
 }

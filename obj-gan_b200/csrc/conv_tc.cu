@@ -1,0 +1,818 @@
+// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (kind::tf32) with TMEM accumulators,
+// operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle), mbarrier producer/consumer pipeline.
+//
+// Covers every stride-1 contraction of the hot path through a "tap list":
+//     out[pix, :] = sum_t  src[pix + (dh_t, dw_t), :] * W[widx_t]          (src out-of-bounds = 0 via TMA fill)
+// which is the forward of the reflection-padded 3x3 convs of HmapResBlock (model.py:63-81; the halo is
+// materialised by og_prep_split), the zero-padded 3x3 convs (model.py:36-39, 1020-1048), their input
+// gradients (taps mirrored, operand re-packed) and the four phases of nearest-2x-upsample + conv3x3
+// (upBlock, model.py:43-49: tap offsets at low resolution, strided output pixels).
+//
+// Precision: fp32 parity (1e-3 end to end) is not reachable with one TF32 product (2^-11 operand rounding,
+// ~35 stacked convs), so by default each product is error-compensated:  a*b ~= ah*bh + al*bh + ah*bl  with
+// ah = a rounded down to tf32, al = a - ah (exact), three MMAs into the same fp32 TMEM accumulator ("3xTF32").
+// nsplit = 1 runs the plain single-TF32 product (reported separately, never the parity mode).
+//
+// GEMM tiling: one CTA = 128 output pixels (a TN x TH x TW patch) x BN output channels (BN % 16 == 0,
+// <= 256); K loop over taps x 32-channel chunks; STAGES-deep smem ring of {A_hi, A_lo, B_hi, B_lo}.
+// Warp roles: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = epilogue (TMEM -> registers -> global, one TMEM lane quadrant each).
+#include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace {
+
+// round-to-nearest tf32 (unbiased; truncation would bias every product the same way and the bias adds up
+// linearly over the reduction).  lo = v - hi is exact in fp32 and is itself rounded to tf32 so that the tensor
+// core's own operand truncation is a no-op: |v - hi - lo| <= 2^-22 |v|.
+__device__ __forceinline__ float tf32_rn(float v) {
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float tf32_hi(float v) { return tf32_rn(v); }
+__device__ __forceinline__ float tf32_lo(float v, float hi) { return tf32_rn(v - hi); }
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;              // tf32 elements per k-chunk = one 128-byte swizzle row
+constexpr int TC_MAX_TAPS = 36;
+constexpr int TC_THREADS = 192;
+
+struct TcTaps {
+  int n;
+  int dh[TC_MAX_TAPS], dw[TC_MAX_TAPS], dn[TC_MAX_TAPS], widx[TC_MAX_TAPS];
+};
+
+struct TcParams {
+  int N, OH, OW;          // GEMM-row pixel grid (before the output stride/phase mapping)
+  int TN, TH, TW;         // tile patch: TN*TH*TW == 128
+  int tiles_h, tiles_w;   // tiles per image along h / w
+  int cchunks;            // ceil(C / 32)
+  int K;                  // output channels actually stored (<= gridDim.y * BN)
+  int nsplit;             // 1 or 3
+  float* y;
+  long long ysn, ysh, ysw;  // output strides (elements) of the FULL-resolution output tensor
+  int osy, osx, opy, opx;   // output pixel = (osy * h + opy, osx * w + opx)
+  int OHfull, OWfull;       // bounds of the output tensor
+  const float* bias;        // [K] or null
+  int act;
+  float slope;
+  TcTaps taps;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tc_act(float v, int act, float slope) {
+  if (act == OG_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == OG_ACT_TANH) return tanhf(v);
+  if (act == OG_ACT_SIGMOID) return og_sigmoid(v);
+  return v;
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                          // layout type: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major, dense
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                    // c_format = F32
+  d |= 2u << 7;                    // a_format = TF32
+  d |= 2u << 10;                   // b_format = TF32
+  d |= (uint32_t)(N >> 3) << 17;   // n_dim
+  d |= (uint32_t)(M >> 4) << 24;   // m_dim
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+               const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+               const TcParams p) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+  constexpr uint32_t B_BYTES = BN * TC_BK * 4;
+  constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw_i = t % p.tiles_w;
+  t /= p.tiles_w;
+  const int th_i = t % p.tiles_h;
+  const int tn_i = t / p.tiles_h;
+  const int n0 = tn_i * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
+  const int col0 = blockIdx.y * BN;
+  const int nk = p.taps.n * p.cchunks;
+  const uint32_t tx_bytes = (p.nsplit == 3) ? STAGE_BYTES : (A_BYTES + B_BYTES);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_ah);
+    prefetch_tmap(&map_bh);
+    if (p.nsplit == 3) {
+      prefetch_tmap(&map_al);
+      prefetch_tmap(&map_bl);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < nk; ++it) {
+        const int tap = it / p.cchunks, cc = it - tap * p.cchunks;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], tx_bytes);
+        const int c0 = cc * TC_BK, ws = w0 + p.taps.dw[tap], hs = h0 + p.taps.dh[tap], widx = p.taps.widx[tap];
+        const int ns = n0 + p.taps.dn[tap];   // image offset: selects a space-to-depth phase block of the source
+        tma_load_4d(sa, &map_ah, &full_bar[stage], c0, ws, hs, ns);
+        tma_load_3d(sa + 2 * A_BYTES, &map_bh, &full_bar[stage], c0, col0, widx);
+        if (p.nsplit == 3) {
+          tma_load_4d(sa + A_BYTES, &map_al, &full_bar[stage], c0, ws, hs, ns);
+          tma_load_3d(sa + 2 * A_BYTES + B_BYTES, &map_bl, &full_bar[stage], c0, col0, widx);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < nk; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+        const uint64_t ah = make_desc_sw128(sa), al = make_desc_sw128(sa + A_BYTES);
+        const uint64_t bh = make_desc_sw128(sa + 2 * A_BYTES), bl = make_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);   // advance 32 bytes inside the swizzle row
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          if (p.nsplit == 3) {
+            umma_tf32(tmem_base, al + koff, bh + koff, idesc, acc);   // small terms first
+            umma_tf32(tmem_base, ah + koff, bl + koff, idesc, 1u);
+            umma_tf32(tmem_base, ah + koff, bh + koff, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, ah + koff, bh + koff, idesc, acc);
+          }
+        }
+        umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(&tmem_full_bar);        // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;               // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;        // tile row = output pixel within the patch
+    const int tw = row % p.TW;
+    const int th = (row / p.TW) % p.TH;
+    const int tn = row / (p.TW * p.TH);
+    const int n = n0 + tn, h = h0 + th, w = w0 + tw;
+    const int oy = p.osy * h + p.opy, ox = p.osx * w + p.opx;
+    const bool row_ok = (n < p.N) && (h < p.OH) && (w < p.OW) && (oy < p.OHfull) && (ox < p.OWfull);
+    float* yrow = p.y + (long long)n * p.ysn + (long long)oy * p.ysh + (long long)ox * p.ysw + col0;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (c + j < BN && col0 + c + j < p.K) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
+            if (p.bias) {
+              float4 b = ldg4(p.bias + col0 + c + j);
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (p.act != OG_ACT_NONE) {
+              v.x = tc_act(v.x, p.act, p.slope); v.y = tc_act(v.y, p.act, p.slope);
+              v.z = tc_act(v.z, p.act, p.slope); v.w = tc_act(v.w, p.act, p.slope);
+            }
+            *reinterpret_cast<float4*>(yrow + c + j) = v;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// fp32 tensor viewed as [d3][d2][d1][d0] (d0 contiguous); strides in elements for d1..d3
+int make_map(CUtensorMap* m, const float* base, int rank, const unsigned long long* dims,
+             const unsigned long long* strides_elems, const unsigned* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return (int)cudaErrorNotSupported;
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_elems[i] * sizeof(float);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1000 + (int)r;
+}
+
+template <int BN, int STAGES>
+int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+              const TcParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, stream>>>(ah, al, bh, bl, p);
+  return (int)cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient on the tensor cores.
+//   dW[t][co][ci] += sum_{n,h,w} G[n,h,w,co] * X[n, h+dh_t, w+dw_t, ci]
+// GEMM per tap: M = co, N = ci, reduction over pixels.  tcgen05.mma wants the reduction index contiguous
+// (K-major) for the proven 128B-swizzle operand path, so og_prep_split_planar first writes channel-planar
+// hi/lo copies  Gt[co][n][h][w], Xt[ci][n][h][w]  (a bandwidth pass, ~20% of the MMA time at stage 3).
+// One pipeline stage = 32 consecutive pixels of one image row: A tile = 128 co x 32 pixels, B tile = BNW ci x
+// 32 pixels, both plain 4-D TMA boxes with out-of-bounds zero fill (which also implements the tap shift at
+// the borders).  Grid: (co tiles of 128, taps, pixel splits); partial sums are reduced with fp32 atomics.
+// ------------------------------------------------------------------------------------------------
+struct TcWgradParams {
+  int N, OH, OW;        // pixel grid of G
+  int cw, chh, cn;      // pixel chunk of one stage: cw x chh x cn = 32 pixels (w fastest)
+  int flatW;            // > 0: maps narrower than 32 pixels are addressed with (h, w) flattened (row length flatW)
+  int wchunks, hchunks; // chunks per row / per image column
+  int total_chunks;
+  int chunks_per_cta;
+  int Kp, C;            // rows (co) and columns (ci) of each dW[t]
+  int nsplit;
+  float* dw;            // [ntaps_out][Kp][C]
+  // entry e: dW[out[e]] += G(rows offset aoff[e]) * X(row offset dh[e], planar copy bvar[e])
+  int aoff[TC_MAX_TAPS], dh[TC_MAX_TAPS], bvar[TC_MAX_TAPS], out[TC_MAX_TAPS];
+};
+
+constexpr int WG_PIX = 32;    // pixels per stage = one 128-byte swizzle row (4 MMA k-steps)
+
+template <int BNW, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_constant__ CUtensorMap map_gl,
+                     const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                     const TcWgradParams p) {
+  constexpr uint32_t A_BYTES = TC_BM * WG_PIX * 4;        // 16 KB
+  constexpr uint32_t B_BYTES = BNW * WG_PIX * 4;
+  constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr uint32_t TMEM_COLS = BNW <= 32 ? 32 : BNW <= 64 ? 64 : BNW <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cotile = blockIdx.x, tap = blockIdx.y;
+  const int ch_beg = blockIdx.z * p.chunks_per_cta;
+  const int ch_end = min(p.total_chunks, ch_beg + p.chunks_per_cta);
+  const int nk = ch_end - ch_beg;
+  const uint32_t tx_bytes = (p.nsplit == 3) ? STAGE_BYTES : (A_BYTES + B_BYTES);
+  if (nk <= 0) return;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_gh);
+    prefetch_tmap(&map_xh);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int dh = p.dh[tap], brow = p.bvar[tap] * p.C, arow = p.aoff[tap] + cotile * TC_BM;
+      for (int it = 0; it < nk; ++it) {
+        const int ch = ch_beg + it;
+        const int wc = ch % p.wchunks;
+        const int t2 = ch / p.wchunks;
+        const int hc = t2 % p.hchunks;
+        const int w0 = wc * p.cw, h = hc * p.chh, n = (t2 / p.hchunks) * p.cn;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], tx_bytes);
+        // the innermost TMA coordinate must stay 16-byte aligned, so the w shift of the tap selects one of the
+        // pre-shifted planar copies of X (see og_prep_split_planar) instead of moving the box; the row shift dh is
+        // a coordinate offset (flattened maps: dh * row length, still a multiple of 4 floats)
+        const int bw = p.flatW ? w0 + dh * p.flatW : w0;
+        const int bh = p.flatW ? 0 : h + dh;
+        tma_load_4d(sa, &map_gh, &full_bar[stage], w0, h, n, arow);
+        tma_load_4d(sa + 2 * A_BYTES, &map_xh, &full_bar[stage], bw, bh, n, brow);
+        if (p.nsplit == 3) {
+          tma_load_4d(sa + A_BYTES, &map_gl, &full_bar[stage], w0, h, n, arow);
+          tma_load_4d(sa + 2 * A_BYTES + B_BYTES, &map_xl, &full_bar[stage], bw, bh, n, brow);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TC_BM, BNW);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < nk; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+        const uint64_t ah = make_desc_sw128(sa), al = make_desc_sw128(sa + A_BYTES);
+        const uint64_t bh = make_desc_sw128(sa + 2 * A_BYTES), bl = make_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+        for (int k = 0; k < WG_PIX / 8; ++k) {
+          const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          if (p.nsplit == 3) {
+            umma_tf32(tmem_base, al + koff, bh + koff, idesc, acc);
+            umma_tf32(tmem_base, ah + koff, bl + koff, idesc, 1u);
+            umma_tf32(tmem_base, ah + koff, bh + koff, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, ah + koff, bh + koff, idesc, acc);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = cotile * TC_BM + q * 32 + lane;
+    const bool row_ok = co < p.Kp;
+    float* drow = p.dw + ((long long)p.out[tap] * p.Kp + co) * p.C;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BNW; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c + j < BNW && c + j < p.C) atomicAdd(drow + c + j, __uint_as_float(r[j]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BNW, int STAGES>
+int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
+                 const TcWgradParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * WG_PIX * 4 + 2 * BNW * WG_PIX * 4) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<BNW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  conv_tc_wgrad_kernel<BNW, STAGES><<<grid, TC_THREADS, smem, stream>>>(gh, gl, xh, xl, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI.
+//   xh/xl : source activations, tf32 hi / lo parts (og_prep_split), NHWC [SN][SH][SW][C] contiguous, C % 4 == 0
+//           (SN = N, or 4*N for a space-to-depth source: phase block (a*2+b) holds x[:, a::2, b::2])
+//   wh/wl : weights hi / lo, [ntaps_w][Kw][C] (og_pack_weights with transposed=1 for fprop), Kw rows
+//   y     : output NHWC, channel count K (K % 4 == 0), element strides ysn/ysh/ysw, spatial bounds OHf x OWf
+//   rows of the GEMM are the pixel grid N x OH x OW; output pixel (osy*h + opy, osx*w + opx)
+//   taps  : ntaps quadruples (dh, dw, dn, weight tap index): source pixel = image n + dn, (h + dh, w + dw), zero
+//           outside [0,SH)x[0,SW);  bias/act: optional epilogue (bias[K], OG_ACT_*)
+// ------------------------------------------------------------------------------------------------
+OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH, int SW, int C, const float* wh,
+                        const float* wl, int ntaps_w, int Kw, float* y, int OH, int OW, int K, long long ysn,
+                        long long ysh, long long ysw, int OHf, int OWf, int osy, int osx, int opy, int opx,
+                        const int* taps_host, int ntaps, int nsplit, const float* bias, int act, float slope,
+                        cudaStream_t stream) {
+  if (C % 4 || K % 4 || ntaps < 1 || ntaps > TC_MAX_TAPS || (nsplit != 1 && nsplit != 3)) return (int)cudaErrorInvalidValue;
+  if ((long long)N * OH * OW == 0) return 0;
+  TcParams p;
+  p.N = N; p.OH = OH; p.OW = OW;
+  // patch shape: TW = largest power of two <= min(OW, 16); TH fills up to 128 / TW within OH; TN the rest
+  int TW = 1;
+  while (TW * 2 <= OW && TW * 2 <= 16) TW *= 2;
+  int TH = 1;
+  while (TH * 2 <= OH && TW * TH * 2 <= TC_BM) TH *= 2;
+  int TN = TC_BM / (TW * TH);
+  // a tile must not straddle two space-to-depth phase blocks of the source (image index n + dn)
+  if (SN != N && (N % TN) != 0) return (int)cudaErrorInvalidValue;
+  p.TN = TN; p.TH = TH; p.TW = TW;
+  p.bias = bias; p.act = act; p.slope = slope;
+  p.tiles_w = og_cdiv(OW, TW);
+  p.tiles_h = og_cdiv(OH, TH);
+  const int tiles_n = og_cdiv(N, TN);
+  p.cchunks = og_cdiv(C, TC_BK);
+  p.K = K;
+  p.nsplit = nsplit;
+  p.y = y; p.ysn = ysn; p.ysh = ysh; p.ysw = ysw;
+  p.osy = osy; p.osx = osx; p.opy = opy; p.opx = opx;
+  p.OHfull = OHf; p.OWfull = OWf;
+  p.taps.n = ntaps;
+  for (int i = 0; i < ntaps; ++i) {
+    p.taps.dh[i] = taps_host[4 * i];
+    p.taps.dw[i] = taps_host[4 * i + 1];
+    p.taps.dn[i] = taps_host[4 * i + 2];
+    p.taps.widx[i] = taps_host[4 * i + 3];
+  }
+  // N tile: whole K if it fits one UMMA (<= 256), else the smallest number of equal tiles (multiple of 16)
+  const int Kr = (K + 15) / 16 * 16;
+  const int ntile = og_cdiv(Kr, 256);
+  int BN = (og_cdiv(Kr, ntile) + 15) / 16 * 16;
+  int BNsel = BN <= 64 ? 64 : BN <= 112 ? 112 : BN <= 208 ? 208 : 256;
+  if (BN <= 32) BNsel = 32;
+  dim3 grid(tiles_n * p.tiles_h * p.tiles_w, og_cdiv(K, BNsel), 1);
+
+  CUtensorMap mah, mal, mbh, mbl;
+  unsigned long long adims[4] = {(unsigned long long)C, (unsigned long long)SW, (unsigned long long)SH, (unsigned long long)SN};
+  unsigned long long astr[3] = {(unsigned long long)C, (unsigned long long)SW * C, (unsigned long long)SH * SW * C};
+  unsigned abox[4] = {(unsigned)TC_BK, (unsigned)TW, (unsigned)TH, (unsigned)TN};
+  unsigned long long bdims[3] = {(unsigned long long)C, (unsigned long long)Kw, (unsigned long long)ntaps_w};
+  unsigned long long bstr[2] = {(unsigned long long)C, (unsigned long long)Kw * C};
+  unsigned bbox[3] = {(unsigned)TC_BK, (unsigned)BNsel, 1u};
+  int rc;
+  if ((rc = make_map(&mah, xh, 4, adims, astr, abox))) return rc;
+  if ((rc = make_map(&mbh, wh, 3, bdims, bstr, bbox))) return rc;
+  if (nsplit == 3) {
+    if ((rc = make_map(&mal, xl, 4, adims, astr, abox))) return rc;
+    if ((rc = make_map(&mbl, wl, 3, bdims, bstr, bbox))) return rc;
+  } else {
+    mal = mah;
+    mbl = mbh;
+  }
+  switch (BNsel) {
+    case 32:  return launch_tc<32, 4>(mah, mal, mbh, mbl, p, grid, stream);
+    case 64:  return launch_tc<64, 4>(mah, mal, mbh, mbl, p, grid, stream);
+    case 112: return launch_tc<112, 3>(mah, mal, mbh, mbl, p, grid, stream);
+    case 208: return launch_tc<208, 2>(mah, mal, mbh, mbl, p, grid, stream);
+    default:  return launch_tc<256, 2>(mah, mal, mbh, mbl, p, grid, stream);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient:  dw[t][co][ci] (fp32, [ntaps][Kp][C], zero-filled here) = sum_pixels G * X(shifted by tap t)
+//   gh/gl : output gradient hi/lo, channel-planar copies [gvariants][Kp][N][OH][OWp]  (og_prep_split_planar)
+//   xh/xl : source activations hi/lo, channel-planar copies [xvariants][C][N][SH][SWp] (w-shifted and/or
+//           space-to-depth phase copies)
+//   entries: nentries quadruples (g copy, dh, x copy, output tap): dw[tap] += G_copy^T * X_copy shifted by dh rows
+// ------------------------------------------------------------------------------------------------
+OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int OH, int OW, int Kp, int gvariants,
+                              const float* xh, const float* xl, int SH, int SW, int C, int xvariants, float* dw,
+                              int ntaps_out, const int* entries_host, int nentries, int nsplit, cudaStream_t stream) {
+  if (nentries < 1 || nentries > TC_MAX_TAPS || (nsplit != 1 && nsplit != 3) || C > 256) return (int)cudaErrorInvalidValue;
+  OG_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)ntaps_out * Kp * C, stream));
+  if ((long long)N * OH * OW == 0) return 0;
+  const int OWp = (OW + 3) / 4 * 4, SWp = (SW + 3) / 4 * 4;
+  TcWgradParams p;
+  p.N = N; p.OH = OH; p.OW = OW;
+  // one stage = 32 consecutive pixels of a row (a TMA box row must be one full 128-byte swizzle line).  Maps
+  // narrower than 32 pixels are addressed with (h, w) flattened, which needs unpadded planar rows on both sides.
+  const bool flat = OW < WG_PIX;
+  if (flat && !(OW == SW && OH == SH && OW % 4 == 0 && (OH * OW) % WG_PIX == 0)) return (int)cudaErrorInvalidValue;
+  p.cw = WG_PIX; p.chh = 1; p.cn = 1;
+  p.flatW = flat ? OW : 0;
+  p.wchunks = flat ? (OH * OW) / WG_PIX : og_cdiv(OW, WG_PIX);
+  p.hchunks = flat ? 1 : OH;
+  p.total_chunks = p.wchunks * p.hchunks * N;
+  p.Kp = Kp; p.C = C; p.nsplit = nsplit; p.dw = dw;
+  for (int i = 0; i < nentries; ++i) {
+    p.aoff[i] = entries_host[4 * i] * Kp;
+    p.dh[i] = entries_host[4 * i + 1];
+    p.bvar[i] = entries_host[4 * i + 2];
+    p.out[i] = entries_host[4 * i + 3];
+  }
+  const int cotiles = og_cdiv(Kp, TC_BM);
+  // pixel splits: ~2 waves of CTAs over 148 SMs, at least 8 chunks per CTA
+  int splits = og_cdiv(296, cotiles * nentries);
+  int maxs = p.total_chunks / 8;
+  if (maxs < 1) maxs = 1;
+  if (splits > maxs) splits = maxs;
+  p.chunks_per_cta = og_cdiv(p.total_chunks, splits);
+  splits = og_cdiv(p.total_chunks, p.chunks_per_cta);
+  dim3 grid(cotiles, nentries, splits);
+
+  const int Cr = (C + 15) / 16 * 16;
+  const int BNsel = Cr <= 32 ? 32 : Cr <= 64 ? 64 : Cr <= 112 ? 112 : Cr <= 208 ? 208 : 256;
+  CUtensorMap mgh, mgl, mxh, mxl;
+  unsigned long long gd[4] = {(unsigned long long)OW, (unsigned long long)OH, (unsigned long long)N,
+                              (unsigned long long)Kp * gvariants};
+  unsigned long long gs[3] = {(unsigned long long)OWp, (unsigned long long)OH * OWp, (unsigned long long)N * OH * OWp};
+  unsigned gb[4] = {(unsigned)WG_PIX, 1u, 1u, (unsigned)TC_BM};
+  unsigned long long xd[4] = {(unsigned long long)SW, (unsigned long long)SH, (unsigned long long)N,
+                              (unsigned long long)C * xvariants};
+  unsigned long long xs[3] = {(unsigned long long)SWp, (unsigned long long)SH * SWp, (unsigned long long)N * SH * SWp};
+  unsigned xb[4] = {(unsigned)WG_PIX, 1u, 1u, (unsigned)BNsel};
+  if (flat) {   // dims (H*W, 1, N, rows)
+    gd[0] = xd[0] = (unsigned long long)OH * OW;
+    gd[1] = xd[1] = 1;
+    gs[0] = xs[0] = (unsigned long long)OH * OW;
+  }
+  int rc;
+  if ((rc = make_map(&mgh, gh, 4, gd, gs, gb))) return rc;
+  if ((rc = make_map(&mxh, xh, 4, xd, xs, xb))) return rc;
+  if (nsplit == 3) {
+    if ((rc = make_map(&mgl, gl, 4, gd, gs, gb))) return rc;
+    if ((rc = make_map(&mxl, xl, 4, xd, xs, xb))) return rc;
+  } else {
+    mgl = mgh;
+    mxl = mxh;
+  }
+  switch (BNsel) {
+    case 32:  return launch_wgrad<32, 4>(mgh, mgl, mxh, mxl, p, grid, stream);
+    case 64:  return launch_wgrad<64, 4>(mgh, mgl, mxh, mxl, p, grid, stream);
+    case 112: return launch_wgrad<112, 3>(mgh, mgl, mxh, mxl, p, grid, stream);
+    case 208: return launch_wgrad<208, 2>(mgh, mgl, mxh, mxl, p, grid, stream);
+    default:  return launch_wgrad<256, 2>(mgh, mgl, mxh, mxl, p, grid, stream);
+  }
+}
+
+// channel-planar tf32 hi/lo copies for the wgrad kernel: t[s][c][n][h'][w'] = Xpad[c][n][h'][w' + s - origin]
+// (zero outside), h' in [0, H+2*pad), row pitch Wp = (W + 2*pad) rounded up to 4 floats, s in [0, nshift).
+// pad = 1 materialises the nn.ReflectionPad2d(1) halo.  s2d = 1: four space-to-depth phase blocks
+// t[phase][s][c][n][h'][w'] with phase (a*2+b) = x[:, a::2, b::2] (stride-2 convs, 2x-upsample adjoints).  The shifted copies exist because TMA needs the innermost
+// box coordinate 16-byte aligned: a tap's w offset picks a copy instead of an unaligned box.
+__global__ void prep_split_planar_kernel(const float* __restrict__ x, int N, int H, int W, int C, int pad, int Wp,
+                                         int nshift, int origin, int s2d, float* __restrict__ th,
+                                         float* __restrict__ tl) {
+  __shared__ float tile[36][33];                   // columns w0-1 .. w0+34 of the (padded / phase) row, 32 channels
+  const int Hp = s2d ? H / 2 : H + 2 * pad, Wq = s2d ? W / 2 : W + 2 * pad;
+  int nh = blockIdx.z;                             // (phase *) n * Hp + h'
+  int phase = 0;
+  if (s2d) {
+    phase = nh / (N * Hp);
+    nh -= phase * N * Hp;
+  }
+  const int n = nh / Hp, hp = nh - n * Hp;
+  int sh;
+  if (s2d) {
+    sh = 2 * hp + (phase >> 1);
+  } else {
+    sh = hp - pad;
+    if (sh < 0) sh = -sh;
+    if (sh >= H) sh = 2 * H - 2 - sh;
+  }
+  const int w0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 36; j += 8) {      // rows = column index, cols = c (coalesced along c)
+    int wq = w0 - 1 + j, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (wq >= 0 && wq < Wq && c < C) {
+      int sw;
+      if (s2d) {
+        sw = 2 * wq + (phase & 1);
+      } else {
+        sw = wq - pad;
+        if (sw < 0) sw = -sw;
+        if (sw >= W) sw = 2 * W - 2 - sw;
+      }
+      v = x[(((long long)n * H + sh) * W + sw) * C + c];
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  const long long plane = (long long)N * Hp * Wp;
+  for (int s = 0; s < nshift; ++s)
+    for (int j = threadIdx.y; j < 32; j += 8) {    // rows = c, cols = w' (coalesced along w')
+      int c = c0 + j, wq = w0 + threadIdx.x;
+      if (c < C && wq < Wp) {
+        float v = tile[threadIdx.x + 1 + s - origin][j];
+        float hi = tf32_rn(v);
+        long long o = (((long long)phase * nshift + s) * C + c) * plane + ((long long)n * Hp + hp) * Wp + wq;
+        th[o] = hi;
+        if (tl) tl[o] = tf32_rn(v - hi);
+      }
+    }
+}
+
+OG_API int og_prep_split_planar(const float* x, int N, int H, int W, int C, int pad, int nshift, int origin, int s2d,
+                                float* th, float* tl, cudaStream_t stream) {
+  if (pad < 0 || pad > 1 || nshift < 1 || nshift > 3 || origin < 0 || origin > 1) return (int)cudaErrorInvalidValue;
+  if (s2d && (pad || (H & 1) || (W & 1))) return (int)cudaErrorInvalidValue;
+  if ((long long)N * H * W * C == 0) return 0;
+  const int Wq = s2d ? W / 2 : W + 2 * pad, Wp = (Wq + 3) / 4 * 4, Hp = s2d ? H / 2 : H + 2 * pad;
+  dim3 grid(og_cdiv(Wp, 32), og_cdiv(C, 32), N * Hp * (s2d ? 4 : 1)), block(32, 8);
+  prep_split_planar_kernel<<<grid, block, 0, stream>>>(x, N, H, W, C, pad, Wp, nshift, origin, s2d, th, tl);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation: tf32 hi/lo split (+ optional reflection halo of 1 pixel)
+//   hi = rn_tf32(x), lo = rn_tf32(x - hi)
+// ------------------------------------------------------------------------------------------------
+
+__global__ void prep_split_kernel(const float* __restrict__ x, int N, int H, int W, int C4, int pad, int s2d,
+                                  long long total, float* __restrict__ xh, float* __restrict__ xl) {
+  // output: [N][H+2p][W+2p][C] or, for s2d, [4][N][H/2][W/2][C] with phase block (a*2+b) = x[:, a::2, b::2]
+  const int Hp = s2d ? H / 2 : H + 2 * pad, Wp = s2d ? W / 2 : W + 2 * pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    long long t = i / C4;
+    int w = (int)(t % Wp);
+    t /= Wp;
+    int h = (int)(t % Hp);
+    long long n = t / Hp;
+    int sh, sw;
+    if (s2d) {
+      int ph = (int)(n / N);
+      n -= (long long)ph * N;
+      sh = 2 * h + (ph >> 1);
+      sw = 2 * w + (ph & 1);
+    } else {
+      sh = h - pad;
+      sw = w - pad;
+      if (sh < 0) sh = -sh;
+      if (sh >= H) sh = 2 * H - 2 - sh;
+      if (sw < 0) sw = -sw;
+      if (sw >= W) sw = 2 * W - 2 - sw;
+    }
+    float4 v = ldg4(x + (((n * H + sh) * W + sw) * C4 + c) * 4);
+    float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    st4(xh + i * 4, hi);
+    if (xl) st4(xl + i * 4, make_float4(tf32_lo(v.x, hi.x), tf32_lo(v.y, hi.y), tf32_lo(v.z, hi.z), tf32_lo(v.w, hi.w)));
+  }
+}
+
+// pad = 0: plain split; pad = 1: nn.ReflectionPad2d(1) halo (model.py:67) materialised while splitting
+OG_API int og_prep_split(const float* x, int N, int H, int W, int C, int pad, int s2d, float* xh, float* xl,
+                         cudaStream_t stream) {
+  if (C % 4 || pad < 0 || pad > 1 || (s2d && (pad || (H & 1) || (W & 1)))) return (int)cudaErrorInvalidValue;
+  long long total = s2d ? (long long)N * H * W * (C / 4) : (long long)N * (H + 2 * pad) * (W + 2 * pad) * (C / 4);
+  if (total == 0) return 0;
+  long long b = (total + 255) / 256;
+  if (b > 148LL * 32) b = 148LL * 32;
+  prep_split_kernel<<<(int)b, 256, 0, stream>>>(x, N, H, W, C / 4, pad, s2d, total, xh, xl);
+  OG_RETURN_LAST_ERROR();
+}

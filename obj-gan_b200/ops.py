@@ -61,11 +61,12 @@ class PackedWeights:
         self.key = None
         self.f = None
         self.t = None
+        self.hl = {}
 
     def get(self, w, cip, kp, split, splitp, need_t):
         key = (w.data_ptr(), w._version, _param_epoch[0], cip, kp, split)
         if key != self.key:
-            self.key, self.f, self.t = key, None, None
+            self.key, self.f, self.t, self.hl = key, None, None, {}
         co, ci, kh, kw = w.shape
         if self.f is None:
             self.f = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float32)
@@ -74,6 +75,234 @@ class PackedWeights:
             self.t = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float32)
             _call("og_pack_weights", _p(w), co, ci, kh, kw, cip, kp, split, splitp, 1, _p(self.t), 0)
         return self.f, self.t
+
+    def get_hilo(self, w, cip, kp, split, splitp, transposed):
+        """tf32 hi / lo parts of the packed matrix ([tap][co][ci] when transposed else [tap][ci][co])."""
+        self.get(w, cip, kp, split, splitp, False)  # refresh the cache key
+        if transposed not in self.hl:
+            co, ci, kh, kw = w.shape
+            hi = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float32)
+            lo = torch.empty_like(hi)
+            _call("og_pack_weights", _p(w), co, ci, kh, kw, cip, kp, split, splitp, transposed, _p(hi), _p(lo))
+            self.hl[transposed] = (hi, lo)
+        return self.hl[transposed]
+
+
+# Contraction engine for the convolutions: "tf32x3" = tcgen05 tensor cores with the error-compensated
+# three-product TF32 split (fp32-level accuracy, the default and the parity mode), "tf32" = one TF32 product
+# (faster, outside the 1e-3 parity budget), "simt" = exact fp32 FMA on the CUDA cores.
+import os as _os
+CONV_ENGINE = _os.environ.get("OBJGAN_CONV", "tf32x3")
+TC_WGRAD = _os.environ.get("OBJGAN_TC_WGRAD", "1") == "1"
+TC_MIN_PIXELS = 2048       # below this the tensor-core tiles cannot fill the machine; SIMT split-K does better
+
+
+def _int_array(rows):
+    import ctypes
+    flat = [int(v) for r in rows for v in r]
+    return (ctypes.c_int * len(flat))(*flat)
+
+
+def _empty_slack(shape, device):
+    """Buffer with 512 bytes of readable slack after the last element."""
+    n = 1
+    for d in shape:
+        n *= d
+    flat = torch.empty(n + 128, device=device, dtype=torch.float32)
+    return flat[:n].view(shape)
+
+
+def _nsplit():
+    return 3 if CONV_ENGINE == "tf32x3" else 1
+
+
+def _split(x, pad=0, s2d=False):
+    """tf32 hi/lo parts of an NHWC tensor; pad=1 adds the reflection halo; s2d gives [4N, H/2, W/2, C]."""
+    n, h, w, c = x.shape
+    shape = (4 * n, h // 2, w // 2, c) if s2d else (n, h + 2 * pad, w + 2 * pad, c)
+    xh = _empty_slack(shape, x.device)
+    xl = _empty_slack(shape, x.device) if CONV_ENGINE == "tf32x3" else None
+    _call("og_prep_split", _p(x), n, h, w, c, pad, 1 if s2d else 0, _p(xh), _p(xl))
+    return xh, xl
+
+
+def _split_planar(x, pad=0, nshift=1, origin=0, s2d=False):
+    """Channel-planar tf32 hi/lo copies [copies][C][N][H'][Wp] (row pitch rounded up to 4) for the wgrad kernel;
+    copy s holds the rows shifted by (s - origin) pixels along w (zero filled); s2d adds the 4 phase blocks."""
+    n, h, w, c = x.shape
+    hh, ww = (h // 2, w // 2) if s2d else (h + 2 * pad, w + 2 * pad)
+    wp = (ww + 3) // 4 * 4
+    shape = ((4 if s2d else 1) * nshift, c, n, hh, wp)
+    th = torch.empty(shape, device=x.device, dtype=torch.float32)
+    tl = torch.empty(shape, device=x.device, dtype=torch.float32) if CONV_ENGINE == "tf32x3" else None
+    _call("og_prep_split_planar", _p(x), n, h, w, c, pad, nshift, origin, 1 if s2d else 0, _p(th), _p(tl))
+    return th, tl
+
+
+def _tc_launch(xh, xl, n, wh, wl, ntaps_w, kw_rows, y, oh, ow, k, osy, op, taps, bias=None, act=ACT_NONE):
+    """taps: (dh, dw, dn, widx) quadruples; xh is [SN, SH, SW, C] with SN = n or 4n (space-to-depth source)."""
+    sn, sh, sw, c = xh.shape
+    _, ohf, owf, kc = y.shape
+    arr = _int_array(taps)
+    import ctypes
+    _call("og_conv2d_tc", _p(xh), _p(xl), n, sn, sh, sw, c, _p(wh), _p(wl), ntaps_w, kw_rows, _p(y), oh, ow, k,
+          ohf * owf * kc, owf * kc, kc, ohf, owf, osy, osy, op[0], op[1], ctypes.addressof(arr), len(taps), _nsplit(),
+          _p(bias), act, LRELU_SLOPE)
+
+
+def _tile_n(oh, ow):
+    tw = 1
+    while tw * 2 <= ow and tw * 2 <= 16:
+        tw *= 2
+    th = 1
+    while th * 2 <= oh and tw * th * 2 <= 128:
+        th *= 2
+    return 128 // (tw * th)
+
+
+def _tc_kind(n, h, w, c, kh, kw, stride, pad, mode):
+    """Which tensor-core formulation (if any) applies to this convolution."""
+    if CONV_ENGINE not in ("tf32x3", "tf32") or _lib.DRY_RUN or c < 32:
+        return None
+    if kh == 3 and kw == 3 and stride == 1 and pad == 1:
+        oh, ow = (2 * h, 2 * w) if mode == UPSAMPLE2X else (h, w)
+        if n * oh * ow < TC_MIN_PIXELS:
+            return None
+        if mode == UPSAMPLE2X and n % _tile_n(h, w) != 0:
+            return None
+        return "s1"
+    if kh == 4 and kw == 4 and stride == 2 and pad == 1 and mode == PAD_ZERO and h % 2 == 0 and w % 2 == 0:
+        if n * (h // 2) * (w // 2) < TC_MIN_PIXELS or n % _tile_n(h // 2, w // 2) != 0:
+            return None
+        return "s2"
+    return None
+
+
+def _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act):
+    n, h, w, c = x.shape
+    wh, wl = cache.get_hilo(weight, c, kp, split, splitp, 1)          # [tap][co][ci]
+    dev = x.device
+    if kind == "s2":                                                   # 4x4 stride 2 pad 1 on space-to-depth phases
+        xh, xl = _split(x, s2d=True)
+        y = torch.empty((n, h // 2, w // 2, kp), device=dev, dtype=torch.float32)
+        taps = []
+        for kh in range(4):
+            dh, a = divmod(kh - 1, 2)
+            for kw in range(4):
+                dw, b = divmod(kw - 1, 2)
+                taps.append((dh, dw, (a * 2 + b) * n, kh * 4 + kw))
+        _tc_launch(xh, xl, n, wh, wl, 16, kp, y, h // 2, w // 2, kp, 1, (0, 0), taps, bias_p, act)
+        return y
+    if mode == PAD_REFLECT:
+        xh, xl = _split(x, 1)
+        y = torch.empty((n, h, w, kp), device=dev, dtype=torch.float32)
+        taps = [(kh, kw, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
+        _tc_launch(xh, xl, n, wh, wl, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act)
+    elif mode == PAD_ZERO:
+        xh, xl = _split(x, 0)
+        y = torch.empty((n, h, w, kp), device=dev, dtype=torch.float32)
+        taps = [(kh - 1, kw - 1, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
+        _tc_launch(xh, xl, n, wh, wl, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act)
+    else:  # UPSAMPLE2X: four output phases, taps addressed at low resolution
+        xh, xl = _split(x, 0)
+        y = torch.empty((n, 2 * h, 2 * w, kp), device=dev, dtype=torch.float32)
+        for py in range(2):
+            for px in range(2):
+                taps = [((py + kh - 1) // 2, (px + kw - 1) // 2, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
+                _tc_launch(xh, xl, n, wh, wl, 9, kp, y, h, w, kp, 2, (py, px), taps, bias_p, act)
+    return y
+
+
+def _tc_dgrad(kind, g, cache, weight, c, kp, split, splitp, mode, h, w):
+    """Input gradient on the tensor cores.  g: (N, OH, OW, kp); returns (N, h, w, c)."""
+    n = g.shape[0]
+    dev = g.device
+    wh, wl = cache.get_hilo(weight, c, kp, split, splitp, 0)          # [tap][ci][co]
+    if kind == "s2":
+        gh, gl = _split(g, 0)
+        oh, ow = g.shape[1], g.shape[2]
+        gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
+        for a in range(2):
+            for b in range(2):
+                taps = [((a + 1 - kh) // 2, (b + 1 - kw) // 2, 0, kh * 4 + kw)
+                        for kh in ((1, 3) if a == 0 else (0, 2)) for kw in ((1, 3) if b == 0 else (0, 2))]
+                _tc_launch(gh, gl, n, wh, wl, 16, c, gx, oh, ow, c, 2, (a, b), taps)
+        return gx
+    if mode == PAD_REFLECT:
+        gh, gl = _split(g, 0)
+        gpad = torch.empty((n, h + 2, w + 2, c), device=dev, dtype=torch.float32)
+        taps = [(-kh, -kw, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
+        _tc_launch(gh, gl, n, wh, wl, 9, c, gpad, h + 2, w + 2, c, 1, (0, 0), taps)
+        gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
+        _call("og_reflect_pad_bwd", _p(gpad), n, h, w, c, _p(gx))
+        return gx
+    if mode == PAD_ZERO:
+        gh, gl = _split(g, 0)
+        gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
+        taps = [(1 - kh, 1 - kw, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
+        _tc_launch(gh, gl, n, wh, wl, 9, c, gx, h, w, c, 1, (0, 0), taps)
+        return gx
+    # UPSAMPLE2X: gx[i,j] = sum_{p,q,kh,kw} g[2i+p+1-kh, 2j+q+1-kw] W[kh,kw]^T ; g read through its 4 phase blocks
+    gh, gl = _split(g, s2d=True)
+    gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
+    taps = []
+    for p_ in range(2):
+        for q_ in range(2):
+            for kh in range(3):
+                fh, pp = divmod(p_ + 1 - kh, 2)
+                for kw in range(3):
+                    fw, qq = divmod(q_ + 1 - kw, 2)
+                    taps.append((fh, fw, (pp * 2 + qq) * n, kh * 3 + kw))
+    _tc_launch(gh, gl, n, wh, wl, 9, c, gx, h, w, c, 1, (0, 0), taps)
+    return gx
+
+
+def _tc_wgrad_ok(kind, mode, oh, ow):
+    """The wgrad kernel streams 32 consecutive pixels per stage: rows of >= 32 pixels, or (for sources with the same
+    unpadded extent as the gradient grid) narrower maps addressed with (h, w) flattened."""
+    if mode == UPSAMPLE2X:
+        oh, ow = oh // 2, ow // 2
+    if ow >= 32:
+        return True
+    return mode != PAD_REFLECT and ow % 4 == 0 and (oh * ow) % 32 == 0
+
+
+def _tc_wgrad(kind, x, g, weight, c, kp, split, splitp, mode):
+    """Weight gradient on the tensor cores; returns the OIHW gradient."""
+    import ctypes
+    n, h, w, _ = x.shape
+    co, ci, kh_, kw_ = weight.shape
+    if kind == "s2":
+        xh, xl = _split_planar(x, 0, 3, 1, s2d=True)                  # 12 copies: phase * 3 + shift
+        gh, gl = _split_planar(g)
+        ent = []
+        for kh in range(4):
+            dh, a = divmod(kh - 1, 2)
+            for kw in range(4):
+                dw, b = divmod(kw - 1, 2)
+                ent.append((0, dh, (a * 2 + b) * 3 + dw + 1, kh * 4 + kw))
+        gv, xv, sh, sw, oh, ow, nt = 1, 12, h // 2, w // 2, g.shape[1], g.shape[2], 16
+    elif mode == UPSAMPLE2X:
+        xh, xl = _split_planar(x, 0, 3, 1)                            # low-res source, shifts -1, 0, +1
+        gh, gl = _split_planar(g, s2d=True)                           # 4 phase blocks of the full-res gradient
+        ent = [(p_ * 2 + q_, (p_ + kh - 1) // 2, (q_ + kw - 1) // 2 + 1, kh * 3 + kw)
+               for p_ in range(2) for q_ in range(2) for kh in range(3) for kw in range(3)]
+        gv, xv, sh, sw, oh, ow, nt = 4, 3, h, w, h, w, 9
+    else:
+        pad = 1 if mode == PAD_REFLECT else 0
+        origin = 0 if mode == PAD_REFLECT else 1   # zero-pad conv: taps at w-1, w, w+1 of the unpadded source
+        off = 0 if mode == PAD_REFLECT else -1
+        xh, xl = _split_planar(x, pad, 3, origin)
+        gh, gl = _split_planar(g)
+        ent = [(0, kh + off, kw, kh * 3 + kw) for kh in range(3) for kw in range(3)]
+        gv, xv, sh, sw, oh, ow, nt = 1, 3, h + 2 * pad, w + 2 * pad, g.shape[1], g.shape[2], 9
+    arr = _int_array(ent)
+    dwp = torch.empty(nt * kp * c, device=x.device, dtype=torch.float32)
+    _call("og_conv2d_wgrad_tc", _p(gh), _p(gl), n, oh, ow, kp, gv, _p(xh), _p(xl), sh, sw, c, xv, _p(dwp), nt,
+          ctypes.addressof(arr), len(ent), _nsplit())
+    gw = torch.empty_like(weight)
+    _call("og_unpack_wgrad", _p(dwp), co, ci, kh_, kw_, c, kp, split, splitp, _p(gw), 0, 1)
+    return gw
 
 
 def _out_hw(h, w, kh, kw, stride, pad, mode):
@@ -108,8 +337,8 @@ class _Conv2d(torch.autograd.Function):
         else:
             splitp, kp = 0, cpad(co)
         need_t = ctx.needs_input_grad[0]
-        wf, _ = cache.get(weight, c, kp, split, splitp, False)
         oh, ow = _out_hw(h, w, kh, kw, stride, pad, mode)
+        kind = _tc_kind(n, h, w, c, kh, kw, stride, pad, mode)
         bias_p = None
         if bias is not None:
             if kp == co:
@@ -118,8 +347,13 @@ class _Conv2d(torch.autograd.Function):
                 assert not split
                 bias_p = torch.zeros(kp, device=x.device, dtype=torch.float32)
                 bias_p[:co] = bias.detach()
-        y = _conv_raw(x, wf, n, h, w, c, oh, ow, kp, kh, kw, stride, pad, mode, bias_p, act,
-                      splitk=(bias is None and act == ACT_NONE))
+        if kind:
+            y = _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act)
+        else:
+            wf, _ = cache.get(weight, c, kp, split, splitp, False)
+            y = _conv_raw(x, wf, n, h, w, c, oh, ow, kp, kh, kw, stride, pad, mode, bias_p, act,
+                          splitk=(bias is None and act == ACT_NONE))
+        ctx.kind = kind
         ctx.cfg = (stride, pad, mode, act, split, splitp, kp, need_t)
         ctx.cache = cache
         ctx.has_bias = bias is not None
@@ -143,7 +377,10 @@ class _Conv2d(torch.autograd.Function):
             scratch = torch.empty(kp, device=g.device, dtype=torch.float64)
             gb = torch.empty(co, device=g.device, dtype=torch.float32)
             _call("og_channel_sum", _p(g), n * oh * ow, kp, _p(scratch), _p(gb), co, 0)
-        if ctx.needs_input_grad[0]:
+        kind = ctx.kind if kp >= 32 else None
+        if ctx.needs_input_grad[0] and kind:
+            gx = _tc_dgrad(kind, g, ctx.cache, weight, c, kp, split, splitp, mode, h, w)
+        elif ctx.needs_input_grad[0]:
             _, wt = ctx.cache.get(weight, c, kp, split, splitp, True)
             if mode == PAD_ZERO:
                 gx = _conv_raw(g, wt, n, oh, ow, kp, h, w, c, kh, kw, stride, pad, TRANSPOSED, None, ACT_NONE)
@@ -156,12 +393,14 @@ class _Conv2d(torch.autograd.Function):
                 gu = _conv_raw(g, wt, n, oh, ow, kp, 2 * h, 2 * w, c, kh, kw, 1, pad, TRANSPOSED, None, ACT_NONE)
                 gx = torch.empty_like(x)
                 _call("og_upsample2x_bwd", _p(gu), n, h, w, c, _p(gx))
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and kind and c <= 256 and TC_WGRAD and _tc_wgrad_ok(kind, mode, oh, ow):
+            gw = _tc_wgrad(kind, x, g, weight, c, kp, split, splitp, mode)
+        elif ctx.needs_input_grad[1]:
             dwp = torch.empty(kh * kw * c * kp, device=g.device, dtype=torch.float32)
             _call("og_conv2d_wgrad_simt", _p(x), n, h, w, c, h * w * c, w * c, c, _p(g), oh, ow, kp, oh * ow * kp,
                   ow * kp, kp, _p(dwp), kh, kw, stride, pad, mode)
             gw = torch.empty_like(weight)
-            _call("og_unpack_wgrad", _p(dwp), co, ci, kh, kw, c, kp, split, splitp, _p(gw), 0)
+            _call("og_unpack_wgrad", _p(dwp), co, ci, kh, kw, c, kp, split, splitp, _p(gw), 0, 0)
         return gx, gw, gb, None, None, None, None, None, None
 
 

@@ -473,7 +473,7 @@ def step_a(state: StepAState, inp: dict, *, lr=2e-4, keep=None):
                 d[k] = v
         for k, gk in zip(state.d_keys[i], grads):
             adam_step(d[k], gk, state.d_m[i][k], state.d_v[i][k], t, lr)
-        losses[f"errPatD{i}"] = float(err)
+        losses[f"errPatD{i}"] = float(err.detach())
         d_grads.append(dict(zip(state.d_keys[i], grads)))
     # (4) G update through the (already updated) PatDs
     errg = g_loss_pat(state.ds, fake, sent)

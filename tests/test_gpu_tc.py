@@ -1,0 +1,105 @@
+"""GPU tests of the tcgen05 tensor-core convolution path (conv_tc.cu) against torch-CPU fp32 convolutions
+(the oracle's arithmetic primitive) at sizes large enough for the dispatcher to pick the tensor cores.
+
+Tolerances: 3xTF32 (the parity mode) must land at fp32 rounding level (<= 2e-5 of max|ref|); a single TF32
+product is only checked loosely (it is not a parity mode)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from objgan_b200 import model, ops
+from objgan_b200.lib import ACT_NONE, PAD_REFLECT, PAD_ZERO, UPSAMPLE2X
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CASES = [
+    # cin, cout, mode, split, N, H, W   (3x3 stride 1 pad 1 unless mode is the string "s2": 4x4 stride 2 pad 1)
+    (194, 388, PAD_REFLECT, 194, 2, 64, 64),     # HmapResBlock conv1 (two N tiles of 208)
+    (194, 194, PAD_REFLECT, 0, 4, 32, 64),       # HmapResBlock conv2
+    (194, 96, UPSAMPLE2X, 48, 2, 64, 64),        # upBlock (four phases)
+    (1024, 768, PAD_ZERO, 0, 36, 16, 16),        # jointConv @16x16 (three N tiles of 256)
+    (64, 48, PAD_ZERO, 0, 2, 80, 72),            # ragged tiles: H, W not multiples of the patch
+    (40, 24, PAD_REFLECT, 0, 5, 48, 48),         # C not a multiple of 32, small N tile
+    (1024, 768, PAD_ZERO, 0, 8, 16, 16),         # jointConv on 16x16 maps (wgrad chunk = 16 x 2 pixels)
+    (96, 192, "s2", 0, 4, 64, 64),               # discriminator conv4x4 s2 (space-to-depth phases)
+    (192, 384, "s2", 0, 8, 32, 32),              # ... on 16x16 outputs
+    (384, 768, "s2", 0, 32, 16, 16),             # ... on 8x8 outputs (tiles span 2 images)
+]
+
+
+def _ref(x, w, mode):
+    if mode == "s2":
+        return F.conv2d(x, w, None, 2, 1)
+    if mode == PAD_REFLECT:
+        return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w)
+    if mode == UPSAMPLE2X:
+        return F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, None, 1, 1)
+    return F.conv2d(x, w, None, 1, 1)
+
+
+def _rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert torch.isfinite(a).all()
+    return (a - b).abs().max().item() / b.abs().max().item()
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-4), ("tf32", 4e-3)])
+@pytest.mark.parametrize("case", CASES)
+def test_tc_conv_fwd_dgrad(case, engine, tol, monkeypatch):
+    cin, cout, mode, split, N, H, W = case
+    monkeypatch.setattr(ops, "CONV_ENGINE", engine)
+    torch.manual_seed(cin + cout + H)
+    if mode == "s2":
+        m = model.Conv2dP(cin, cout, 4, 2, 1).to(DEV)
+    else:
+        m = model.Conv2dP(cin, cout, 3, 1, 1, mode=mode, split=split).to(DEV)
+    x = torch.randn(N, cin, H, W)
+    w = m.weight.detach().cpu().clone()
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    yr = _ref(xr, wr, mode)
+    gy = torch.randn_like(yr)
+    gxr, gwr = torch.autograd.grad(yr, (xr, wr), gy)
+    xg = x.to(DEV).requires_grad_(True)
+    k, st = (4, 2) if mode == "s2" else (3, 1)
+    assert ops._tc_kind(N, H, W, ops.cpad(cin), k, k, st, 1, PAD_ZERO if mode == "s2" else mode)
+    y_nhwc = m(ops.to_nhwc(xg))
+    if split:
+        sp = ops.cpad(split)
+        y = torch.cat((y_nhwc[..., :split], y_nhwc[..., sp:sp + split]), -1).permute(0, 3, 1, 2)
+        assert (y_nhwc[..., split:sp] == 0).all() and (y_nhwc[..., sp + split:] == 0).all()
+        gfull = torch.zeros_like(y_nhwc)
+        g_nhwc = gy.permute(0, 2, 3, 1).to(DEV)
+        gfull[..., :split] = g_nhwc[..., :split]
+        gfull[..., sp:sp + split] = g_nhwc[..., split:]
+        assert _rel(y, yr) <= tol, ("fwd", _rel(y, yr))
+        y_nhwc.backward(gfull)
+    else:
+        y = ops.to_nchw(y_nhwc, cout)
+        assert _rel(y, yr) <= tol, ("fwd", _rel(y, yr))
+        y.backward(gy.to(DEV))
+    assert _rel(xg.grad, gxr) <= tol, ("dgrad", _rel(xg.grad, gxr))
+    assert _rel(m.weight.grad, gwr) <= tol, ("wgrad", _rel(m.weight.grad, gwr))
+
+
+def test_prep_split_exact():
+    """hi + lo reconstructs x to 2^-21, both parts are tf32-representable, the reflection halo matches F.pad."""
+    x = torch.randn(2, 8, 6, 8, device=DEV) * 3
+    xn = ops.to_nhwc(x)
+    monkey = ops.CONV_ENGINE
+    ops.CONV_ENGINE = "tf32x3"
+    try:
+        hi, lo = ops._split(xn, 1)
+        shi, slo = ops._split(xn, s2d=True)
+    finally:
+        ops.CONV_ENGINE = monkey
+    want = F.pad(x, (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1)
+    for a in range(2):
+        for b in range(2):
+            blk = (shi + slo)[(a * 2 + b) * 2:(a * 2 + b + 1) * 2]
+            ref = x[:, :, a::2, b::2].permute(0, 2, 3, 1)
+            assert ((blk - ref).abs() <= ref.abs() * 2.0 ** -21).all()
+    assert ((hi + lo - want).abs() <= want.abs() * 2.0 ** -21).all()
+    assert ((hi.view(torch.int32) & 0x1FFF) == 0).all()
+    assert ((lo.view(torch.int32) & 0x1FFF) == 0).all()
