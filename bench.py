@@ -227,6 +227,14 @@ def run_b200(args):
     torch.cuda.synchronize()
     h2d = synth.input_bytes(host)
 
+    graphed = False
+    if not args.no_graph:
+        try:
+            tr.capture(dev)          # whole step (fwd, bwd, all-reduce, Adam+EMA) as one CUDA graph
+            graphed = True
+        except Exception as e:       # report and fall back to eager launches
+            print(f"[bench] CUDA graph capture failed, running eager: {e!r}", file=sys.stderr)
+            tr._graph = None
     for _ in range(args.warmup):
         tr.step(dev)
     sampler = ClockSampler(local)
@@ -259,7 +267,8 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "step_a_b16_256 (BASELINE configs[1]: full G_NET 64/128/256 + 3 patch Ds, batch 16/GPU)",
                    "global_batch": world * B, "words": 18, "rois": 10, "parallelism": f"dp{world}",
-                   "l2": "inputs (0.47 GB/step) and activations (>10 GB) exceed the 126 MB L2; no explicit flush"},
+                   "l2": "inputs (0.47 GB/step) and activations (>10 GB) exceed the 126 MB L2; no explicit flush",
+                   "conv_engine": __import__("objgan_b200.ops", fromlist=["x"]).CONV_ENGINE, "cuda_graph": graphed},
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_attention": roof_att,
@@ -278,6 +287,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

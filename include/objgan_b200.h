@@ -158,8 +158,11 @@ int og_reparam_bwd(const float* x, int xs, const float* eps, const float* gc, in
                    cudaStream_t stream);
 int og_bce(const float* p, long long n, float target, float weight, float* loss_accum, float* gp, cudaStream_t stream);
 int og_kl(const float* x, int xs, int B, int D, float weight, float* loss_accum, float* gx, cudaStream_t stream);
+/* step: 1-based Adam step from the host, or (step_dev != NULL) read from a device counter so that a whole training
+ * step can be replayed from a CUDA graph; og_inc_i64 bumps such a counter. */
 int og_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long long n, double lr, double b1, double b2,
-                double eps, int step, float gscale, float decay, cudaStream_t stream);
+                double eps, int step, const long long* step_dev, float gscale, float decay, cudaStream_t stream);
+int og_inc_i64(long long* counter, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -392,6 +392,7 @@ struct TcWgradParams {
   int total_chunks;
   int chunks_per_cta;
   int Kp, C;            // rows (co) and columns (ci) of each dW[t]
+  int cotiles;          // blockIdx.x = citile * cotiles + cotile
   int nsplit;
   float* dw;            // [ntaps_out][Kp][C]
   // entry e: dW[out[e]] += G(rows offset aoff[e]) * X(row offset dh[e], planar copy bvar[e])
@@ -415,7 +416,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cotile = blockIdx.x, tap = blockIdx.y;
+  const int cotile = blockIdx.x % p.cotiles, citile = blockIdx.x / p.cotiles, tap = blockIdx.y;
   const int ch_beg = blockIdx.z * p.chunks_per_cta;
   const int ch_end = min(p.total_chunks, ch_beg + p.chunks_per_cta);
   const int nk = ch_end - ch_beg;
@@ -442,7 +443,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int dh = p.dh[tap], brow = p.bvar[tap] * p.C, arow = p.aoff[tap] + cotile * TC_BM;
+      const int dh = p.dh[tap], brow = p.bvar[tap] * p.C + citile * BNW, arow = p.aoff[tap] + cotile * TC_BM;
       for (int it = 0; it < nk; ++it) {
         const int ch = ch_beg + it;
         const int wc = ch % p.wchunks;
@@ -504,7 +505,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
     const int q = warp & 3;
     const int co = cotile * TC_BM + q * 32 + lane;
     const bool row_ok = co < p.Kp;
-    float* drow = p.dw + ((long long)p.out[tap] * p.Kp + co) * p.C;
+    float* drow = p.dw + ((long long)p.out[tap] * p.Kp + co) * p.C + citile * BNW;
+    const int cleft = p.C - citile * BNW;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -514,7 +516,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
       if (row_ok) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (c + j < BNW && c + j < p.C) atomicAdd(drow + c + j, __uint_as_float(r[j]));
+          if (c + j < BNW && c + j < cleft) atomicAdd(drow + c + j, __uint_as_float(r[j]));
       }
     }
     tc_fence_before();
@@ -632,7 +634,7 @@ OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH,
 OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int OH, int OW, int Kp, int gvariants,
                               const float* xh, const float* xl, int SH, int SW, int C, int xvariants, float* dw,
                               int ntaps_out, const int* entries_host, int nentries, int nsplit, cudaStream_t stream) {
-  if (nentries < 1 || nentries > TC_MAX_TAPS || (nsplit != 1 && nsplit != 3) || C > 256) return (int)cudaErrorInvalidValue;
+  if (nentries < 1 || nentries > TC_MAX_TAPS || (nsplit != 1 && nsplit != 3)) return (int)cudaErrorInvalidValue;
   OG_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)ntaps_out * Kp * C, stream));
   if ((long long)N * OH * OW == 0) return 0;
   const int OWp = (OW + 3) / 4 * 4, SWp = (SW + 3) / 4 * 4;
@@ -655,17 +657,18 @@ OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int OH, i
     p.out[i] = entries_host[4 * i + 3];
   }
   const int cotiles = og_cdiv(Kp, TC_BM);
+  const int Cr = (C + 15) / 16 * 16;
+  const int BNsel = Cr <= 32 ? 32 : Cr <= 64 ? 64 : Cr <= 112 ? 112 : Cr <= 208 ? 208 : 256;
+  const int citiles = og_cdiv(C, BNsel);
+  p.cotiles = cotiles;
   // pixel splits: ~2 waves of CTAs over 148 SMs, at least 8 chunks per CTA
-  int splits = og_cdiv(296, cotiles * nentries);
+  int splits = og_cdiv(296, cotiles * citiles * nentries);
   int maxs = p.total_chunks / 8;
   if (maxs < 1) maxs = 1;
   if (splits > maxs) splits = maxs;
   p.chunks_per_cta = og_cdiv(p.total_chunks, splits);
   splits = og_cdiv(p.total_chunks, p.chunks_per_cta);
-  dim3 grid(cotiles, nentries, splits);
-
-  const int Cr = (C + 15) / 16 * 16;
-  const int BNsel = Cr <= 32 ? 32 : Cr <= 64 ? 64 : Cr <= 112 ? 112 : Cr <= 208 ? 208 : 256;
+  dim3 grid(cotiles * citiles, nentries, splits);
   CUtensorMap mgh, mgl, mxh, mxl;
   unsigned long long gd[4] = {(unsigned long long)OW, (unsigned long long)OH, (unsigned long long)N,
                               (unsigned long long)Kp * gvariants};

@@ -429,7 +429,13 @@ OG_API int og_kl(const float* x, int xs, int B, int D, float weight, float* loss
 // ---------------------------------------------------------------------------------------------
 __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, float* __restrict__ avg, long long n, float lr, float b1,
-                                float b2, float eps, float bc1, float sqrt_bc2, float gscale, float decay) {
+                                float b2, float eps, double b1d, double b2d, int step_host,
+                                const long long* __restrict__ step_dev, float gscale, float decay) {
+  // bias corrections in double, like torch.optim.Adam's python scalars; the step count comes from the host or,
+  // when the step is replayed from a CUDA graph, from a device counter (og_inc_i64 bumps it before this launch)
+  const double st = step_dev ? (double)(*step_dev) : (double)step_host;
+  const float bc1 = (float)(1.0 - pow(b1d, st));
+  const float sqrt_bc2 = (float)sqrt(1.0 - pow(b2d, st));
   const float step_size = lr / bc1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -445,12 +451,16 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
   }
 }
 OG_API int og_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long long n, double lr, double b1,
-                       double b2, double eps, int step, float gscale, float decay, cudaStream_t stream) {
+                       double b2, double eps, int step, const long long* step_dev, float gscale, float decay,
+                       cudaStream_t stream) {
   if (n == 0) return 0;
-  // bias corrections in double on the host, like torch.optim.Adam's python scalars
-  double bc1 = 1.0 - pow(b1, (double)step);
-  double sqrt_bc2 = sqrt(1.0 - pow(b2, (double)step));
-  adam_ema_kernel<<<eblocks(n), 256, 0, stream>>>(p, g, m, v, avg, n, (float)lr, (float)b1, (float)b2, (float)eps,
-                                                   (float)bc1, (float)sqrt_bc2, gscale, decay);
+  adam_ema_kernel<<<eblocks(n), 256, 0, stream>>>(p, g, m, v, avg, n, (float)lr, (float)b1, (float)b2, (float)eps, b1, b2,
+                                                   step, step_dev, gscale, decay);
+  OG_RETURN_LAST_ERROR();
+}
+
+__global__ void inc_i64_kernel(long long* c) { *c += 1; }
+OG_API int og_inc_i64(long long* counter, cudaStream_t stream) {
+  inc_i64_kernel<<<1, 1, 0, stream>>>(counter);
   OG_RETURN_LAST_ERROR();
 }

@@ -162,7 +162,7 @@ def _tile_n(oh, ow):
 
 def _tc_kind(n, h, w, c, kh, kw, stride, pad, mode):
     """Which tensor-core formulation (if any) applies to this convolution."""
-    if CONV_ENGINE not in ("tf32x3", "tf32") or _lib.DRY_RUN or c < 32:
+    if CONV_ENGINE not in ("tf32x3", "tf32") or _lib.DRY_RUN:
         return None
     if kh == 3 and kw == 3 and stride == 1 and pad == 1:
         oh, ow = (2 * h, 2 * w) if mode == UPSAMPLE2X else (h, w)
@@ -377,7 +377,7 @@ class _Conv2d(torch.autograd.Function):
             scratch = torch.empty(kp, device=g.device, dtype=torch.float64)
             gb = torch.empty(co, device=g.device, dtype=torch.float32)
             _call("og_channel_sum", _p(g), n * oh * ow, kp, _p(scratch), _p(gb), co, 0)
-        kind = ctx.kind if kp >= 32 else None
+        kind = ctx.kind
         if ctx.needs_input_grad[0] and kind:
             gx = _tc_dgrad(kind, g, ctx.cache, weight, c, kp, split, splitp, mode, h, w)
         elif ctx.needs_input_grad[0]:
@@ -393,7 +393,7 @@ class _Conv2d(torch.autograd.Function):
                 gu = _conv_raw(g, wt, n, oh, ow, kp, 2 * h, 2 * w, c, kh, kw, 1, pad, TRANSPOSED, None, ACT_NONE)
                 gx = torch.empty_like(x)
                 _call("og_upsample2x_bwd", _p(gu), n, h, w, c, _p(gx))
-        if ctx.needs_input_grad[1] and kind and c <= 256 and TC_WGRAD and _tc_wgrad_ok(kind, mode, oh, ow):
+        if ctx.needs_input_grad[1] and kind and TC_WGRAD and _tc_wgrad_ok(kind, mode, oh, ow):
             gw = _tc_wgrad(kind, x, g, weight, c, kp, split, splitp, mode)
         elif ctx.needs_input_grad[1]:
             dwp = torch.empty(kh * kw * c * kp, device=g.device, dtype=torch.float32)
@@ -912,9 +912,12 @@ def roi_align_avg(features, rois, ah, aw, scale):
 
 
 # --------------------------------------------------------------------------------------------------
-def adam_ema_(p, g, m, v, avg, step, *, lr=2e-4, b1=0.5, b2=0.999, eps=1e-8, gscale=1.0, decay=0.999):
-    """Fused Adam (+EMA) over flat fp32 buffers, in place."""
-    _chk(p, g, m, v, avg)
+def adam_ema_(p, g, m, v, avg, step, *, lr=2e-4, b1=0.5, b2=0.999, eps=1e-8, gscale=1.0, decay=0.999, step_dev=None):
+    """Fused Adam (+EMA) over flat fp32 buffers, in place.  ``step_dev`` (int64 device scalar) replaces the host
+    step count and is incremented first, which keeps the call replayable from a CUDA graph."""
+    _chk(p, g, m, v, avg, step_dev)
+    if step_dev is not None:
+        _call("og_inc_i64", _p(step_dev))
     _call("og_adam_ema", _p(p), _p(g), _p(m), _p(v), _p(avg), p.numel(), float(lr), float(b1), float(b2), float(eps),
-          int(step), float(gscale), float(decay))
+          int(step), _p(step_dev), float(gscale), float(decay))
     bump_param_epoch()

@@ -45,6 +45,7 @@ class FlatBucket:
         self.avg = self.flat.clone() if ema else None
         self.offsets = offs
         self.step = 0
+        self.step_dev = torch.zeros((), device=dev, dtype=torch.int64)   # device mirror (CUDA-graph replay)
         ops.bump_param_epoch()
 
     def zero_grad(self):
@@ -57,7 +58,7 @@ class FlatBucket:
     def adam(self, lr, gscale=1.0):
         self.step += 1
         ops.adam_ema_(self.flat, self.grad, self.m, self.v, self.avg, self.step, lr=lr, b1=0.5, b2=0.999, eps=1e-8,
-                      gscale=gscale, decay=0.999)
+                      gscale=gscale, decay=0.999, step_dev=self.step_dev)
 
     def ema_state_dict(self):
         """EMA weights keyed like ``module.state_dict()`` (what the reference saves as netG_epoch_%d.pth,
@@ -136,7 +137,60 @@ class StepATrainer:
                  inp["mask"], inp["hmaps"], inp["rois"], inp["fm_rois"], inp["num_rois"], inp["bt_masks"],
                  inp["fm_bt_masks"], inp["glb_max_num_roi"])
 
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, inp: dict, warmup: int = 2) -> None:
+        """Capture one whole Step-A step (forward, backward, all-reduce, optimiser) into a CUDA graph.  ``inp`` fixes
+        the shapes; later ``step`` calls copy their inputs into the captured static buffers and replay.  The ~1200
+        kernel launches of a step then cost one graph launch instead of ~0.1 ms of Python/ctypes each."""
+        from . import lib as _l
+        self._static = {}
+        for k, v in inp.items():
+            if torch.is_tensor(v):
+                self._static[k] = v.clone()
+            elif isinstance(v, (list, tuple)):
+                self._static[k] = [t.clone() for t in v]
+            else:
+                self._static[k] = v
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):          # allocator / kernel-attribute / packed-weight-cache steady state
+                self._eager_step(self._static)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        n0 = _l.get().launches
+        with torch.cuda.graph(self._graph):
+            self._static_out = self._eager_step(self._static)
+        self.launches_per_step = _l.get().launches - n0
+        ops.bump_param_epoch()
+
+    def _load_static(self, inp: dict) -> None:
+        for k, v in inp.items():
+            dst = self._static.get(k)
+            if torch.is_tensor(v) and torch.is_tensor(dst):
+                if dst.data_ptr() != v.data_ptr():
+                    dst.copy_(v, non_blocking=True)
+            elif isinstance(v, (list, tuple)):
+                for d, t in zip(dst, v):
+                    if d.data_ptr() != t.data_ptr():
+                        d.copy_(t, non_blocking=True)
+
     def step(self, inp: dict) -> dict:
+        """One Step-A step.  Eager, or a replay of the captured CUDA graph after ``capture``."""
+        if getattr(self, "_graph", None) is None:
+            return self._eager_step(inp)
+        from . import lib as _l
+        self._load_static(inp)
+        self._graph.replay()
+        _l.get().launches += self.launches_per_step
+        for b in [self.bG, *self.bD]:
+            b.step += 1
+        ops.bump_param_epoch()
+        return self._static_out
+
+    def _eager_step(self, inp: dict) -> dict:
         """One Step-A step on device-resident inputs.  Returns losses as device scalars."""
         lr_d, lr_g = cfg.TRAIN.DISCRIMINATOR_LR, cfg.TRAIN.GENERATOR_LR
         gs = 1.0 / self.world
@@ -178,7 +232,11 @@ class StepATrainer:
     def step_from_host(self, host_inp: dict) -> float:
         """The public end-to-end call: pinned host batch in, scalar generator loss out (forces the
         device->host read of the step's result)."""
-        out = self.step(self.to_device(host_inp))
+        if getattr(self, "_graph", None) is not None:
+            self._load_static(host_inp)        # pinned host -> captured static device buffers (async H2D)
+            out = self.step(self._static)
+        else:
+            out = self.step(self.to_device(host_inp))
         return float((out["errG"] + out["kl"]).item())
 
 

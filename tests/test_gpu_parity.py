@@ -37,12 +37,12 @@ def rel_l2(a, b):
     return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
 
 
-def close_grad(a, b, what=""):
+def close_grad(a, b, what="", l2=5e-3, mx=3e-2):
     """Network-level gradients: LeakyReLU / max sign flips on near-zero pre-activations and tiny-batch BatchNorm make
     a handful of entries jump when the summation order changes (the reference does this to itself, DESIGN.md
     "Parity budget"), so these are judged in the L2 norm (5e-3) with a loose max-norm guard (3e-2)."""
-    assert rel_l2(a, b) <= 5e-3, (what, "l2", rel_l2(a, b))
-    assert rel(a, b) <= 3e-2, (what, "max", rel(a, b))
+    assert rel_l2(a, b) <= l2, (what, "l2", rel_l2(a, b))
+    assert rel(a, b) <= mx, (what, "max", rel(a, b))
 
 
 def nhwc(x):  # NCHW cpu -> NHWC(+pad) cuda
@@ -380,7 +380,11 @@ def test_g_net_forward_parity():
             assert int(sd2[k]) == int(sd[k]) == 1
 
 
-def test_pat_d_loss_parity():
+@pytest.mark.parametrize("engine,l2,mx", [("simt", 5e-3, 3e-2), ("tf32x3", 3e-2, 1e-1)])
+def test_pat_d_loss_parity(engine, l2, mx, monkeypatch):
+    """simt = exact fp32 contractions (strict); tf32x3 = tensor cores, whose ~1e-5 per-conv rounding is amplified by
+    the LeakyReLU / BatchNorm(B=4) chain like any other perturbation (DESIGN.md "Parity budget")."""
+    monkeypatch.setattr(ops, "CONV_ENGINE", engine)
     torch.manual_seed(12)
     d = model.PAT_D_NET128()
     d.apply(model.weights_init)
@@ -397,7 +401,7 @@ def test_pat_d_loss_parity():
     err.backward()
     params = dict(d.named_parameters())
     for k, g in zip(keys, grads):
-        close_grad(params[k].grad, g, what=k)
+        close_grad(params[k].grad, g, what=k, l2=l2, mx=mx)
 
 
 def test_adam_ema_kernel():
@@ -457,8 +461,8 @@ def test_step_a_parity(engine, cos_min, l2_max, monkeypatch):
             assert ((dp[k].detach().cpu() - state.ds[i][k])[sel]).abs().max().item() < 5e-5, (i, k)
         sd = d.state_dict()
         for k in sd:
-            if "running" in k:
-                close(sd[k], state.ds[i][k], 1e-3, what=k)
+            if "running" in k:  # batch means are cancellation-heavy: relative-to-max error of a near-zero mean
+                close(sd[k], state.ds[i][k], 1e-3 if engine == "simt" else 2e-2, what=k)
     ema = t.bG.ema_state_dict()
     for k in state.g_keys:
         gr = keep["g_grads"][k]
@@ -469,3 +473,22 @@ def test_step_a_parity(engine, cos_min, l2_max, monkeypatch):
         assert ((ema[k].cpu() - state.g_avg[k])[sel]).abs().max().item() < 1e-6, k
         moved = (gparams[k].detach().cpu() - p0[k]).abs().max().item()
         assert moved > 1e-5, k   # the optimiser really stepped
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The captured whole-step CUDA graph computes the same step as eager launches (same seeds, same inputs)."""
+    inp = synth.make_inputs(2, seed=8, parity=True)
+    a = trainer.StepATrainer(device=DEV, seed=5)
+    b = trainer.StepATrainer(device=DEV, seed=5)
+    da, db = a.to_device(inp), b.to_device(inp)
+    for _ in range(3):
+        oa = a.step(da)
+    b.capture(db, warmup=2)       # two eager warm-up steps, then the capture itself (not executed)
+    ob = b.step(db)               # third step = first replay
+    torch.cuda.synchronize()
+    assert b.launches_per_step > 500
+    for k in ("errPatD0", "errPatD1", "errPatD2", "errG", "kl"):
+        assert abs(float(oa[k]) - float(ob[k])) <= 2e-2 * max(1.0, abs(float(oa[k]))), k
+    for i in range(3):
+        close(ob["fake_imgs"][i], oa["fake_imgs"][i], 2e-2, what=f"fake{i}")
+    assert int(b.bG.step_dev) == 3 and b.bG.step == 3

@@ -25,6 +25,9 @@ CASES = [
     (96, 192, "s2", 0, 4, 64, 64),               # discriminator conv4x4 s2 (space-to-depth phases)
     (192, 384, "s2", 0, 8, 32, 32),              # ... on 16x16 outputs
     (384, 768, "s2", 0, 32, 16, 16),             # ... on 8x8 outputs (tiles span 2 images)
+    (48, 3, PAD_ZERO, 0, 2, 64, 64),             # GET_IMAGE_G: 3 output channels (dgrad reads an 8-channel source)
+    (3, 96, "s2", 0, 4, 64, 64),                 # discriminator first layer: 3 (->8) input channels
+    (80, 24, PAD_REFLECT, 0, 2, 64, 64),         # G_HMAP conv3x3
 ]
 
 
