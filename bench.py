@@ -141,10 +141,18 @@ def conv_roofline(hbm, bf16_tf, src):
     flops = 2.0 * B * H * H * (9 * C) * (2 * C)          # algorithmic, unpadded
     achieved = flops / (ms * 1e-3) / 1e12
     peak = bf16_tf / 2.0                                   # tf32 dense = half the bf16 rate (nominal 1.1 vs 2.25 PF)
-    return {"bound": "tensor", "kernel": "conv_gemm_kernel<8> (res-block conv1 194->388 @128x128, B=16)",
+    from objgan_b200 import ops as _ops
+    eng = _ops.CONV_ENGINE
+    kname = {"simt": "conv_gemm_kernel<8> (fp32 FMA)", "tf32": "conv_tc2_kernel<208> (tcgen05 kind::tf32, 1 product)",
+             "tf32x3": "conv_tc2_kernel<208> (tcgen05 kind::tf32, 3xTF32 error-compensated)"}[eng]
+    note = {"simt": "CUDA-core fp32 path", "tf32": "single TF32 product (not the parity mode)",
+            "tf32x3": "3 MMAs per algorithmic product, so frac <= 1/3 by construction; prep_split pass included"}[eng]
+    return {"bound": "tensor", "kernel": kname + " + prep_split: res-block conv1 194->388 3x3 @128x128, B=16",
             "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-            "traffic": None, "ms_per_launch": round(ms, 3),
-            "peak_source": f"{src} bf16 cuBLAS burst / 2 (tf32:bf16 nominal ratio); kernel computes in fp32 on CUDA cores"}
+            "traffic": 1.267e9 if eng != "simt" else None, "ms_per_launch": round(ms, 3),
+            "algorithmic_flops_per_launch": flops,
+            "peak_source": f"{src} bf16 cuBLAS burst / 2 (tf32:bf16 nominal ratio); {note}; traffic = dram read+write of the "
+                           "conv kernel from profiles/r01_ncu_conv_tc_summary.md (single-tile variant)"}
 
 
 def attn_roofline(hbm, src):

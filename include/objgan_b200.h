@@ -60,6 +60,15 @@ int og_conv2d_simt(const float* x, int N, int H, int W, int C, long long xsn, lo
 int og_conv2d_wgrad_simt(const float* x, int N, int H, int W, int C, long long xsn, long long xsh, long long xsw,
                          const float* g, int OH, int OW, int K, long long gsn, long long gsh, long long gsw,
                          float* dw_packed, int KH, int KW, int stride, int pad, int mode, cudaStream_t stream);
+/* <= 8 output channels with a long reduction (the k4 s2 p0 logit heads, ref: model.py:1031-1033): dot-product
+ * kernels instead of GEMM tiles.  Contiguous NHWC, zero padding, output channels padded to 8, wpacked [(kh,kw,ci)][8]. */
+int og_conv2d_narrow_fwd(const float* x, int N, int H, int W, int C, const float* wpacked, float* y, int OH, int OW,
+                         int KH, int KW, int stride, int pad, const float* bias, int act, float slope,
+                         cudaStream_t stream);
+int og_conv2d_narrow_dgrad(const float* g, int N, int H, int W, int C, const float* wpacked, float* gx, int OH, int OW,
+                           int KH, int KW, int stride, int pad, cudaStream_t stream);
+int og_conv2d_narrow_wgrad(const float* x, int N, int H, int W, int C, const float* g, float* dw_packed, int OH, int OW,
+                           int KH, int KW, int stride, int pad, cudaStream_t stream);
 /* OIHW parameter (state_dict layout) <-> kernel-native matrices.  split/splitp: GLU halves of the
  * output channels are each padded to splitp.  transposed=1 gives the dgrad operand.  out_lo != NULL also writes
  * the tf32 hi/lo split used by the tensor-core path. */

@@ -74,18 +74,24 @@ OG_API int og_words_proj_bwd(const float* words, const float* W, const float* gs
 // mask: [B][L] bytes (1 = padding word) or null.  wc: [B][Q][cs] (pad lanes zeroed), attn: [B][L][Q].
 // Mask quirk (ref: GlobalAttention.py:108): row (b, q) uses the caption mask of sample (b*Q + q) mod B.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ATT_Q) att_general_fwd_kernel(const float* __restrict__ h,
+template <int LM>
+__global__ void __launch_bounds__(ATT_Q, 8) att_general_fwd_kernel(const float* __restrict__ h,
                                                                 const float* __restrict__ src,
                                                                 const unsigned char* __restrict__ mask, int B, int Q,
                                                                 int idf, int cs, int L, float* __restrict__ wc,
                                                                 float* __restrict__ attn) {
-  extern __shared__ float smem[];
+  // The word projections src[c][0..L) live in shared memory as rows of LM floats (zero padded) and are read with
+  // 128-bit broadcast loads: one LDS.128 feeds four FMAs, otherwise the kernel is LSU-issue bound, not HBM bound.
+  extern __shared__ __align__(16) float smem[];
   const int pitch = cs + 1;
-  float* tile = smem;                    // [ATT_Q][pitch]
-  float* ssrc = smem + ATT_Q * pitch;    // [idf][L]
+  float* ssrc = smem;                    // [idf][LM]
+  float* tile = smem + idf * LM;         // [ATT_Q][pitch]
   const int b = blockIdx.y, q0 = blockIdx.x * ATT_Q, t = threadIdx.x;
   const int nq = min(ATT_Q, Q - q0);
-  for (int i = t; i < idf * L; i += ATT_Q) ssrc[i] = src[(long long)b * idf * L + i];
+  for (int i = t; i < idf * LM; i += ATT_Q) {
+    int c = i / LM, l = i - c * LM;
+    ssrc[i] = l < L ? src[((long long)b * idf + c) * L + l] : 0.f;
+  }
   const float* hb = h + ((long long)b * Q + q0) * cs;
   for (int i = t; i < nq * cs / 4; i += ATT_Q) {
     float4 v = ldg4(hb + i * 4);
@@ -95,49 +101,57 @@ __global__ void __launch_bounds__(ATT_Q) att_general_fwd_kernel(const float* __r
   }
   __syncthreads();
   if (t < nq) {
-    float s[LMAX];
+    float s[LM];
 #pragma unroll
-    for (int l = 0; l < LMAX; ++l) s[l] = 0.f;
+    for (int l = 0; l < LM; ++l) s[l] = 0.f;
     float* row = tile + t * pitch;
     for (int c = 0; c < idf; ++c) {
-      float hv = row[c];
-      const float* sr = ssrc + c * L;
+      const float hv = row[c];
+      const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
 #pragma unroll
-      for (int l = 0; l < LMAX; ++l)
-        if (l < L) s[l] = fmaf(hv, sr[l], s[l]);
+      for (int l4 = 0; l4 < LM / 4; ++l4) {
+        const float4 w = sr[l4];
+        s[4 * l4] = fmaf(hv, w.x, s[4 * l4]);
+        s[4 * l4 + 1] = fmaf(hv, w.y, s[4 * l4 + 1]);
+        s[4 * l4 + 2] = fmaf(hv, w.z, s[4 * l4 + 2]);
+        s[4 * l4 + 3] = fmaf(hv, w.w, s[4 * l4 + 3]);
+      }
     }
     const int q = q0 + t;
     float mx = -INFINITY;
     if (mask) {
       const unsigned char* mr = mask + (((long long)b * Q + q) % B) * L;
 #pragma unroll
-      for (int l = 0; l < LMAX; ++l)
+      for (int l = 0; l < LM; ++l)
         if (l < L && mr[l]) s[l] = -INFINITY;
     }
 #pragma unroll
-    for (int l = 0; l < LMAX; ++l)
+    for (int l = 0; l < LM; ++l)
       if (l < L) mx = fmaxf(mx, s[l]);
     float sum = 0.f;
 #pragma unroll
-    for (int l = 0; l < LMAX; ++l)
-      if (l < L) {
-        s[l] = expf(s[l] - mx);
-        sum += s[l];
-      }
+    for (int l = 0; l < LM; ++l) {
+      s[l] = l < L ? expf(s[l] - mx) : 0.f;
+      sum += s[l];
+    }
     const float inv = 1.f / sum;
 #pragma unroll
-    for (int l = 0; l < LMAX; ++l)
-      if (l < L) {
-        s[l] *= inv;
-        attn[((long long)b * L + l) * Q + q] = s[l];
-      }
+    for (int l = 0; l < LM; ++l) {
+      s[l] *= inv;
+      if (l < L) attn[((long long)b * L + l) * Q + q] = s[l];
+    }
     for (int c = 0; c < cs; ++c) {
       float acc = 0.f;
       if (c < idf) {
-        const float* sr = ssrc + c * L;
+        const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
 #pragma unroll
-        for (int l = 0; l < LMAX; ++l)
-          if (l < L) acc = fmaf(sr[l], s[l], acc);
+        for (int l4 = 0; l4 < LM / 4; ++l4) {
+          const float4 w = sr[l4];
+          acc = fmaf(w.x, s[4 * l4], acc);
+          acc = fmaf(w.y, s[4 * l4 + 1], acc);
+          acc = fmaf(w.z, s[4 * l4 + 2], acc);
+          acc = fmaf(w.w, s[4 * l4 + 3], acc);
+        }
       }
       row[c] = acc;
     }
@@ -155,10 +169,16 @@ OG_API int og_att_general_fwd(const float* h, const float* src, const unsigned c
                               int cs, int L, float* wc, float* attn, cudaStream_t stream) {
   if (L > LMAX || cs % 4 || idf > cs) return (int)cudaErrorInvalidValue;
   if (B == 0 || Q == 0) return 0;
-  size_t sm = sizeof(float) * (ATT_Q * (cs + 1) + idf * L);
-  OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const int LMsel = L <= 20 ? 20 : LMAX;
+  size_t sm = sizeof(float) * (ATT_Q * (cs + 1) + idf * LMsel);
   dim3 grid(og_cdiv(Q, ATT_Q), B);
-  att_general_fwd_kernel<<<grid, ATT_Q, sm, stream>>>(h, src, mask, B, Q, idf, cs, L, wc, attn);
+  if (L <= 20) {   // captions of the hot path have 12..18 words: keep the per-thread score vector small
+    OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    att_general_fwd_kernel<20><<<grid, ATT_Q, sm, stream>>>(h, src, mask, B, Q, idf, cs, L, wc, attn);
+  } else {
+    OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    att_general_fwd_kernel<LMAX><<<grid, ATT_Q, sm, stream>>>(h, src, mask, B, Q, idf, cs, L, wc, attn);
+  }
   OG_RETURN_LAST_ERROR();
 }
 

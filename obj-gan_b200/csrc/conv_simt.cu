@@ -372,6 +372,119 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Co, int Ci
 }
 
 // ---------------------------------------------------------------------------------------------
+// "narrow" convolutions: at most 8 output channels and a long reduction (the k4 s2 p0 logit heads of
+// D_GET_LOGITS, model.py:1031-1033: 768 -> 1 on 16x16 / 8x8 / 4x4 maps).  A GEMM tile is the wrong shape for
+// them (7 CTAs, 1536 k-steps each); these are dot products: one warp per output pixel in the forward,
+// one thread per input element in dgrad, one thread per weight row in wgrad.  Weights: packed [(kh,kw,ci)][8].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_narrow_fwd_kernel(const float* __restrict__ x, int N, int H, int W, int C,
+                                                              const float* __restrict__ w, float* __restrict__ y,
+                                                              int OH, int OW, int KH, int KW, int stride, int pad,
+                                                              const float* __restrict__ bias, int act, float slope) {
+  const int lane = threadIdx.x & 31;
+  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pix >= (long long)N * OH * OW) return;
+  const int n = (int)(pix / (OH * OW));
+  const int rem = (int)(pix - (long long)n * OH * OW);
+  const int oh = rem / OW, ow = rem - oh * OW;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int C4 = C >> 2;
+  for (int kh = 0; kh < KH; ++kh) {
+    const int ih = oh * stride + kh - pad;
+    if (ih < 0 || ih >= H) continue;
+    for (int kw = 0; kw < KW; ++kw) {
+      const int iw = ow * stride + kw - pad;
+      if (iw < 0 || iw >= W) continue;
+      const float* xp = x + (((long long)n * H + ih) * W + iw) * C;
+      const float* wp = w + (long long)(kh * KW + kw) * C * 8;
+      for (int c4 = lane; c4 < C4; c4 += 32) {
+        const float4 xv = ldg4(xp + c4 * 4);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 w0 = ldg4(wp + (c4 * 4 + k) * 8), w1 = ldg4(wp + (c4 * 4 + k) * 8 + 4);
+          acc[0] = fmaf(xs[k], w0.x, acc[0]); acc[1] = fmaf(xs[k], w0.y, acc[1]);
+          acc[2] = fmaf(xs[k], w0.z, acc[2]); acc[3] = fmaf(xs[k], w0.w, acc[3]);
+          acc[4] = fmaf(xs[k], w1.x, acc[4]); acc[5] = fmaf(xs[k], w1.y, acc[5]);
+          acc[6] = fmaf(xs[k], w1.z, acc[6]); acc[7] = fmaf(xs[k], w1.w, acc[7]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]);
+  if (lane < 8) {
+    float v = acc[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j)
+      if (lane == j) v = acc[j];
+    if (bias) v += bias[lane];
+    y[pix * 8 + lane] = apply_act(v, act, slope);
+  }
+}
+
+// gx[n,ih,iw,ci] = sum_{kh,kw: (ih+pad-kh) % stride == 0} sum_co g[n,oh,ow,co] * w[(kh,kw,ci)][co]
+__global__ void conv_narrow_dgrad_kernel(const float* __restrict__ g, int N, int H, int W, int C,
+                                         const float* __restrict__ w, float* __restrict__ gx, int OH, int OW, int KH,
+                                         int KW, int stride, int pad, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % C);
+    long long t = i / C;
+    const int iw = (int)(t % W);
+    t /= W;
+    const int ih = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc = 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      const int th = ih + pad - kh;
+      if (th < 0 || th % stride) continue;
+      const int oh = th / stride;
+      if (oh >= OH) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int tw = iw + pad - kw;
+        if (tw < 0 || tw % stride) continue;
+        const int ow = tw / stride;
+        if (ow >= OW) continue;
+        const float* gp = g + (((long long)n * OH + oh) * OW + ow) * 8;
+        const float* wp = w + ((long long)(kh * KW + kw) * C + ci) * 8;
+        const float4 g0 = ldg4(gp), g1 = ldg4(gp + 4), w0 = ldg4(wp), w1 = ldg4(wp + 4);
+        acc += g0.x * w0.x + g0.y * w0.y + g0.z * w0.z + g0.w * w0.w + g1.x * w1.x + g1.y * w1.y + g1.z * w1.z +
+               g1.w * w1.w;
+      }
+    }
+    gx[i] = acc;
+  }
+}
+
+// dw[(kh,kw,ci)][co] = sum_{n,oh,ow} x[n,ih,iw,ci] * g[n,oh,ow,co]
+__global__ void conv_narrow_wgrad_kernel(const float* __restrict__ x, int N, int H, int W, int C,
+                                         const float* __restrict__ g, float* __restrict__ dw, int OH, int OW, int KH,
+                                         int KW, int stride, int pad, int R) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int ci = r % C, tap = r / C, kh = tap / KW, kw = tap - kh * KW;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int n = 0; n < N; ++n)
+    for (int oh = 0; oh < OH; ++oh) {
+      const int ih = oh * stride + kh - pad;
+      if (ih < 0 || ih >= H) continue;
+      for (int ow = 0; ow < OW; ++ow) {
+        const int iw = ow * stride + kw - pad;
+        if (iw < 0 || iw >= W) continue;
+        const float xv = __ldg(x + (((long long)n * H + ih) * W + iw) * C + ci);
+        const float* gp = g + (((long long)n * OH + oh) * OW + ow) * 8;
+        const float4 g0 = ldg4(gp), g1 = ldg4(gp + 4);
+        acc[0] = fmaf(xv, g0.x, acc[0]); acc[1] = fmaf(xv, g0.y, acc[1]); acc[2] = fmaf(xv, g0.z, acc[2]);
+        acc[3] = fmaf(xv, g0.w, acc[3]); acc[4] = fmaf(xv, g1.x, acc[4]); acc[5] = fmaf(xv, g1.y, acc[5]);
+        acc[6] = fmaf(xv, g1.z, acc[6]); acc[7] = fmaf(xv, g1.w, acc[7]);
+      }
+    }
+  st4(dw + (long long)r * 8, make_float4(acc[0], acc[1], acc[2], acc[3]));
+  st4(dw + (long long)r * 8 + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+}
+
+// ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
 static int pick_splits(long long tiles, int nk, int want_ctas) {
@@ -468,5 +581,32 @@ OG_API int og_unpack_wgrad(const float* dw_packed, int Co, int Ci, int KH, int K
   if (blocks > 148 * 16) blocks = 148 * 16;
   unpack_wgrad_kernel<<<blocks, 256, 0, stream>>>(dw_packed, Co, Ci, KH, KW, Cip, Kp, split, splitp, grad_oihw,
                                                   accumulate, transposed);
+  OG_RETURN_LAST_ERROR();
+}
+
+// contiguous NHWC tensors, zero padding, output channels padded to exactly 8; wpacked = [(kh,kw,ci)][8]
+OG_API int og_conv2d_narrow_fwd(const float* x, int N, int H, int W, int C, const float* wpacked, float* y, int OH,
+                                int OW, int KH, int KW, int stride, int pad, const float* bias, int act, float slope,
+                                cudaStream_t stream) {
+  if (C % 4) return (int)cudaErrorInvalidValue;
+  long long pix = (long long)N * OH * OW;
+  if (pix == 0) return 0;
+  conv_narrow_fwd_kernel<<<og_cdiv(pix, 8), 256, 0, stream>>>(x, N, H, W, C, wpacked, y, OH, OW, KH, KW, stride, pad,
+                                                              bias, act, slope);
+  OG_RETURN_LAST_ERROR();
+}
+OG_API int og_conv2d_narrow_dgrad(const float* g, int N, int H, int W, int C, const float* wpacked, float* gx, int OH,
+                                  int OW, int KH, int KW, int stride, int pad, cudaStream_t stream) {
+  long long total = (long long)N * H * W * C;
+  if (total == 0) return 0;
+  long long b = (total + 255) / 256;
+  if (b > 148LL * 32) b = 148LL * 32;
+  conv_narrow_dgrad_kernel<<<(int)b, 256, 0, stream>>>(g, N, H, W, C, wpacked, gx, OH, OW, KH, KW, stride, pad, total);
+  OG_RETURN_LAST_ERROR();
+}
+OG_API int og_conv2d_narrow_wgrad(const float* x, int N, int H, int W, int C, const float* g, float* dw_packed, int OH,
+                                  int OW, int KH, int KW, int stride, int pad, cudaStream_t stream) {
+  int R = KH * KW * C;
+  conv_narrow_wgrad_kernel<<<og_cdiv(R, 128), 128, 0, stream>>>(x, N, H, W, C, g, dw_packed, OH, OW, KH, KW, stride, pad, R);
   OG_RETURN_LAST_ERROR();
 }

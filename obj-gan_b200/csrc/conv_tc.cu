@@ -58,6 +58,7 @@ struct TcParams {
   const float* bias;        // [K] or null
   int act;
   float slope;
+  int ksplit;               // > 1: gridDim.z CTAs share one output tile, each reduces a slice of the (tap, chunk) loop
   TcTaps taps;
 };
 
@@ -199,8 +200,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   const int tn_i = t / p.tiles_h;
   const int n0 = tn_i * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
   const int col0 = blockIdx.y * BN;
-  const int nk = p.taps.n * p.cchunks;
+  const int nk_total = p.taps.n * p.cchunks;
+  const int per_split = (nk_total + p.ksplit - 1) / p.ksplit;
+  const int it_beg = blockIdx.z * per_split;
+  const int nk = min(nk_total, it_beg + per_split) - it_beg;
   const uint32_t tx_bytes = (p.nsplit == 3) ? STAGE_BYTES : (A_BYTES + B_BYTES);
+  if (nk <= 0) return;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_ah);
@@ -228,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nk; ++it) {
-        const int tap = it / p.cchunks, cc = it - tap * p.cchunks;
+        const int tap = (it_beg + it) / p.cchunks, cc = (it_beg + it) - tap * p.cchunks;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
         mbar_expect_tx(&full_bar[stage], tx_bytes);
@@ -309,7 +314,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
               v.x = tc_act(v.x, p.act, p.slope); v.y = tc_act(v.y, p.act, p.slope);
               v.z = tc_act(v.z, p.act, p.slope); v.w = tc_act(v.w, p.act, p.slope);
             }
-            *reinterpret_cast<float4*>(yrow + c + j) = v;
+            if (p.ksplit > 1) {   // partial sum of this K slice (output zero-filled by the launcher)
+              atomicAdd(yrow + c + j, v.x); atomicAdd(yrow + c + j + 1, v.y);
+              atomicAdd(yrow + c + j + 2, v.z); atomicAdd(yrow + c + j + 3, v.w);
+            } else {
+              *reinterpret_cast<float4*>(yrow + c + j) = v;
+            }
           }
         }
       }
@@ -320,6 +330,168 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two-tile variant for large problems: one CTA computes TWO 128-pixel tiles (adjacent tile indices) against
+// the same weight tile, with two TMEM accumulators.  The single-tile kernel above is bound by L2->SM traffic
+// (85 KB of operands per 12 MMAs at BN = 208, measured 9.3 TB/s = the LTS throughput cap, tensor pipe 41 %);
+// sharing each B (weight) stage between two A (pixel) tiles cuts that to 58.5 KB per tile.  Separate smem rings:
+// 3 A slots (hi+lo, 32 KB each) and 2 B slots.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                const TcParams p) {
+  constexpr int AS = 3, BS = 2;
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;   // 16 KB (one of hi / lo)
+  constexpr uint32_t B_BYTES = BN * TC_BK * 4;
+  constexpr uint32_t A_SLOT = 2 * A_BYTES, B_SLOT = 2 * B_BYTES;
+  constexpr uint32_t ACC_STRIDE = 256;               // TMEM column offset of the second accumulator
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + AS * A_SLOT;
+  __shared__ __align__(8) uint64_t fullA[AS], emptyA[AS], fullB[BS], emptyB[BS], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.y * BN;
+  const int nk = p.taps.n * p.cchunks;
+  const bool split3 = p.nsplit == 3;
+  // the two tiles of this CTA
+  int tn0[2], th0[2], tw0[2];
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    int t = blockIdx.x * 2 + hf;
+    const int tw_i = t % p.tiles_w;
+    t /= p.tiles_w;
+    const int th_i = t % p.tiles_h;
+    const int tn_i = t / p.tiles_h;     // may run past the last image for an odd tile count: TMA then zero-fills
+    tn0[hf] = tn_i * p.TN; th0[hf] = th_i * p.TH; tw0[hf] = tw_i * p.TW;
+  }
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_ah);
+    prefetch_tmap(&map_bh);
+    for (int s = 0; s < AS; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int it = 0; it < nk; ++it) {
+        const int tap = it / p.cchunks, cc = it - tap * p.cchunks;
+        const int c0 = cc * TC_BK, widx = p.taps.widx[tap];
+        mbar_wait(&emptyB[bs], bph ^ 1);
+        uint8_t* sb = smem_b + (size_t)bs * B_SLOT;
+        mbar_expect_tx(&fullB[bs], split3 ? B_SLOT : B_BYTES);
+        tma_load_3d(sb, &map_bh, &fullB[bs], c0, col0, widx);
+        if (split3) tma_load_3d(sb + B_BYTES, &map_bl, &fullB[bs], c0, col0, widx);
+        if (++bs == BS) { bs = 0; bph ^= 1; }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&emptyA[as], aph ^ 1);
+          uint8_t* sa = smem_a + (size_t)as * A_SLOT;
+          mbar_expect_tx(&fullA[as], split3 ? A_SLOT : A_BYTES);
+          const int ws = tw0[hf] + p.taps.dw[tap], hs = th0[hf] + p.taps.dh[tap], ns = tn0[hf] + p.taps.dn[tap];
+          tma_load_4d(sa, &map_ah, &fullA[as], c0, ws, hs, ns);
+          if (split3) tma_load_4d(sa + A_BYTES, &map_al, &fullA[as], c0, ws, hs, ns);
+          if (++as == AS) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int it = 0; it < nk; ++it) {
+        mbar_wait(&fullB[bs], bph);
+        const uint32_t sb = smem_u32(smem_b + (size_t)bs * B_SLOT);
+        const uint64_t bh = make_desc_sw128(sb), bl = make_desc_sw128(sb + B_BYTES);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&fullA[as], aph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + (size_t)as * A_SLOT);
+          const uint64_t ah = make_desc_sw128(sa), al = make_desc_sw128(sa + A_BYTES);
+          const uint32_t d = tmem_base + hf * ACC_STRIDE;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+            if (split3) {
+              umma_tf32(d, al + koff, bh + koff, idesc, acc);
+              umma_tf32(d, ah + koff, bl + koff, idesc, 1u);
+              umma_tf32(d, ah + koff, bh + koff, idesc, 1u);
+            } else {
+              umma_tf32(d, ah + koff, bh + koff, idesc, acc);
+            }
+          }
+          umma_commit(&emptyA[as]);
+          if (++as == AS) { as = 0; aph ^= 1; }
+        }
+        umma_commit(&emptyB[bs]);
+        if (++bs == BS) { bs = 0; bph ^= 1; }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tw = row % p.TW;
+    const int th = (row / p.TW) % p.TH;
+    const int tn = row / (p.TW * p.TH);
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {
+      const int n = tn0[hf] + tn, h = th0[hf] + th, w = tw0[hf] + tw;
+      const int oy = p.osy * h + p.opy, ox = p.osx * w + p.opx;
+      const bool row_ok = (n < p.N) && (h < p.OH) && (w < p.OW) && (oy < p.OHfull) && (ox < p.OWfull);
+      float* yrow = p.y + (long long)n * p.ysn + (long long)oy * p.ysh + (long long)ox * p.ysw + col0;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * ACC_STRIDE + c), r);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c + j < BN && col0 + c + j < p.K) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                     __uint_as_float(r[j + 3]));
+              if (p.bias) {
+                float4 b = ldg4(p.bias + col0 + c + j);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if (p.act != OG_ACT_NONE) {
+                v.x = tc_act(v.x, p.act, p.slope); v.y = tc_act(v.y, p.act, p.slope);
+                v.z = tc_act(v.z, p.act, p.slope); v.w = tc_act(v.w, p.act, p.slope);
+              }
+              *reinterpret_cast<float4*>(yrow + c + j) = v;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -528,6 +700,160 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
   }
 }
 
+// two co-tiles (256 output channels) per CTA sharing every X stage -- same idea as conv_tc2_kernel
+template <int BNW>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_constant__ CUtensorMap map_gl,
+                      const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                      const TcWgradParams p) {
+  constexpr int AS = 3, BS = 2;
+  constexpr uint32_t A_BYTES = TC_BM * WG_PIX * 4;
+  constexpr uint32_t B_BYTES = BNW * WG_PIX * 4;
+  constexpr uint32_t A_SLOT = 2 * A_BYTES, B_SLOT = 2 * B_BYTES;
+  constexpr uint32_t ACC_STRIDE = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + AS * A_SLOT;
+  __shared__ __align__(8) uint64_t fullA[AS], emptyA[AS], fullB[BS], emptyB[BS], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int copairs = (p.cotiles + 1) / 2;
+  const int copair = blockIdx.x % copairs, citile = blockIdx.x / copairs, tap = blockIdx.y;
+  const int ch_beg = blockIdx.z * p.chunks_per_cta;
+  const int ch_end = min(p.total_chunks, ch_beg + p.chunks_per_cta);
+  const int nk = ch_end - ch_beg;
+  const bool split3 = p.nsplit == 3;
+  if (nk <= 0) return;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_gh);
+    prefetch_tmap(&map_xh);
+    for (int s = 0; s < AS; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      const int dh = p.dh[tap], brow = p.bvar[tap] * p.C + citile * BNW;
+      const int arow0 = p.aoff[tap] + copair * 2 * TC_BM;
+      for (int it = 0; it < nk; ++it) {
+        const int ch = ch_beg + it;
+        const int wc = ch % p.wchunks;
+        const int t2 = ch / p.wchunks;
+        const int hc = t2 % p.hchunks;
+        const int w0 = wc * p.cw, h = hc * p.chh, n = (t2 / p.hchunks) * p.cn;
+        const int bw = p.flatW ? w0 + dh * p.flatW : w0;
+        const int bh = p.flatW ? 0 : h + dh;
+        mbar_wait(&emptyB[bs], bph ^ 1);
+        uint8_t* sb = smem_b + (size_t)bs * B_SLOT;
+        mbar_expect_tx(&fullB[bs], split3 ? B_SLOT : B_BYTES);
+        tma_load_4d(sb, &map_xh, &fullB[bs], bw, bh, n, brow);
+        if (split3) tma_load_4d(sb + B_BYTES, &map_xl, &fullB[bs], bw, bh, n, brow);
+        if (++bs == BS) { bs = 0; bph ^= 1; }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&emptyA[as], aph ^ 1);
+          uint8_t* sa = smem_a + (size_t)as * A_SLOT;
+          mbar_expect_tx(&fullA[as], split3 ? A_SLOT : A_BYTES);
+          // rows past this copy's Kp rows would read the next copy: clamp by pointing fully out of range
+          const int arow = (copair * 2 + hf) < p.cotiles ? arow0 + hf * TC_BM : 0x3fffffff;
+          tma_load_4d(sa, &map_gh, &fullA[as], w0, h, n, arow);
+          if (split3) tma_load_4d(sa + A_BYTES, &map_gl, &fullA[as], w0, h, n, arow);
+          if (++as == AS) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TC_BM, BNW);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int it = 0; it < nk; ++it) {
+        mbar_wait(&fullB[bs], bph);
+        const uint32_t sb = smem_u32(smem_b + (size_t)bs * B_SLOT);
+        const uint64_t bh = make_desc_sw128(sb), bl = make_desc_sw128(sb + B_BYTES);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&fullA[as], aph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + (size_t)as * A_SLOT);
+          const uint64_t ah = make_desc_sw128(sa), al = make_desc_sw128(sa + A_BYTES);
+          const uint32_t d = tmem_base + hf * ACC_STRIDE;
+#pragma unroll
+          for (int k = 0; k < WG_PIX / 8; ++k) {
+            const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+            if (split3) {
+              umma_tf32(d, al + koff, bh + koff, idesc, acc);
+              umma_tf32(d, ah + koff, bl + koff, idesc, 1u);
+              umma_tf32(d, ah + koff, bh + koff, idesc, 1u);
+            } else {
+              umma_tf32(d, ah + koff, bh + koff, idesc, acc);
+            }
+          }
+          umma_commit(&emptyA[as]);
+          if (++as == AS) { as = 0; aph ^= 1; }
+        }
+        umma_commit(&emptyB[bs]);
+        if (++bs == BS) { bs = 0; bph ^= 1; }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int cleft = p.C - citile * BNW;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {
+      const int co = (copair * 2 + hf) * TC_BM + q * 32 + lane;
+      const bool row_ok = co < p.Kp;
+      float* drow = p.dw + ((long long)p.out[tap] * p.Kp + co) * p.C + citile * BNW;
+#pragma unroll 1
+      for (int c = 0; c < BNW; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * ACC_STRIDE + c), r);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c + j < BNW && c + j < cleft) atomicAdd(drow + c + j, __uint_as_float(r[j]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int BNW>
+int launch_wgrad2(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
+                  const TcWgradParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)3 * (2 * TC_BM * WG_PIX * 4) + (size_t)2 * (2 * BNW * WG_PIX * 4) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad2_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  conv_tc_wgrad2_kernel<BNW><<<grid, TC_THREADS, smem, stream>>>(gh, gl, xh, xl, p);
+  return (int)cudaGetLastError();
+}
+
 template <int BNW, int STAGES>
 int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
                  const TcWgradParams& p, dim3 grid, cudaStream_t stream) {
@@ -539,6 +865,20 @@ int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap
     configured = true;
   }
   conv_tc_wgrad_kernel<BNW, STAGES><<<grid, TC_THREADS, smem, stream>>>(gh, gl, xh, xl, p);
+  return (int)cudaGetLastError();
+}
+
+template <int BN>
+int launch_tc2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+               const TcParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)3 * (2 * TC_BM * TC_BK * 4) + (size_t)2 * (2 * BN * TC_BK * 4) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  conv_tc2_kernel<BN><<<grid, TC_THREADS, smem, stream>>>(ah, al, bh, bl, p);
   return (int)cudaGetLastError();
 }
 
@@ -596,6 +936,23 @@ OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH,
   int BNsel = BN <= 64 ? 64 : BN <= 112 ? 112 : BN <= 208 ? 208 : 256;
   if (BN <= 32) BNsel = 32;
   dim3 grid(tiles_n * p.tiles_h * p.tiles_w, og_cdiv(K, BNsel), 1);
+  // few output tiles (small feature maps): split the reduction over gridDim.z and combine with atomics
+  p.ksplit = 1;
+  {
+    const long long tiles = (long long)grid.x * grid.y;
+    const int nk_total = ntaps * p.cchunks;
+    const bool dense = ysw == K && ysh == (long long)OWf * K && ysn == (long long)OHf * OWf * K && osy == 1 && osx == 1 &&
+                       OH == OHf && OW == OWf;
+    if (tiles < 100 && nk_total >= 16 && !bias && act == OG_ACT_NONE && dense) {
+      int s = (int)((256 + tiles - 1) / tiles);
+      if (s > nk_total / 8) s = nk_total / 8;
+      if (s > 1) {
+        p.ksplit = s;
+        grid.z = s;
+        OG_CHECK(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)N * OH * OW * K, stream));
+      }
+    }
+  }
 
   CUtensorMap mah, mal, mbh, mbl;
   unsigned long long adims[4] = {(unsigned long long)C, (unsigned long long)SW, (unsigned long long)SH, (unsigned long long)SN};
@@ -613,6 +970,13 @@ OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH,
   } else {
     mal = mah;
     mbl = mbh;
+  }
+  // large problems: two pixel tiles per CTA share every weight stage (see conv_tc2_kernel)
+  static const bool no_tc2 = getenv("OG_NO_TC2") != nullptr;
+  if (!no_tc2 && p.ksplit == 1 && (BNsel == 208 || BNsel == 256) && (long long)grid.x * grid.y >= 2 * 148 * 2) {
+    dim3 grid2((grid.x + 1) / 2, grid.y, 1);
+    return BNsel == 208 ? launch_tc2<208>(mah, mal, mbh, mbl, p, grid2, stream)
+                        : launch_tc2<256>(mah, mal, mbh, mbl, p, grid2, stream);
   }
   switch (BNsel) {
     case 32:  return launch_tc<32, 4>(mah, mal, mbh, mbl, p, grid, stream);
@@ -693,6 +1057,19 @@ OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int OH, i
     mgl = mgh;
     mxl = mxh;
   }
+  static const bool no_tc2 = getenv("OG_NO_TC2") != nullptr;
+  if (!no_tc2 && cotiles >= 2 && (BNsel == 208 || BNsel == 256)) {
+    // two co-tiles per CTA share every X stage (L2 -> SM traffic is the bound of this kernel)
+    const int copairs = (cotiles + 1) / 2;
+    int sp = og_cdiv(296, copairs * citiles * nentries);
+    if (sp > maxs) sp = maxs;
+    if (sp < 1) sp = 1;
+    p.chunks_per_cta = og_cdiv(p.total_chunks, sp);
+    sp = og_cdiv(p.total_chunks, p.chunks_per_cta);
+    dim3 grid2(copairs * citiles, nentries, sp);
+    return BNsel == 208 ? launch_wgrad2<208>(mgh, mgl, mxh, mxl, p, grid2, stream)
+                        : launch_wgrad2<256>(mgh, mgl, mxh, mxl, p, grid2, stream);
+  }
   switch (BNsel) {
     case 32:  return launch_wgrad<32, 4>(mgh, mgl, mxh, mxl, p, grid, stream);
     case 64:  return launch_wgrad<64, 4>(mgh, mgl, mxh, mxl, p, grid, stream);
@@ -746,17 +1123,24 @@ __global__ void prep_split_planar_kernel(const float* __restrict__ x, int N, int
   }
   __syncthreads();
   const long long plane = (long long)N * Hp * Wp;
-  for (int s = 0; s < nshift; ++s)
-    for (int j = threadIdx.y; j < 32; j += 8) {    // rows = c, cols = w' (coalesced along w')
-      int c = c0 + j, wq = w0 + threadIdx.x;
-      if (c < C && wq < Wp) {
-        float v = tile[threadIdx.x + 1 + s - origin][j];
-        float hi = tf32_rn(v);
-        long long o = (((long long)phase * nshift + s) * C + c) * plane + ((long long)n * Hp + hp) * Wp + wq;
-        th[o] = hi;
-        if (tl) tl[o] = tf32_rn(v - hi);
+  // 256 threads = 32 channels x 8 groups of 4 consecutive w': 128-bit stores, conflict-free tile reads
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int cj = tid >> 3, w4 = (tid & 7) * 4;
+  const int c = c0 + cj, wq = w0 + w4;
+  if (c < C && wq < Wp) {
+    for (int s = 0; s < nshift; ++s) {
+      float v[4], hi[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k] = tile[w4 + k + 1 + s - origin][cj];
+        hi[k] = tf32_rn(v[k]);
       }
+      const long long o = (((long long)phase * nshift + s) * C + c) * plane + ((long long)n * Hp + hp) * Wp + wq;
+      st4(th + o, make_float4(hi[0], hi[1], hi[2], hi[3]));
+      if (tl) st4(tl + o, make_float4(tf32_rn(v[0] - hi[0]), tf32_rn(v[1] - hi[1]), tf32_rn(v[2] - hi[2]),
+                                      tf32_rn(v[3] - hi[3])));
     }
+  }
 }
 
 OG_API int og_prep_split_planar(const float* x, int N, int H, int W, int C, int pad, int nshift, int origin, int s2d,

@@ -94,7 +94,7 @@ class PackedWeights:
 import os as _os
 CONV_ENGINE = _os.environ.get("OBJGAN_CONV", "tf32x3")
 TC_WGRAD = _os.environ.get("OBJGAN_TC_WGRAD", "1") == "1"
-TC_MIN_PIXELS = 2048       # below this the tensor-core tiles cannot fill the machine; SIMT split-K does better
+TC_MIN_PIXELS = 256        # smaller problems go to the exact-fp32 SIMT kernels (the tc kernel splits K on small maps)
 
 
 def _int_array(rows):
@@ -347,13 +347,20 @@ class _Conv2d(torch.autograd.Function):
                 assert not split
                 bias_p = torch.zeros(kp, device=x.device, dtype=torch.float32)
                 bias_p[:co] = bias.detach()
+        narrow = kind is None and kp == 8 and mode == PAD_ZERO and n * oh * ow <= 65536
         if kind:
             y = _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act)
+        elif narrow:
+            wf, _ = cache.get(weight, c, kp, split, splitp, False)
+            y = torch.empty((n, oh, ow, 8), device=x.device, dtype=torch.float32)
+            _call("og_conv2d_narrow_fwd", _p(x), n, h, w, c, _p(wf), _p(y), oh, ow, kh, kw, stride, pad, _p(bias_p), act,
+                  LRELU_SLOPE)
         else:
             wf, _ = cache.get(weight, c, kp, split, splitp, False)
             y = _conv_raw(x, wf, n, h, w, c, oh, ow, kp, kh, kw, stride, pad, mode, bias_p, act,
                           splitk=(bias is None and act == ACT_NONE))
         ctx.kind = kind
+        ctx.narrow = narrow
         ctx.cfg = (stride, pad, mode, act, split, splitp, kp, need_t)
         ctx.cache = cache
         ctx.has_bias = bias is not None
@@ -378,6 +385,17 @@ class _Conv2d(torch.autograd.Function):
             gb = torch.empty(co, device=g.device, dtype=torch.float32)
             _call("og_channel_sum", _p(g), n * oh * ow, kp, _p(scratch), _p(gb), co, 0)
         kind = ctx.kind
+        if ctx.narrow:
+            wf, _ = ctx.cache.get(weight, c, kp, split, splitp, False)
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                _call("og_conv2d_narrow_dgrad", _p(g), n, h, w, c, _p(wf), _p(gx), oh, ow, kh, kw, stride, pad)
+            if ctx.needs_input_grad[1]:
+                dwp = torch.empty(kh * kw * c * 8, device=g.device, dtype=torch.float32)
+                _call("og_conv2d_narrow_wgrad", _p(x), n, h, w, c, _p(g), _p(dwp), oh, ow, kh, kw, stride, pad)
+                gw = torch.empty_like(weight)
+                _call("og_unpack_wgrad", _p(dwp), co, ci, kh, kw, c, kp, split, splitp, _p(gw), 0, 0)
+            return gx, gw, gb, None, None, None, None, None, None
         if ctx.needs_input_grad[0] and kind:
             gx = _tc_dgrad(kind, g, ctx.cache, weight, c, kp, split, splitp, mode, h, w)
         elif ctx.needs_input_grad[0]:

@@ -161,9 +161,13 @@ class StepATrainer:
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         n0 = _l.get().launches
-        with torch.cuda.graph(self._graph):
+        # capture on the SAME side stream as the warm-up: autograd's AccumulateGrad nodes remember the stream they were
+        # created on, and gradient accumulation issued on any other stream would fall outside the capture
+        with torch.cuda.graph(self._graph, stream=side):
             self._static_out = self._eager_step(self._static)
         self.launches_per_step = _l.get().launches - n0
+        for b in [self.bG, *self.bD]:
+            b.step -= 1          # the captured pass was recorded, not executed
         ops.bump_param_epoch()
 
     def _load_static(self, inp: dict) -> None:

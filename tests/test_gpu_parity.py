@@ -476,19 +476,29 @@ def test_step_a_parity(engine, cos_min, l2_max, monkeypatch):
 
 
 def test_cuda_graph_replay_matches_eager():
-    """The captured whole-step CUDA graph computes the same step as eager launches (same seeds, same inputs)."""
-    inp = synth.make_inputs(2, seed=8, parity=True)
+    """A replay of the captured whole-step CUDA graph computes the same step as eager launches from the same state."""
+    inp = synth.make_inputs(4, seed=8, parity=True)
     a = trainer.StepATrainer(device=DEV, seed=5)
     b = trainer.StepATrainer(device=DEV, seed=5)
     da, db = a.to_device(inp), b.to_device(inp)
-    for _ in range(3):
-        oa = a.step(da)
-    b.capture(db, warmup=2)       # two eager warm-up steps, then the capture itself (not executed)
-    ob = b.step(db)               # third step = first replay
+    b.capture(db, warmup=2)                      # two eager warm-up steps, then the capture itself (not executed)
+    # bring the eager trainer to exactly b's state (weights, Adam moments, EMA, BatchNorm buffers, step counters)
+    for x, y in zip([a.bG, *a.bD], [b.bG, *b.bD]):
+        for name in ("flat", "m", "v"):
+            getattr(x, name).copy_(getattr(y, name))
+        x.step, _ = y.step, x.step_dev.copy_(y.step_dev)
+    a.bG.avg.copy_(b.bG.avg)
+    for ma, mb in zip([a.netG, *a.netsPatD], [b.netG, *b.netsPatD]):
+        for ba, bb in zip(ma.buffers(), mb.buffers()):
+            ba.copy_(bb)
+    ops.bump_param_epoch()
+    oa = a.step(da)                              # eager
+    ob = b.step(db)                              # graph replay
     torch.cuda.synchronize()
     assert b.launches_per_step > 500
     for k in ("errPatD0", "errPatD1", "errPatD2", "errG", "kl"):
-        assert abs(float(oa[k]) - float(ob[k])) <= 2e-2 * max(1.0, abs(float(oa[k]))), k
+        assert abs(float(oa[k]) - float(ob[k])) <= 1e-3 * max(1.0, abs(float(oa[k]))), k
     for i in range(3):
-        close(ob["fake_imgs"][i], oa["fake_imgs"][i], 2e-2, what=f"fake{i}")
-    assert int(b.bG.step_dev) == 3 and b.bG.step == 3
+        close(ob["fake_imgs"][i], oa["fake_imgs"][i], 1e-4, what=f"fake{i}")   # forward is deterministic
+    assert rel_l2(b.bG.grad, a.bG.grad) < 1e-2                                  # backward has atomics (order varies)
+    assert int(b.bG.step_dev) == int(a.bG.step_dev) == 3 and b.bG.step == 3
