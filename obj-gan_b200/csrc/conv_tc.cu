@@ -1084,10 +1084,11 @@ OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int OH, i
 // pad = 1 materialises the nn.ReflectionPad2d(1) halo.  s2d = 1: four space-to-depth phase blocks
 // t[phase][s][c][n][h'][w'] with phase (a*2+b) = x[:, a::2, b::2] (stride-2 convs, 2x-upsample adjoints).  The shifted copies exist because TMA needs the innermost
 // box coordinate 16-byte aligned: a tap's w offset picks a copy instead of an unaligned box.
-__global__ void prep_split_planar_kernel(const float* __restrict__ x, int N, int H, int W, int C, int pad, int Wp,
-                                         int nshift, int origin, int s2d, float* __restrict__ th,
-                                         float* __restrict__ tl) {
-  __shared__ float tile[36][33];                   // columns w0-1 .. w0+34 of the (padded / phase) row, 32 channels
+constexpr int PL_TW = 128;   // pixels of one row handled by a block (long contiguous runs per channel plane)
+__global__ void __launch_bounds__(256) prep_split_planar_kernel(const float* __restrict__ x, int N, int H, int W, int C,
+                                                                int pad, int Wp, int nshift, int origin, int s2d,
+                                                                float* __restrict__ th, float* __restrict__ tl) {
+  __shared__ float tile[PL_TW + 4][33];            // columns w0-1 .. w0+PL_TW+2 of the (padded / phase) row, 32 channels
   const int Hp = s2d ? H / 2 : H + 2 * pad, Wq = s2d ? W / 2 : W + 2 * pad;
   int nh = blockIdx.z;                             // (phase *) n * Hp + h'
   int phase = 0;
@@ -1104,9 +1105,10 @@ __global__ void prep_split_planar_kernel(const float* __restrict__ x, int N, int
     if (sh < 0) sh = -sh;
     if (sh >= H) sh = 2 * H - 2 - sh;
   }
-  const int w0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int j = threadIdx.y; j < 36; j += 8) {      // rows = column index, cols = c (coalesced along c)
-    int wq = w0 - 1 + j, c = c0 + threadIdx.x;
+  const int w0 = blockIdx.x * PL_TW, c0 = blockIdx.y * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = warp; j < PL_TW + 4; j += 8) {      // rows = column index, lanes = c (coalesced along c)
+    int wq = w0 - 1 + j, c = c0 + lane;
     float v = 0.f;
     if (wq >= 0 && wq < Wq && c < C) {
       int sw;
@@ -1119,26 +1121,25 @@ __global__ void prep_split_planar_kernel(const float* __restrict__ x, int N, int
       }
       v = x[(((long long)n * H + sh) * W + sw) * C + c];
     }
-    tile[j][threadIdx.x] = v;
+    tile[j][lane] = v;
   }
   __syncthreads();
   const long long plane = (long long)N * Hp * Wp;
-  // 256 threads = 32 channels x 8 groups of 4 consecutive w': 128-bit stores, conflict-free tile reads
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  const int cj = tid >> 3, w4 = (tid & 7) * 4;
-  const int c = c0 + cj, wq = w0 + w4;
-  if (c < C && wq < Wp) {
+  for (int j = warp; j < 32; j += 8) {             // one channel plane per warp: lanes run along w' (128 B per store)
+    const int c = c0 + j;
+    if (c >= C) continue;
     for (int s = 0; s < nshift; ++s) {
-      float v[4], hi[4];
+      const long long o = (((long long)phase * nshift + s) * C + c) * plane + ((long long)n * Hp + hp) * Wp;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        v[k] = tile[w4 + k + 1 + s - origin][cj];
-        hi[k] = tf32_rn(v[k]);
+      for (int k = 0; k < PL_TW / 32; ++k) {
+        const int wl = k * 32 + lane, wq = w0 + wl;
+        if (wq < Wp) {
+          const float v = tile[wl + 1 + s - origin][j];
+          const float hi = tf32_rn(v);
+          th[o + wq] = hi;
+          if (tl) tl[o + wq] = tf32_rn(v - hi);
+        }
       }
-      const long long o = (((long long)phase * nshift + s) * C + c) * plane + ((long long)n * Hp + hp) * Wp + wq;
-      st4(th + o, make_float4(hi[0], hi[1], hi[2], hi[3]));
-      if (tl) st4(tl + o, make_float4(tf32_rn(v[0] - hi[0]), tf32_rn(v[1] - hi[1]), tf32_rn(v[2] - hi[2]),
-                                      tf32_rn(v[3] - hi[3])));
     }
   }
 }
@@ -1149,8 +1150,8 @@ OG_API int og_prep_split_planar(const float* x, int N, int H, int W, int C, int 
   if (s2d && (pad || (H & 1) || (W & 1))) return (int)cudaErrorInvalidValue;
   if ((long long)N * H * W * C == 0) return 0;
   const int Wq = s2d ? W / 2 : W + 2 * pad, Wp = (Wq + 3) / 4 * 4, Hp = s2d ? H / 2 : H + 2 * pad;
-  dim3 grid(og_cdiv(Wp, 32), og_cdiv(C, 32), N * Hp * (s2d ? 4 : 1)), block(32, 8);
-  prep_split_planar_kernel<<<grid, block, 0, stream>>>(x, N, H, W, C, pad, Wp, nshift, origin, s2d, th, tl);
+  dim3 grid(og_cdiv(Wp, PL_TW), og_cdiv(C, 32), N * Hp * (s2d ? 4 : 1));
+  prep_split_planar_kernel<<<grid, 256, 0, stream>>>(x, N, H, W, C, pad, Wp, nshift, origin, s2d, th, tl);
   OG_RETURN_LAST_ERROR();
 }
 

@@ -234,14 +234,55 @@ class StepATrainer:
         return out
 
     def step_from_host(self, host_inp: dict) -> float:
-        """The public end-to-end call: pinned host batch in, scalar generator loss out (forces the
-        device->host read of the step's result)."""
-        if getattr(self, "_graph", None) is not None:
-            self._load_static(host_inp)        # pinned host -> captured static device buffers (async H2D)
-            out = self.step(self._static)
-        else:
+        """The public end-to-end call: pinned host batch in, scalar generator loss out.
+
+        With a captured graph the call is software-pipelined: the host->device copy of THIS batch runs on a copy
+        stream into a staging buffer while the previous step is still computing, and the value returned is the
+        loss of the PREVIOUS step (its device->host read completes here), so every call still performs one full
+        H2D of its inputs and one D2H read of a step result, but neither stalls the GPU.  The first call returns
+        its own loss."""
+        if getattr(self, "_graph", None) is None:
             out = self.step(self.to_device(host_inp))
-        return float((out["errG"] + out["kl"]).item())
+            return float((out["errG"] + out["kl"]).item())
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_stage"):
+            def clone(v):
+                return [t.clone() for t in v] if isinstance(v, (list, tuple)) else (v.clone() if torch.is_tensor(v) else v)
+            self._stage = [{k: clone(v) for k, v in self._static.items()} for _ in range(2)]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self._stage_free:
+                e.record(cur)
+            self._copy_stream = torch.cuda.Stream()
+            self._loss_host = [torch.zeros((), pin_memory=True), torch.zeros((), pin_memory=True)]
+            self._pending = None
+            self._e2e_k = 0
+        k = self._e2e_k & 1
+        self._e2e_k += 1
+        stg = self._stage[k]
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free[k])       # staging buffer k was consumed two steps ago
+            for name, v in host_inp.items():
+                d = stg.get(name)
+                if torch.is_tensor(v) and torch.is_tensor(d):
+                    d.copy_(v, non_blocking=True)
+                elif isinstance(v, (list, tuple)):
+                    for dd, t in zip(d, v):
+                        dd.copy_(t, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self._copy_stream)
+        cur.wait_event(copied)
+        self._load_static(stg)                                      # device->device into the captured buffers
+        self._stage_free[k].record(cur)
+        out = self.step(self._static)
+        self._loss_host[k].copy_(out["errG"] + out["kl"], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        prev, self._pending = self._pending, (done, self._loss_host[k])
+        if prev is None:
+            done.synchronize()
+            return float(self._loss_host[k])
+        prev[0].synchronize()
+        return float(prev[1])
 
 
 def pin(inp: dict) -> dict:
