@@ -139,6 +139,9 @@ int og_paint_max_bwd(const float* f, const float* m, const float* g, int gstride
                      int Rtot, long long P, float* g_f, cudaStream_t stream);
 int og_func_attention_fwd(const float* query, const float* ctx, int B, int ndf, int Lq, int S, float gamma1, float* wc,
                           float* attn, cudaStream_t stream);
+int og_func_attention_bwd(const float* query, const float* ctx, const float* attn, const float* g_wc,
+                          const float* g_attn, int B, int ndf, int Lq, int S, float gamma1, float* g_query, float* g_ctx,
+                          cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Layout, adjoints of pad / upsample, concat, losses, optimiser
@@ -160,6 +163,9 @@ int og_copy_channels(const float* src, int sstride, int soff, float* dst, int ds
 int og_broadcast_channels(const float* c, int B, int Cc, float* dst, int dstride, int doff, long long pix_per_img,
                           cudaStream_t stream);
 int og_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
+/* F.interpolate(bilinear, align_corners=True) on NHWC (ref: model.py:1217-1218, 1283-1284) and its adjoint */
+int og_bilinear_fwd(const float* x, int N, int IH, int IW, int C, int OH, int OW, float* y, cudaStream_t stream);
+int og_bilinear_bwd(const float* g, int N, int IH, int IW, int C, int OH, int OW, float* gx, cudaStream_t stream);
 int og_glu_fwd(const float* x, long long P, int Ch, float* out, cudaStream_t stream);
 int og_glu_bwd(const float* x, const float* g, long long P, int Ch, float* gx, cudaStream_t stream);
 int og_reparam_fwd(const float* x, int xs, const float* eps, int B, int D, float* c, int cs, cudaStream_t stream);

@@ -574,3 +574,125 @@ OG_API int og_func_attention_fwd(const float* query, const float* ctx, int B, in
   func_attention_fwd_kernel<<<B, 256, sm, stream>>>(query, ctx, ndf, Lq, S, gamma1, wc, attn);
   OG_RETURN_LAST_ERROR();
 }
+
+// ---------------------------------------------------------------------------------------------
+// func_attention backward (ref: GlobalAttention.py:32-70): one block per (image, caption) pair.
+//   S[s,l] = sum_c ctx[c,s] q[c,l];  P = softmax_l(S);  P2 = softmax_s(gamma1 * P^T);  wc[c,l] = sum_s ctx[c,s] P2[l,s]
+// inputs: query, ctx, attn (= P2, the saved forward output), g_wc [B][ndf][Lq], g_attn [B][Lq][S] or null
+// outputs: g_query [B][ndf][Lq], g_ctx [B][ndf][S]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) func_attention_bwd_kernel(const float* __restrict__ query,
+                                                                 const float* __restrict__ ctx,
+                                                                 const float* __restrict__ attn,
+                                                                 const float* __restrict__ g_wc,
+                                                                 const float* __restrict__ g_attn, int ndf, int Lq,
+                                                                 int S, float gamma1, float* __restrict__ g_query,
+                                                                 float* __restrict__ g_ctx) {
+  extern __shared__ float smem[];
+  float* sq = smem;                 // [ndf][Lq]   query
+  float* sg = sq + ndf * Lq;        // [ndf][Lq]   g_wc
+  float* sP = sg + ndf * Lq;        // [S][Lq]     P, then gS
+  float* sP2 = sP + S * Lq;         // [Lq][S]     P2
+  float* sG = sP2 + Lq * S;         // [Lq][S]     gP2, then gT
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const float* qb = query + (long long)b * ndf * Lq;
+  const float* cb = ctx + (long long)b * ndf * S;
+  const float* gb = g_wc + (long long)b * ndf * Lq;
+  for (int i = t; i < ndf * Lq; i += 256) {
+    sq[i] = qb[i];
+    sg[i] = gb[i];
+  }
+  for (int i = t; i < Lq * S; i += 256) sP2[i] = attn[(long long)b * Lq * S + i];
+  __syncthreads();
+  // (1) recompute P (softmax over the words, per region) and gP2[l,s] = sum_c g_wc[c,l] ctx[c,s] (+ g_attn)
+  for (int s = t; s < S; s += 256) {
+    float acc[LMAX], gp[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      acc[l] = 0.f;
+      gp[l] = 0.f;
+    }
+    for (int c = 0; c < ndf; ++c) {
+      const float cv = __ldg(cb + (long long)c * S + s);
+      const float* qr = sq + c * Lq;
+      const float* gr = sg + c * Lq;
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l)
+        if (l < Lq) {
+          acc[l] = fmaf(cv, qr[l], acc[l]);
+          gp[l] = fmaf(cv, gr[l], gp[l]);
+        }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < Lq) mx = fmaxf(mx, acc[l]);
+    float sum = 0.f;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < Lq) {
+        acc[l] = expf(acc[l] - mx);
+        sum += acc[l];
+      }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < Lq) {
+        sP[s * Lq + l] = acc[l] * inv;
+        sG[l * S + s] = gp[l] + (g_attn ? g_attn[((long long)b * Lq + l) * S + s] : 0.f);
+      }
+  }
+  __syncthreads();
+  // (2) softmax backward over the regions, per word: gT = P2 * (gP2 - <gP2, P2>)
+  for (int l = warp; l < Lq; l += 8) {
+    float d = 0.f;
+    for (int s = lane; s < S; s += 32) d = fmaf(sG[l * S + s], sP2[l * S + s], d);
+    d = warp_sum(d);
+    for (int s = lane; s < S; s += 32) sG[l * S + s] = sP2[l * S + s] * (sG[l * S + s] - d);
+  }
+  __syncthreads();
+  // (3) softmax backward over the words, per region: gS = P * (gP - <gP, P>),  gP = gamma1 * gT^T
+  for (int s = t; s < S; s += 256) {
+    float d = 0.f;
+    for (int l = 0; l < Lq; ++l) d = fmaf(gamma1 * sG[l * S + s], sP[s * Lq + l], d);
+    for (int l = 0; l < Lq; ++l) sP[s * Lq + l] = sP[s * Lq + l] * (gamma1 * sG[l * S + s] - d);
+  }
+  __syncthreads();
+  // (4) g_ctx[c,s] = sum_l g_wc[c,l] P2[l,s] + gS[s,l] q[c,l];   g_query[c,l] = sum_s gS[s,l] ctx[c,s]
+  for (int c = warp; c < ndf; c += 8) {
+    float gq[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) gq[l] = 0.f;
+    const float* qr = sq + c * Lq;
+    const float* gr = sg + c * Lq;
+    for (int s = lane; s < S; s += 32) {
+      const float cv = __ldg(cb + (long long)c * S + s);
+      float a = 0.f;
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l)
+        if (l < Lq) {
+          const float gs = sP[s * Lq + l];
+          a = fmaf(gr[l], sP2[l * S + s], a);
+          a = fmaf(gs, qr[l], a);
+          gq[l] = fmaf(gs, cv, gq[l]);
+        }
+      g_ctx[((long long)b * ndf + c) * S + s] = a;
+    }
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < Lq) {
+        const float v = warp_sum(gq[l]);
+        if (lane == 0) g_query[((long long)b * ndf + c) * Lq + l] = v;
+      }
+  }
+}
+OG_API int og_func_attention_bwd(const float* query, const float* ctx, const float* attn, const float* g_wc,
+                                 const float* g_attn, int B, int ndf, int Lq, int S, float gamma1, float* g_query,
+                                 float* g_ctx, cudaStream_t stream) {
+  if (Lq > LMAX) return (int)cudaErrorInvalidValue;
+  if (B == 0) return 0;
+  size_t sm = sizeof(float) * (2 * (size_t)ndf * Lq + 3 * (size_t)S * Lq);
+  OG_CHECK(cudaFuncSetAttribute(func_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  func_attention_bwd_kernel<<<B, 256, sm, stream>>>(query, ctx, attn, g_wc, g_attn, ndf, Lq, S, gamma1, g_query, g_ctx);
+  OG_RETURN_LAST_ERROR();
+}

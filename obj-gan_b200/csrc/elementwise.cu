@@ -464,3 +464,72 @@ OG_API int og_inc_i64(long long* counter, cudaStream_t stream) {
   inc_i64_kernel<<<1, 1, 0, stream>>>(counter);
   OG_RETURN_LAST_ERROR();
 }
+
+// ---------------------------------------------------------------------------------------------
+// F.interpolate(mode='bilinear', align_corners=True) on NHWC tensors (OBJ_SS_D_NET / OBJ_LS_D_NET front end,
+// ref: model.py:1217-1218, 1283-1284): src index = dst * (in-1)/(out-1), weights in fp32 like ATen.
+// ---------------------------------------------------------------------------------------------
+__global__ void bilinear_fwd_kernel(const float* __restrict__ x, int IH, int IW, int OH, int OW, int C4, float rh,
+                                    float rw, long long total, float* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    long long t = i / C4;
+    int ow = (int)(t % OW);
+    t /= OW;
+    int oh = (int)(t % OH);
+    long long n = t / OH;
+    float fh = rh * oh, fw = rw * ow;
+    int h0 = (int)fh, w0 = (int)fw;
+    int h1 = h0 + (h0 < IH - 1), w1 = w0 + (w0 < IW - 1);
+    float lh = fh - h0, lw = fw - w0, hh = 1.f - lh, hw = 1.f - lw;
+    const float* b = x + n * IH * IW * C4 * 4;
+    float4 a = ldg4(b + ((long long)h0 * IW + w0) * C4 * 4 + c * 4), bq = ldg4(b + ((long long)h0 * IW + w1) * C4 * 4 + c * 4);
+    float4 cq = ldg4(b + ((long long)h1 * IW + w0) * C4 * 4 + c * 4), d = ldg4(b + ((long long)h1 * IW + w1) * C4 * 4 + c * 4);
+    float4 o;
+    o.x = hh * (hw * a.x + lw * bq.x) + lh * (hw * cq.x + lw * d.x);
+    o.y = hh * (hw * a.y + lw * bq.y) + lh * (hw * cq.y + lw * d.y);
+    o.z = hh * (hw * a.z + lw * bq.z) + lh * (hw * cq.z + lw * d.z);
+    o.w = hh * (hw * a.w + lw * bq.w) + lh * (hw * cq.w + lw * d.w);
+    st4(y + i * 4, o);
+  }
+}
+__global__ void bilinear_bwd_kernel(const float* __restrict__ g, int IH, int IW, int OH, int OW, int C, float rh,
+                                    float rw, long long total, float* __restrict__ gx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long t = i / C;
+    int ow = (int)(t % OW);
+    t /= OW;
+    int oh = (int)(t % OH);
+    long long n = t / OH;
+    float fh = rh * oh, fw = rw * ow;
+    int h0 = (int)fh, w0 = (int)fw;
+    int h1 = h0 + (h0 < IH - 1), w1 = w0 + (w0 < IW - 1);
+    float lh = fh - h0, lw = fw - w0, hh = 1.f - lh, hw = 1.f - lw;
+    float gv = g[i];
+    float* b = gx + n * IH * IW * C + c;
+    atomicAdd(b + ((long long)h0 * IW + w0) * C, gv * hh * hw);
+    atomicAdd(b + ((long long)h0 * IW + w1) * C, gv * hh * lw);
+    atomicAdd(b + ((long long)h1 * IW + w0) * C, gv * lh * hw);
+    atomicAdd(b + ((long long)h1 * IW + w1) * C, gv * lh * lw);
+  }
+}
+OG_API int og_bilinear_fwd(const float* x, int N, int IH, int IW, int C, int OH, int OW, float* y, cudaStream_t stream) {
+  if (C % 4) return (int)cudaErrorInvalidValue;
+  long long total = (long long)N * OH * OW * (C / 4);
+  if (total == 0) return 0;
+  float rh = OH > 1 ? (float)(IH - 1) / (float)(OH - 1) : 0.f, rw = OW > 1 ? (float)(IW - 1) / (float)(OW - 1) : 0.f;
+  bilinear_fwd_kernel<<<eblocks(total), 256, 0, stream>>>(x, IH, IW, OH, OW, C / 4, rh, rw, total, y);
+  OG_RETURN_LAST_ERROR();
+}
+// gx is zero-filled here
+OG_API int og_bilinear_bwd(const float* g, int N, int IH, int IW, int C, int OH, int OW, float* gx, cudaStream_t stream) {
+  OG_CHECK(cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)N * IH * IW * C, stream));
+  long long total = (long long)N * OH * OW * C;
+  if (total == 0) return 0;
+  float rh = OH > 1 ? (float)(IH - 1) / (float)(OH - 1) : 0.f, rw = OW > 1 ? (float)(IW - 1) / (float)(OW - 1) : 0.f;
+  bilinear_bwd_kernel<<<eblocks(total), 256, 0, stream>>>(g, IH, IW, OH, OW, C, rh, rw, total, gx);
+  OG_RETURN_LAST_ERROR();
+}

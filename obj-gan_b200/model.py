@@ -540,6 +540,60 @@ class PAT_D_NET256(_PatD):
 
 
 # --------------------------------------------------------------------------------------------------
+# object discriminators (ref: model.py:1184-1312): 512x512 bilinear front end, shape code, conv encoder,
+# RoIAlignAvg over the 10 box slots of every image, roi code.  forward() returns (B, 10, 384, 4, 4) like the reference;
+# the logit heads are D_GET_LOGITS(ndf // 2, nef) applied by objD_loss (loss glue: SURVEY 8f "next").
+# --------------------------------------------------------------------------------------------------
+class _ObjD(_Base):
+    n_layer = 3
+
+    def __init__(self, num_classes, b_jcu=True):
+        super().__init__()
+        ndf = cfg.GAN.DF_DIM
+        nef = cfg.TEXT.GLOVE_EMBEDDING_DIM + cfg.GAN.GF_DIM
+        ngf = cfg.GAN.GF_DIM // 4
+        self.roi_size = cfg.ROI.ROI_BASE_SIZE
+        self.im_scales = np.array([1])
+        n_layer = self.n_layer
+        self.img_code = _EncodeImage(ngf, ndf, n_layer)
+        self.shp_code = _Slots(_1=Conv2dP(num_classes, ngf, 3, 1, 1, bias=True, mode=PAD_REFLECT))
+        self.feat_dim = ndf * min(2 ** (n_layer - 1), 8)
+        self.roi_code = _Slots(_0=Conv2dP(self.feat_dim, ndf * 4, 4, 1, 1, bias=True, act=ACT_LRELU))
+        self.RoIAlignAvg = RoIAlignAvg(self.roi_size, self.roi_size, 1.0 / 16.0)
+        self.UNCOND_DNET = D_GET_LOGITS(ndf // 2, nef, bcondition=False) if b_jcu else None
+        self.COND_DNET = D_GET_LOGITS(ndf // 2, nef, bcondition=True)
+        self.ngf = ngf
+
+    def forward(self, x_var, s_var, fm_rois, num_rois, img_size=512):
+        # (x, y, w, h) -> (x1, y1, x2, y2) on the host, on a COPY (the reference mutates a CPU caller's tensor in place,
+        # ref: model.py:1213-1214; on CUDA it works on a copy too)
+        fm = fm_rois.detach().cpu().numpy().astype(np.float64, copy=True)
+        fm[:, :, [2, 3]] = fm[:, :, [0, 1]] + fm[:, :, [2, 3]]
+        b = fm.shape[0]
+        x = ops.bilinear(ops.to_nhwc(x_var), img_size, img_size)
+        s = ops.bilinear(ops.to_nhwc(s_var), img_size, img_size)
+        new_s = ops.instance_norm_act(self.shp_code[1](s), NA_LRELU)
+        x_s = ops.cat_channels([x, new_s], [x_var.shape[1], self.ngf])
+        code = self.img_code(x_s)                                           # NHWC (B, S/2^n, S/2^n, feat_dim)
+        rois = _get_rois_blob(fm.reshape(b * fm.shape[1], fm.shape[2])[:, :4], np.array([1] * b * cfg.ROI.BOXES_NUM))
+        rois_t = torch.from_numpy(rois).to(x_var.device)
+        pooled = self.RoIAlignAvg(ops.to_nchw(code, self.feat_dim), rois_t)  # (B*10, C, 5, 5)
+        pooled = self.roi_code[0](ops.to_nhwc(pooled))                       # conv k4 s1 p1 + bias + LReLU
+        out = ops.to_nchw(pooled, pooled.shape[3])
+        return out.view(b, cfg.ROI.BOXES_NUM, out.shape[1], out.shape[2], out.shape[3])
+
+
+class OBJ_SS_D_NET(_ObjD):
+    """ref: model.py:1184-1246 (small-scale objects: 3 encoder layers, 64x64 feature map)."""
+    n_layer = 3
+
+
+class OBJ_LS_D_NET(_ObjD):
+    """ref: model.py:1250-1312 (large-scale objects: 4 encoder layers, 32x32 feature map)."""
+    n_layer = 4
+
+
+# --------------------------------------------------------------------------------------------------
 # ROIAlign modules (ref: models/roi_align/modules/roi_align.py) and the rois blob helper
 # --------------------------------------------------------------------------------------------------
 class RoIAlign(nn.Module):

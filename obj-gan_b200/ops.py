@@ -858,16 +858,62 @@ def paint_max(f, m):
     return _PaintMax.apply(f, m)
 
 
+class _FuncAttention(torch.autograd.Function):
+    """DAMSM attention (reference: GlobalAttention.py:32-70) on the reference's NCHW tensors."""
+
+    @staticmethod
+    def forward(ctx, query, context, gamma1):
+        _chk(query, context)
+        query, context = query.contiguous(), context.contiguous()
+        b, ndf, lq = query.shape
+        ih, iw = context.shape[2:]
+        wc = torch.empty((b, ndf, lq), device=query.device, dtype=torch.float32)
+        attn = torch.empty((b, lq, ih, iw), device=query.device, dtype=torch.float32)
+        _call("og_func_attention_fwd", _p(query), _p(context), b, ndf, lq, ih * iw, float(gamma1), _p(wc), _p(attn))
+        ctx.gamma1 = float(gamma1)
+        ctx.save_for_backward(query, context, attn)
+        return wc, attn
+
+    @staticmethod
+    def backward(ctx, g_wc, g_attn):
+        query, context, attn = ctx.saved_tensors
+        b, ndf, lq = query.shape
+        s = context.shape[2] * context.shape[3]
+        g_q = torch.empty_like(query)
+        g_c = torch.empty_like(context)
+        ga = g_attn.contiguous() if g_attn is not None else None
+        _call("og_func_attention_bwd", _p(query), _p(context), _p(attn), _p(g_wc.contiguous()), _p(ga), b, ndf, lq, s,
+              ctx.gamma1, _p(g_q), _p(g_c))
+        return g_q, g_c, None
+
+
 def func_attention(query, context, gamma1):
-    """DAMSM attention, forward only (reference: GlobalAttention.py:32-70)."""
-    _chk(query, context)
-    query, context = query.contiguous(), context.contiguous()
-    b, ndf, lq = query.shape
-    ih, iw = context.shape[2:]
-    wc = torch.empty((b, ndf, lq), device=query.device, dtype=torch.float32)
-    attn = torch.empty((b, lq, ih, iw), device=query.device, dtype=torch.float32)
-    _call("og_func_attention_fwd", _p(query), _p(context), b, ndf, lq, ih * iw, float(gamma1), _p(wc), _p(attn))
-    return wc, attn
+    return _FuncAttention.apply(query, context, gamma1)
+
+
+class _Bilinear(torch.autograd.Function):
+    """F.interpolate(size, mode='bilinear', align_corners=True) on NHWC tensors."""
+
+    @staticmethod
+    def forward(ctx, x, oh, ow):
+        _chk(x)
+        x = x.contiguous()
+        n, h, w, c = x.shape
+        y = torch.empty((n, oh, ow, c), device=x.device, dtype=torch.float32)
+        _call("og_bilinear_fwd", _p(x), n, h, w, c, oh, ow, _p(y))
+        ctx.dims = (n, h, w, c, oh, ow)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        n, h, w, c, oh, ow = ctx.dims
+        gx = torch.empty((n, h, w, c), device=g.device, dtype=torch.float32)
+        _call("og_bilinear_bwd", _p(g.contiguous()), n, h, w, c, oh, ow, _p(gx))
+        return gx, None, None
+
+
+def bilinear(x, oh, ow):
+    return _Bilinear.apply(x, oh, ow)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -396,6 +396,43 @@ def get_rois_blob_np(fm_rois_xywh, boxes_num=10):
     return np.hstack((levels, flat)).astype(np.float32)
 
 
+class _RoIAlignAvgFn(torch.autograd.Function):
+    """Differentiable wrapper of the numpy ROIAlign restatement (forward + adjoint), for oracle gradients."""
+
+    @staticmethod
+    def forward(ctx, feat, rois, ah, aw, scale):
+        ctx.cfg = (tuple(feat.shape), ah, aw, scale)
+        ctx.rois = rois
+        x = roi_align_forward_np(feat.detach().numpy(), rois, ah + 1, aw + 1, scale)
+        return F.avg_pool2d(torch.from_numpy(x), kernel_size=2, stride=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, ah, aw, scale = ctx.cfg
+        g6 = torch.zeros(g.shape[0], g.shape[1], ah + 1, aw + 1)
+        for dh in (0, 1):
+            for dw in (0, 1):
+                g6[:, :, dh:dh + ah, dw:dw + aw] += g / 4
+        return torch.from_numpy(roi_align_backward_np(g6.numpy(), ctx.rois, shape, ah + 1, aw + 1, scale)), None, None, \
+            None, None
+
+
+def obj_d_net_forward(sd, x, s, fm_rois, n_layer, img_size=512, update=True, boxes_num=10):
+    """OBJ_SS_D_NET / OBJ_LS_D_NET .forward (ref: model.py:1212-1246 / 1278-1312; n_layer = 3 / 4).
+    x (B,3,256,256), s (B,80,256,256), fm_rois (B,10,>=4) [x,y,w,h,...] -> (B, 10, 384, 4, 4).
+    Lines 1227-1241 (the Variable/resize_ idiom that no longer runs) are restated from their intent: build the
+    (B*10, 5) float32 roi blob with _get_rois_blob and pool every slot, valid or not."""
+    x5 = F.interpolate(x, size=(img_size, img_size), mode="bilinear", align_corners=True)
+    s5 = F.interpolate(s, size=(img_size, img_size), mode="bilinear", align_corners=True)
+    ns = reflect_conv3x3(s5, sd["shp_code.1.weight"], sd["shp_code.1.bias"])
+    ns = F.leaky_relu(instance_norm(ns), LRELU)
+    code = pat_d_net(torch.cat((x5, ns), 1), sd, update, n_layer)
+    rois = get_rois_blob_np(np.asarray(fm_rois, dtype=np.float64), boxes_num)
+    pooled = _RoIAlignAvgFn.apply(code, rois, 5, 5, 1.0 / 16.0)
+    out = F.leaky_relu(F.conv2d(pooled, sd["roi_code.0.weight"], sd["roi_code.0.bias"], 1, 1), LRELU)
+    return out.view(x.shape[0], boxes_num, out.shape[1], out.shape[2], out.shape[3])
+
+
 # --------------------------------------------------------------------------------------
 # optimiser (trainer.py:197-224, 461-462)
 # --------------------------------------------------------------------------------------

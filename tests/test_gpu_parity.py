@@ -244,11 +244,17 @@ def test_bu_att_and_paint():
 
 def test_func_attention():
     torch.manual_seed(9)
-    q, ctx = torch.randn(6, 256, 15), torch.randn(6, 256, 17, 17)
+    q, ctx = torch.randn(6, 256, 15, requires_grad=True), torch.randn(6, 256, 17, 17, requires_grad=True)
     w_r, a_r = O.func_attention(q, ctx, 4.0)
-    w, a = ops.func_attention(q.to(DEV), ctx.to(DEV), 4.0)
+    gw, ga = torch.randn_like(w_r), torch.randn_like(a_r)
+    (w_r * gw).sum().add((a_r * ga).sum()).backward()
+    qg, cg = q.detach().to(DEV).requires_grad_(True), ctx.detach().to(DEV).requires_grad_(True)
+    w, a = ops.func_attention(qg, cg, 4.0)
     close(w, w_r)
     close(a, a_r)
+    (w * gw.to(DEV)).sum().add((a * ga.to(DEV)).sum()).backward()
+    close(qg.grad, q.grad, what="g_query")
+    close(cg.grad, ctx.grad, what="g_context")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -502,3 +508,33 @@ def test_cuda_graph_replay_matches_eager():
         close(ob["fake_imgs"][i], oa["fake_imgs"][i], 1e-4, what=f"fake{i}")   # forward is deterministic
     assert rel_l2(b.bG.grad, a.bG.grad) < 1e-2                                  # backward has atomics (order varies)
     assert int(b.bG.step_dev) == int(a.bG.step_dev) == 3 and b.bG.step == 3
+
+
+@pytest.mark.parametrize("cls,n_layer", [("OBJ_SS_D_NET", 3), ("OBJ_LS_D_NET", 4)])
+def test_obj_d_net_parity(cls, n_layer, monkeypatch):
+    """Object discriminators (512x512 bilinear front end, shape code, encoder, RoIAlignAvg, roi code): forward and the
+    gradients w.r.t. the fake image and the parameters, exact-fp32 engine against the oracle."""
+    monkeypatch.setattr(ops, "CONV_ENGINE", "simt")
+    torch.manual_seed(14)
+    net = getattr(model, cls)(80)
+    net.apply(model.weights_init)
+    net.to(DEV)
+    sd = _cpu_sd(net)
+    inp = synth.make_inputs(2, seed=6, parity=True)
+    x, s, fm = inp["imgs"][2], inp["hmaps"][2], inp["fm_rois"]
+    keys = [k for k in O.trainable_keys(sd) if not k.startswith(("COND_DNET", "UNCOND_DNET"))]
+    live, leaves = O._with_grad(sd, keys)
+    xr = x.clone().requires_grad_(True)
+    out_r = O.obj_d_net_forward(live, xr, s, fm.numpy(), n_layer)
+    g = torch.randn_like(out_r)
+    grads = torch.autograd.grad(out_r, [xr] + [leaves[k] for k in keys], g)
+    xg = x.to(DEV).requires_grad_(True)
+    out = net(xg, s.to(DEV), fm.to(DEV), inp["num_rois"].to(DEV))
+    close(out, out_r.detach(), what="fwd")
+    out.backward(g.to(DEV))
+    close_grad(xg.grad, grads[0], what="g_image")
+    params = dict(net.named_parameters())
+    for k, gr in zip(keys, grads[1:]):
+        if k == "shp_code.1.bias":
+            continue      # bias ahead of InstanceNorm: true gradient is zero
+        close_grad(params[k].grad, gr, what=k)
