@@ -77,6 +77,13 @@ int og_pack_weights(const float* w_oihw, int Co, int Ci, int KH, int KW, int Cip
 int og_unpack_wgrad(const float* dw_packed, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split, int splitp,
                     float* grad_oihw, int accumulate, int transposed, cudaStream_t stream);
 
+/* upBlock (nearest 2x upsample + conv3x3, ref: model.py:43-49) as four 2x2 phase convolutions with pre-summed
+ * weights: Wp[16][..] (tap t = ((p*2+q)*2+a)*2+b) from the OIHW parameter, and the adjoint map for the gradient. */
+int og_pack_upsample_weights(const float* w_oihw, int Co, int Ci, int Cip, int Kp, int split, int splitp,
+                             int transposed, float* out, float* out_lo, cudaStream_t stream);
+int og_unpack_upsample_wgrad(const float* dwp, int Co, int Ci, int Cip, int Kp, int split, int splitp,
+                             float* grad_oihw, cudaStream_t stream);
+
 /* Tensor-core path (tcgen05.mma kind::tf32, TMEM accumulators, TMA operand staging) for the stride-1
  * contractions that dominate the step (HmapResBlock / upBlock / jointConv forward and input gradients).
  * og_prep_split writes the tf32 hi/lo parts of an activation tensor (pad=1 also materialises the

@@ -12,6 +12,18 @@
 #include "common.cuh"
 
 constexpr int LMAX = 32;   // max caption length handled in registers (reference uses 12..18)
+
+// Blackwell packed fp32 FMA (FFMA2): two independent fp32 FMAs per issue slot, bit-identical to two fmaf calls.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
 constexpr int ATT_Q = 128; // queries per block
 
 // src[b][c][l] = sum_k W[c][k] * words[b][k][l]
@@ -75,7 +87,7 @@ OG_API int og_words_proj_bwd(const float* words, const float* W, const float* gs
 // Mask quirk (ref: GlobalAttention.py:108): row (b, q) uses the caption mask of sample (b*Q + q) mod B.
 // ---------------------------------------------------------------------------------------------
 template <int LM>
-__global__ void __launch_bounds__(ATT_Q, 8) att_general_fwd_kernel(const float* __restrict__ h,
+__global__ void __launch_bounds__(ATT_Q, 7) att_general_fwd_kernel(const float* __restrict__ h,
                                                                 const float* __restrict__ src,
                                                                 const unsigned char* __restrict__ mask, int B, int Q,
                                                                 int idf, int cs, int L, float* __restrict__ wc,
@@ -102,20 +114,25 @@ __global__ void __launch_bounds__(ATT_Q, 8) att_general_fwd_kernel(const float* 
   __syncthreads();
   if (t < nq) {
     float s[LM];
+    float2 s2[LM / 2];
 #pragma unroll
-    for (int l = 0; l < LM; ++l) s[l] = 0.f;
+    for (int l = 0; l < LM / 2; ++l) s2[l] = make_float2(0.f, 0.f);
     float* row = tile + t * pitch;
     for (int c = 0; c < idf; ++c) {
       const float hv = row[c];
+      const float2 hv2 = make_float2(hv, hv);
       const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
 #pragma unroll
       for (int l4 = 0; l4 < LM / 4; ++l4) {
         const float4 w = sr[l4];
-        s[4 * l4] = fmaf(hv, w.x, s[4 * l4]);
-        s[4 * l4 + 1] = fmaf(hv, w.y, s[4 * l4 + 1]);
-        s[4 * l4 + 2] = fmaf(hv, w.z, s[4 * l4 + 2]);
-        s[4 * l4 + 3] = fmaf(hv, w.w, s[4 * l4 + 3]);
+        s2[2 * l4] = ffma2(hv2, make_float2(w.x, w.y), s2[2 * l4]);
+        s2[2 * l4 + 1] = ffma2(hv2, make_float2(w.z, w.w), s2[2 * l4 + 1]);
       }
+    }
+#pragma unroll
+    for (int l = 0; l < LM / 2; ++l) {
+      s[2 * l] = s2[l].x;
+      s[2 * l + 1] = s2[l].y;
     }
     const int q = q0 + t;
     float mx = -INFINITY;
@@ -140,18 +157,20 @@ __global__ void __launch_bounds__(ATT_Q, 8) att_general_fwd_kernel(const float* 
       s[l] *= inv;
       if (l < L) attn[((long long)b * L + l) * Q + q] = s[l];
     }
+#pragma unroll
+    for (int l = 0; l < LM / 2; ++l) s2[l] = make_float2(s[2 * l], s[2 * l + 1]);
     for (int c = 0; c < cs; ++c) {
       float acc = 0.f;
       if (c < idf) {
         const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
+        float2 a2 = make_float2(0.f, 0.f);   // two interleaved partial sums (even / odd words)
 #pragma unroll
         for (int l4 = 0; l4 < LM / 4; ++l4) {
           const float4 w = sr[l4];
-          acc = fmaf(w.x, s[4 * l4], acc);
-          acc = fmaf(w.y, s[4 * l4 + 1], acc);
-          acc = fmaf(w.z, s[4 * l4 + 2], acc);
-          acc = fmaf(w.w, s[4 * l4 + 3], acc);
+          a2 = ffma2(make_float2(w.x, w.y), s2[2 * l4], a2);
+          a2 = ffma2(make_float2(w.z, w.w), s2[2 * l4 + 1], a2);
         }
+        acc = a2.x + a2.y;
       }
       row[c] = acc;
     }

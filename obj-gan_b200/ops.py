@@ -76,6 +76,18 @@ class PackedWeights:
             _call("og_pack_weights", _p(w), co, ci, kh, kw, cip, kp, split, splitp, 1, _p(self.t), 0)
         return self.f, self.t
 
+    def get_up_hilo(self, w, cip, kp, split, splitp, transposed):
+        """Pre-summed 2x2 phase weights of an upsample+conv3x3 layer, tf32 hi / lo ([16][co][ci] or [16][ci][co])."""
+        self.get(w, cip, kp, split, splitp, False)
+        key = ("up", transposed)
+        if key not in self.hl:
+            co, ci, _, _ = w.shape
+            hi = torch.empty(16 * cip * kp, device=w.device, dtype=torch.float32)
+            lo = torch.empty_like(hi)
+            _call("og_pack_upsample_weights", _p(w), co, ci, cip, kp, split, splitp, transposed, _p(hi), _p(lo))
+            self.hl[key] = (hi, lo)
+        return self.hl[key]
+
     def get_hilo(self, w, cip, kp, split, splitp, transposed):
         """tf32 hi / lo parts of the packed matrix ([tap][co][ci] when transposed else [tap][ci][co])."""
         self.get(w, cip, kp, split, splitp, False)  # refresh the cache key
@@ -178,10 +190,14 @@ def _tc_kind(n, h, w, c, kh, kw, stride, pad, mode):
     return None
 
 
+_UP_OFF = ((-1, 0), (0, 1))   # low-res row/col offsets read by output phase 0 / 1 of upsample + conv3x3
+
+
 def _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act):
     n, h, w, c = x.shape
-    wh, wl = cache.get_hilo(weight, c, kp, split, splitp, 1)          # [tap][co][ci]
     dev = x.device
+    if mode != UPSAMPLE2X:
+        wh, wl = cache.get_hilo(weight, c, kp, split, splitp, 1)      # [tap][co][ci]
     if kind == "s2":                                                   # 4x4 stride 2 pad 1 on space-to-depth phases
         xh, xl = _split(x, s2d=True)
         y = torch.empty((n, h // 2, w // 2, kp), device=dev, dtype=torch.float32)
@@ -203,13 +219,15 @@ def _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act):
         y = torch.empty((n, h, w, kp), device=dev, dtype=torch.float32)
         taps = [(kh - 1, kw - 1, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
         _tc_launch(xh, xl, n, wh, wl, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act)
-    else:  # UPSAMPLE2X: four output phases, taps addressed at low resolution
+    else:  # UPSAMPLE2X: four output phases of 2x2 taps at low resolution, weights pre-summed per phase
+        wh, wl = cache.get_up_hilo(weight, c, kp, split, splitp, 1)
         xh, xl = _split(x, 0)
         y = torch.empty((n, 2 * h, 2 * w, kp), device=dev, dtype=torch.float32)
         for py in range(2):
             for px in range(2):
-                taps = [((py + kh - 1) // 2, (px + kw - 1) // 2, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
-                _tc_launch(xh, xl, n, wh, wl, 9, kp, y, h, w, kp, 2, (py, px), taps, bias_p, act)
+                taps = [(_UP_OFF[py][a], _UP_OFF[px][b], 0, ((py * 2 + px) * 2 + a) * 2 + b)
+                        for a in range(2) for b in range(2)]
+                _tc_launch(xh, xl, n, wh, wl, 16, kp, y, h, w, kp, 2, (py, px), taps, bias_p, act)
     return y
 
 
@@ -217,7 +235,8 @@ def _tc_dgrad(kind, g, cache, weight, c, kp, split, splitp, mode, h, w):
     """Input gradient on the tensor cores.  g: (N, OH, OW, kp); returns (N, h, w, c)."""
     n = g.shape[0]
     dev = g.device
-    wh, wl = cache.get_hilo(weight, c, kp, split, splitp, 0)          # [tap][ci][co]
+    if mode != UPSAMPLE2X:
+        wh, wl = cache.get_hilo(weight, c, kp, split, splitp, 0)      # [tap][ci][co]
     if kind == "s2":
         gh, gl = _split(g, 0)
         oh, ow = g.shape[1], g.shape[2]
@@ -242,18 +261,13 @@ def _tc_dgrad(kind, g, cache, weight, c, kp, split, splitp, mode, h, w):
         taps = [(1 - kh, 1 - kw, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
         _tc_launch(gh, gl, n, wh, wl, 9, c, gx, h, w, c, 1, (0, 0), taps)
         return gx
-    # UPSAMPLE2X: gx[i,j] = sum_{p,q,kh,kw} g[2i+p+1-kh, 2j+q+1-kw] W[kh,kw]^T ; g read through its 4 phase blocks
+    # UPSAMPLE2X: adjoint of the four phase convolutions: gx[i,j] = sum_{p,q,a,b} G_pq[i - off(p,a), j - off(q,b)] Wp^T
+    wh, wl = cache.get_up_hilo(weight, c, kp, split, splitp, 0)
     gh, gl = _split(g, s2d=True)
     gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
-    taps = []
-    for p_ in range(2):
-        for q_ in range(2):
-            for kh in range(3):
-                fh, pp = divmod(p_ + 1 - kh, 2)
-                for kw in range(3):
-                    fw, qq = divmod(q_ + 1 - kw, 2)
-                    taps.append((fh, fw, (pp * 2 + qq) * n, kh * 3 + kw))
-    _tc_launch(gh, gl, n, wh, wl, 9, c, gx, h, w, c, 1, (0, 0), taps)
+    taps = [(-_UP_OFF[p_][a], -_UP_OFF[q_][b], (p_ * 2 + q_) * n, ((p_ * 2 + q_) * 2 + a) * 2 + b)
+            for p_ in range(2) for q_ in range(2) for a in range(2) for b in range(2)]
+    _tc_launch(gh, gl, n, wh, wl, 16, c, gx, h, w, c, 1, (0, 0), taps)
     return gx
 
 
@@ -285,9 +299,9 @@ def _tc_wgrad(kind, x, g, weight, c, kp, split, splitp, mode):
     elif mode == UPSAMPLE2X:
         xh, xl = _split_planar(x, 0, 3, 1)                            # low-res source, shifts -1, 0, +1
         gh, gl = _split_planar(g, s2d=True)                           # 4 phase blocks of the full-res gradient
-        ent = [(p_ * 2 + q_, (p_ + kh - 1) // 2, (q_ + kw - 1) // 2 + 1, kh * 3 + kw)
-               for p_ in range(2) for q_ in range(2) for kh in range(3) for kw in range(3)]
-        gv, xv, sh, sw, oh, ow, nt = 4, 3, h, w, h, w, 9
+        ent = [(p_ * 2 + q_, _UP_OFF[p_][a], _UP_OFF[q_][b] + 1, ((p_ * 2 + q_) * 2 + a) * 2 + b)
+               for p_ in range(2) for q_ in range(2) for a in range(2) for b in range(2)]
+        gv, xv, sh, sw, oh, ow, nt = 4, 3, h, w, h, w, 16
     else:
         pad = 1 if mode == PAD_REFLECT else 0
         origin = 0 if mode == PAD_REFLECT else 1   # zero-pad conv: taps at w-1, w, w+1 of the unpadded source
@@ -301,7 +315,10 @@ def _tc_wgrad(kind, x, g, weight, c, kp, split, splitp, mode):
     _call("og_conv2d_wgrad_tc", _p(gh), _p(gl), n, oh, ow, kp, gv, _p(xh), _p(xl), sh, sw, c, xv, _p(dwp), nt,
           ctypes.addressof(arr), len(ent), _nsplit())
     gw = torch.empty_like(weight)
-    _call("og_unpack_wgrad", _p(dwp), co, ci, kh_, kw_, c, kp, split, splitp, _p(gw), 0, 1)
+    if mode == UPSAMPLE2X and kind == "s1":
+        _call("og_unpack_upsample_wgrad", _p(dwp), co, ci, c, kp, split, splitp, _p(gw))
+    else:
+        _call("og_unpack_wgrad", _p(dwp), co, ci, kh_, kw_, c, kp, split, splitp, _p(gw), 0, 1)
     return gw
 
 
