@@ -160,19 +160,21 @@ def attn_roofline(hbm, src):
     = 7.47 MB."""
     from objgan_b200 import ops
     B, Q, C, L = 16, 16384, 48, 18
-    h = torch.randn(B, 128, 128, C, device="cuda")
-    srcw = torch.randn(B, C, L, device="cuda")
+    # 8 independent input sets (8 x 119 MB >> 126 MB L2): launched back to back between two events, so every launch
+    # reads HBM-cold data and the host's launch latency is hidden behind the previous kernel
+    sets = [(torch.randn(B, 128, 128, C, device="cuda"), torch.randn(B, C, L, device="cuda")) for _ in range(8)]
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
     times = []
-    for i in range(8):
-        flush.zero_()                                       # evict L2 (256 MB > 126 MB)
+    for i in range(6):
+        flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.att_general(h, srcw, None, C)
+        for h, srcw in sets:
+            ops.att_general(h, srcw, None, C)
         e1.record()
         torch.cuda.synchronize()
-        if i >= 3:
-            times.append(e0.elapsed_time(e1))
+        if i >= 2:
+            times.append(e0.elapsed_time(e1) / len(sets))
     ms = sum(times) / len(times)
     byts = 4.0 * Q * (2 * C + L) * B
     ach = byts / (ms * 1e-3) / 1e9
@@ -181,11 +183,35 @@ def attn_roofline(hbm, src):
             "peak_source": f"{src} copy bandwidth"}
 
 
-def cpu_step_a(batch, steps, warmup, seed=1234):
-    """Reference algorithm (oracle port) on the host cores: Step-A at batch `batch`."""
+def _best_cpu_threads():
+    """The reference's CPU path is torch CPU ops; on a many-core host more threads is not always faster at batch 2,
+    so give it the best of a few thread counts (measured on one G forward each) -- the fairest CPU arm we can build."""
     from objgan_b200 import model, synth
     from oracle import objgan_oracle as O
-    torch.set_num_threads(os.cpu_count())
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    g = model.G_NET(80)
+    sd = g.state_dict()
+    inp = synth.make_inputs(2, seed=1, parity=False)
+    best, best_t = cores, float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        with torch.no_grad():
+            O.g_net_forward({k: v.clone() for k, v in sd.items()}, inp)      # warm
+            t0 = time.perf_counter()
+            O.g_net_forward({k: v.clone() for k, v in sd.items()}, inp)
+            dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
+def cpu_step_a(batch, steps, warmup, seed=1234):
+    """Reference algorithm (oracle port) on the host cores: Step-A at batch `batch`.  Returns img/s, s/step, threads."""
+    from objgan_b200 import model, synth
+    from oracle import objgan_oracle as O
+    threads = _best_cpu_threads()
+    torch.set_num_threads(threads)
     torch.manual_seed(seed)
     g = model.G_NET(80)
     ds = [model.PAT_D_NET64(), model.PAT_D_NET128(), model.PAT_D_NET256()]
@@ -197,7 +223,7 @@ def cpu_step_a(batch, steps, warmup, seed=1234):
     for _ in range(steps):
         O.step_a(state, inp)
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps
+    return batch * steps / dt, dt / steps, threads
 
 
 def run_reference(args):
@@ -205,8 +231,7 @@ def run_reference(args):
     if rank != 0:
         return
     B = 2
-    ips, spstep = cpu_step_a(B, args.steps, args.warmup)
-    cores = os.cpu_count()
+    ips, spstep, cores = cpu_step_a(B, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(ips, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(spstep * 1e3, 1), "higher_is_better": True,
@@ -215,7 +240,7 @@ def run_reference(args):
                    "global_batch": B, "words": 18, "rois": 10},
         "cpu_baseline": {"value": round(ips, 4), "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} Step-A steps at batch {B} (oracle/objgan_oracle.py, torch CPU fp32, "
-                                   f"{cores} threads)"},
+                                   f"{cores} threads = best of 8/16/32/64/all {os.cpu_count()} host cores)"},
         "e2e": {"value": round(ips, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -265,9 +290,10 @@ def run_b200(args):
     roof_att = attn_roofline(hbm, src)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ips, sps = cpu_step_a(2, 1, 0)
-        cpu = {"value": round(ips, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"1 Step-A step at batch 2 ({sps:.1f} s) of oracle/objgan_oracle.py, torch CPU fp32, all host threads"}
+        ips, sps, thr = cpu_step_a(2, 1, 0)
+        cpu = {"value": round(ips, 4), "unit": UNIT, "cores": thr, "kind": "port",
+               "sample": f"1 Step-A step at batch 2 ({sps:.1f} s) of oracle/objgan_oracle.py, torch CPU fp32, {thr} threads "
+                         f"(best of 8/16/32/64/all {os.cpu_count()} host cores)"}
     step_tflops = 2 * GMAC_PER_IMG_STEP_A * 1e9 * value / 1e12
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,

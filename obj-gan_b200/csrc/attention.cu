@@ -192,7 +192,8 @@ OG_API int og_att_general_fwd(const float* h, const float* src, const unsigned c
   size_t sm = sizeof(float) * (ATT_Q * (cs + 1) + idf * LMsel);
   dim3 grid(og_cdiv(Q, ATT_Q), B);
   if (L <= 20) {   // captions of the hot path have 12..18 words: keep the per-thread score vector small
-    OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    if (sm > 48 * 1024)
+      OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     att_general_fwd_kernel<20><<<grid, ATT_Q, sm, stream>>>(h, src, mask, B, Q, idf, cs, L, wc, attn);
   } else {
     OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

@@ -973,7 +973,8 @@ OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH,
   }
   // large problems: two pixel tiles per CTA share every weight stage (see conv_tc2_kernel)
   static const bool no_tc2 = getenv("OG_NO_TC2") != nullptr;
-  if (!no_tc2 && p.ksplit == 1 && (BNsel == 208 || BNsel == 256) && (long long)grid.x * grid.y >= 2 * 148 * 2) {
+  static const long long tc2_min = getenv("OG_TC2_MIN") ? atoll(getenv("OG_TC2_MIN")) : 2 * 148 * 2;
+  if (!no_tc2 && p.ksplit == 1 && (BNsel == 208 || BNsel == 256) && (long long)grid.x * grid.y >= tc2_min) {
     dim3 grid2((grid.x + 1) / 2, grid.y, 1);
     return BNsel == 208 ? launch_tc2<208>(mah, mal, mbh, mbl, p, grid2, stream)
                         : launch_tc2<256>(mah, mal, mbh, mbl, p, grid2, stream);

@@ -62,3 +62,41 @@ def KL_loss(mu, logvar):
     rows = torch.zeros(mu.shape[0], ops.cpad(2 * d), device=mu.device)
     rows = torch.cat((mu, logvar, rows[:, 2 * d:]), 1)
     return ops.kl_rows(rows, d, 1.0)
+
+
+def permute_seg(seg_conditions, rois, num_rois):
+    """ref: miscc/utils.py:445-462 -- per sample, shuffle the segmentation channels of the classes present (host
+    `random.shuffle`, like the reference); returns the permuted maps and the indices of the samples that changed."""
+    import random
+    from copy import deepcopy
+
+    import numpy as np
+    new_seg = seg_conditions.clone()
+    rois_np = rois.detach().cpu().numpy() if torch.is_tensor(rois) else np.asarray(rois)
+    nums = num_rois.detach().cpu().numpy().tolist() if torch.is_tensor(num_rois) else list(num_rois)
+    valid = []
+    for b in range(seg_conditions.size(0)):
+        if nums[b] == 0:
+            continue
+        classes = list(np.unique(rois_np[b, :nums[b], 4]).astype(int))
+        shuffled = deepcopy(classes)
+        random.shuffle(shuffled)
+        if classes != shuffled:
+            valid.append(b)
+            new_seg[b, classes] = seg_conditions[b, shuffled]
+    return new_seg, valid
+
+
+def shpD_loss(netShpD, real_imgs, fake_imgs, seg_conditions, rois, num_rois):
+    """ref: miscc/losses.py:213-251."""
+    real_features = netShpD(real_imgs, seg_conditions)
+    fake_features = netShpD(fake_imgs.detach(), seg_conditions)
+    fake_seg, valid = permute_seg(seg_conditions, rois, num_rois)
+    net = netShpD.module if hasattr(netShpD, "module") else netShpD
+    err = ops.bce(net.UNCOND_DNET(real_features), 1.0, 1.0)
+    fake_err = ops.bce(net.UNCOND_DNET(fake_features), 0.0, 1.0)
+    if len(valid) > 0:
+        idx = torch.as_tensor(valid, device=real_imgs.device)
+        wrong = netShpD(real_imgs[idx], fake_seg[idx])
+        return err + (fake_err + ops.bce(net.UNCOND_DNET(wrong), 0.0, 1.0)) / 2.0
+    return err + fake_err

@@ -540,6 +540,40 @@ class PAT_D_NET256(_PatD):
 
 
 # --------------------------------------------------------------------------------------------------
+# shape discriminators (ref: model.py:1111-1179): image || shape-code(seg map) -> conv encoder; UNCOND head only
+# --------------------------------------------------------------------------------------------------
+class _ShpD(_Base):
+    def __init__(self, num_classes):
+        super().__init__()
+        ndf, nef = cfg.GAN.DF_DIM, cfg.TEXT.EMBEDDING_DIM
+        ngf = cfg.GAN.GF_DIM // 4
+        self.img_code = _EncodeImage(ngf, ndf, cfg.GAN.LAYER_D_NUM)
+        self.shp_code = _Slots(_1=Conv2dP(num_classes, ngf, 3, 1, 1, bias=True, mode=PAD_REFLECT))
+        self.UNCOND_DNET = D_GET_LOGITS(ndf, nef, bcondition=False)
+        self.ngf = ngf
+        self.out_channels = ndf * 8
+        self.nhwc_features = True
+
+    def forward(self, x_var, s_var):
+        new_s = ops.instance_norm_act(self.shp_code[1](ops.to_nhwc(s_var)), NA_LRELU)
+        x_s = ops.cat_channels([ops.to_nhwc(x_var), new_s], [x_var.shape[1], self.ngf])
+        f = self.img_code(x_s)
+        return NHWCFeature(f, self.out_channels) if self.nhwc_features else ops.to_nchw(f, self.out_channels)
+
+
+class SHP_D_NET64(_ShpD):
+    """ref: model.py:1111-1132."""
+
+
+class SHP_D_NET128(_ShpD):
+    """ref: model.py:1135-1156."""
+
+
+class SHP_D_NET256(_ShpD):
+    """ref: model.py:1159-1179."""
+
+
+# --------------------------------------------------------------------------------------------------
 # object discriminators (ref: model.py:1184-1312): 512x512 bilinear front end, shape code, conv encoder,
 # RoIAlignAvg over the 10 box slots of every image, roi code.  forward() returns (B, 10, 384, 4, 4) like the reference;
 # the logit heads are D_GET_LOGITS(ndf // 2, nef) applied by objD_loss (loss glue: SURVEY 8f "next").

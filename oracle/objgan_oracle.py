@@ -264,6 +264,13 @@ def d_get_logits(h, sd, p, c_code=None, update=True):
     return torch.sigmoid(F.conv2d(h, sd[p + ".outlogits.0.weight"], sd[p + ".outlogits.0.bias"], 2, 0))
 
 
+def shp_d_net(x, seg, sd, update=True):
+    """SHP_D_NET{64,128,256}.forward (ref: model.py:1111-1179): cat(image, shp_code(seg)) -> conv encoder."""
+    ns = reflect_conv3x3(seg, sd["shp_code.1.weight"], sd["shp_code.1.bias"])
+    ns = F.leaky_relu(instance_norm(ns), LRELU)
+    return pat_d_net(torch.cat((x, ns), 1), sd, update)
+
+
 def bce(p, target):
     """nn.BCELoss() (mean) on probabilities; log clamped at -100 like PyTorch."""
     t = torch.full_like(p, float(target))

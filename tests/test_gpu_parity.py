@@ -538,3 +538,30 @@ def test_obj_d_net_parity(cls, n_layer, monkeypatch):
         if k == "shp_code.1.bias":
             continue      # bias ahead of InstanceNorm: true gradient is zero
         close_grad(params[k].grad, gr, what=k)
+
+
+def test_shp_d_net_parity(monkeypatch):
+    """SHP_D_NET128 body + UNCOND head: forward and parameter / image gradients against the oracle (exact-fp32 engine)."""
+    monkeypatch.setattr(ops, "CONV_ENGINE", "simt")
+    torch.manual_seed(15)
+    net = model.SHP_D_NET128(80)
+    net.apply(model.weights_init)
+    net.to(DEV)
+    sd = _cpu_sd(net)
+    inp = synth.make_inputs(4, seed=7, parity=True)
+    x, seg = inp["imgs"][1], inp["hmaps"][1]
+    keys = O.trainable_keys(sd)
+    live, leaves = O._with_grad(sd, keys)
+    xr = x.clone().requires_grad_(True)
+    loss_r = O.bce(O.d_get_logits(O.shp_d_net(xr, seg, live), live, "UNCOND_DNET"), 1)
+    grads = torch.autograd.grad(loss_r, [xr] + [leaves[k] for k in keys])
+    xg = x.to(DEV).requires_grad_(True)
+    loss = ops.bce(net.UNCOND_DNET(net(xg, seg.to(DEV))), 1.0)
+    assert abs(float(loss) - float(loss_r)) < 1e-4 * max(1.0, abs(float(loss_r)))
+    loss.backward()
+    close_grad(xg.grad, grads[0], what="g_image")
+    params = dict(net.named_parameters())
+    for k, gr in zip(keys, grads[1:]):
+        if k == "shp_code.1.bias":
+            continue
+        close_grad(params[k].grad, gr, what=k)

@@ -106,3 +106,16 @@ def test_prep_split_exact():
     assert ((hi + lo - want).abs() <= want.abs() * 2.0 ** -21).all()
     assert ((hi.view(torch.int32) & 0x1FFF) == 0).all()
     assert ((lo.view(torch.int32) & 0x1FFF) == 0).all()
+
+
+def test_two_tile_kernels_on_small_cases():
+    """The two-tile-per-CTA kernels (conv_tc2 / wgrad2) are normally picked only for >= 592 tiles; force them on the
+    small parity cases through OG_TC2_MIN in a fresh process (the library reads the variable once)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, OG_TC2_MIN="4")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-k",
+                        "test_tc_conv_fwd_dgrad and tf32x3 and (case0 or case1 or case3 or case6)"],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
