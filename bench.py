@@ -151,6 +151,8 @@ def conv_roofline(hbm, bf16_tf, src):
             "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
             "traffic": 1.267e9 if eng != "simt" else None, "ms_per_launch": round(ms, 3),
             "algorithmic_flops_per_launch": flops,
+            "tf32_mma_tflops": round(achieved * (3 if eng == "tf32x3" else 1), 1) if eng != "simt" else None,
+            "frac_of_peak_counting_issued_mmas": round(achieved * (3 if eng == "tf32x3" else 1) / peak, 4) if eng != "simt" else None,
             "peak_source": f"{src} bf16 cuBLAS burst / 2 (tf32:bf16 nominal ratio); {note}; traffic = dram read+write of the "
                            "conv kernel from profiles/r01_ncu_conv_tc_summary.md (single-tile variant)"}
 

@@ -97,7 +97,7 @@ int og_prep_split(const float* x, int N, int H, int W, int C, int pad, int s2d, 
 int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH, int SW, int C, const float* wh,
                  const float* wl, int ntaps_w, int Kw, float* y, int OH, int OW, int K, long long ysn, long long ysh,
                  long long ysw, int OHf, int OWf, int osy, int osx, int opy, int opx, const int* taps_host, int ntaps,
-                 int nsplit, const float* bias, int act, float slope, cudaStream_t stream);
+                 int tap_layout, int nsplit, const float* bias, int act, float slope, cudaStream_t stream);
 /* dw[tap][co][ci] += sum over pixels of G_copy[n,h,w,co] * X_copy[n,h+dh,w,ci]; operands are the channel-planar
  * hi/lo copies written by og_prep_split_planar ([copy][c][n][h][w], row pitch rounded up to 4 floats; pad=1 adds
  * the reflection halo; copies = w-shifted and/or space-to-depth phase versions, because a TMA box must start

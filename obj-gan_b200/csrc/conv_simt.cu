@@ -320,25 +320,38 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
 // and the kernel-native K-major matrices.
 //   co_map(co) = co < split ? co : co + (splitp - split)   (GLU halves each padded to splitp)
 // ---------------------------------------------------------------------------------------------
+// output-major: one thread per element of the packed matrix (coalesced writes, zero padding written in place; the
+// strided OIHW reads hit the same 32-byte sectors for neighbouring taps and stay in L1/L2)
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Co, int Ci, int KH, int KW, int Cip, int Kp,
                                     int split, int splitp, int transposed, float* __restrict__ out,
                                     float* __restrict__ out_lo) {
-  long long total = (long long)Co * Ci * KH * KW;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int kw = (int)(i % KW);
-    long long t = i / KW;
-    int kh = (int)(t % KH);
-    t /= KH;
-    int ci = (int)(t % Ci);
-    int co = (int)(t / Ci);
-    int cm = (split > 0 && co >= split) ? co + (splitp - split) : co;
-    long long o;
-    if (!transposed)
-      o = ((long long)(kh * KW + kw) * Cip + ci) * Kp + cm;
-    else
-      o = ((long long)(kh * KW + kw) * Kp + cm) * Cip + ci;
-    float v = w[i];
+  const long long total = (long long)KH * KW * Cip * Kp;
+  const int taps = KH * KW;
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total;
+       o += (long long)gridDim.x * blockDim.x) {
+    int cm, ci, tap;
+    if (!transposed) {            // [(tap, ci)][cm]
+      cm = (int)(o % Kp);
+      long long t = o / Kp;
+      ci = (int)(t % Cip);
+      tap = (int)(t / Cip);
+    } else {                      // [(tap, cm)][ci]
+      ci = (int)(o % Cip);
+      long long t = o / Cip;
+      cm = (int)(t % Kp);
+      tap = (int)(t / Kp);
+    }
+    // inverse of the GLU-half padding map: cm -> co (or a padding lane)
+    int co;
+    if (split > 0) {
+      if (cm < split) co = cm;
+      else if (cm >= splitp && cm < splitp + split) co = cm - (splitp - split);
+      else co = -1;
+    } else {
+      co = cm < Co ? cm : -1;
+    }
+    float v = 0.f;
+    if (co >= 0 && co < Co && ci < Ci) v = __ldg(w + ((long long)co * Ci + ci) * taps + tap);
     if (out_lo) {  // tf32 hi/lo split for the 3xTF32 tensor-core path
       uint32_t uh, ul;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(uh) : "f"(v));
@@ -563,10 +576,7 @@ OG_API int og_conv2d_wgrad_simt(const float* x, int N, int H, int W, int C, long
 
 OG_API int og_pack_weights(const float* w_oihw, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split,
                            int splitp, int transposed, float* out, float* out_lo, cudaStream_t stream) {
-  long long n = (long long)KH * KW * Cip * Kp;
-  OG_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * n, stream));
-  if (out_lo) OG_CHECK(cudaMemsetAsync(out_lo, 0, sizeof(float) * n, stream));
-  long long total = (long long)Co * Ci * KH * KW;
+  long long total = (long long)KH * KW * Cip * Kp;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_weights_kernel<<<blocks, 256, 0, stream>>>(w_oihw, Co, Ci, KH, KW, Cip, Kp, split, splitp, transposed, out,

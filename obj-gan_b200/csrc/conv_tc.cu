@@ -59,6 +59,7 @@ struct TcParams {
   int act;
   float slope;
   int ksplit;               // > 1: gridDim.z CTAs share one output tile, each reduces a slice of the (tap, chunk) loop
+  int tall;                 // taps come in groups of 3 consecutive source rows: load one (TH+2)-row A patch per group
   TcTaps taps;
 };
 
@@ -340,13 +341,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
 // sharing each B (weight) stage between two A (pixel) tiles cuts that to 58.5 KB per tile.  Separate smem rings:
 // 3 A slots (hi+lo, 32 KB each) and 2 B slots.
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+// TALL = true (3x3 stride-1 taps, 8x16 pixel patches): the three kernel rows of one kernel column read the same
+// pixels shifted by whole patch rows, so ONE (8+2)-row A patch per (kernel column, channel chunk) serves three
+// k-iterations through descriptor offsets of 16 rows (2 KB, swizzle-phase preserving): A traffic / 2.4.
+template <int BN, bool TALL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                 const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                 const TcParams p) {
   constexpr int AS = 3, BS = 2;
-  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;   // 16 KB (one of hi / lo)
+  constexpr uint32_t A_BYTES = (TALL ? 160 : TC_BM) * TC_BK * 4;   // one of hi / lo: 128 rows, or 10 x 16 patch rows
   constexpr uint32_t B_BYTES = BN * TC_BK * 4;
   constexpr uint32_t A_SLOT = 2 * A_BYTES, B_SLOT = 2 * B_BYTES;
   constexpr uint32_t ACC_STRIDE = 256;               // TMEM column offset of the second accumulator
@@ -391,24 +395,41 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      for (int it = 0; it < nk; ++it) {
-        const int tap = it / p.cchunks, cc = it - tap * p.cchunks;
-        const int c0 = cc * TC_BK, widx = p.taps.widx[tap];
+      auto load_b = [&](int tap, int c0) {
         mbar_wait(&emptyB[bs], bph ^ 1);
         uint8_t* sb = smem_b + (size_t)bs * B_SLOT;
         mbar_expect_tx(&fullB[bs], split3 ? B_SLOT : B_BYTES);
-        tma_load_3d(sb, &map_bh, &fullB[bs], c0, col0, widx);
-        if (split3) tma_load_3d(sb + B_BYTES, &map_bl, &fullB[bs], c0, col0, widx);
+        tma_load_3d(sb, &map_bh, &fullB[bs], c0, col0, p.taps.widx[tap]);
+        if (split3) tma_load_3d(sb + B_BYTES, &map_bl, &fullB[bs], c0, col0, p.taps.widx[tap]);
         if (++bs == BS) { bs = 0; bph ^= 1; }
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          mbar_wait(&emptyA[as], aph ^ 1);
-          uint8_t* sa = smem_a + (size_t)as * A_SLOT;
-          mbar_expect_tx(&fullA[as], split3 ? A_SLOT : A_BYTES);
-          const int ws = tw0[hf] + p.taps.dw[tap], hs = th0[hf] + p.taps.dh[tap], ns = tn0[hf] + p.taps.dn[tap];
-          tma_load_4d(sa, &map_ah, &fullA[as], c0, ws, hs, ns);
-          if (split3) tma_load_4d(sa + A_BYTES, &map_al, &fullA[as], c0, ws, hs, ns);
-          if (++as == AS) { as = 0; aph ^= 1; }
+      };
+      auto load_a = [&](int hf, int tap, int c0) {
+        mbar_wait(&emptyA[as], aph ^ 1);
+        uint8_t* sa = smem_a + (size_t)as * A_SLOT;
+        mbar_expect_tx(&fullA[as], split3 ? A_SLOT : A_BYTES);
+        const int ws = tw0[hf] + p.taps.dw[tap], hs = th0[hf] + p.taps.dh[tap], ns = tn0[hf] + p.taps.dn[tap];
+        tma_load_4d(sa, &map_ah, &fullA[as], c0, ws, hs, ns);
+        if (split3) tma_load_4d(sa + A_BYTES, &map_al, &fullA[as], c0, ws, hs, ns);
+        if (++as == AS) { as = 0; aph ^= 1; }
+      };
+      if (TALL) {
+        const int groups = (p.taps.n / 3) * p.cchunks;
+        for (int g = 0; g < groups; ++g) {
+          const int kwi = g / p.cchunks, cc = g - kwi * p.cchunks;
+          const int c0 = cc * TC_BK, t0 = kwi * 3;       // taps t0, t0+1, t0+2: same column, consecutive rows
+          load_a(0, t0, c0);
+          load_b(t0, c0);                                // first weight stage before the second patch: the MMAs of
+          load_a(1, t0, c0);                             // half 0 can start while half 1's patch is in flight
+          load_b(t0 + 1, c0);
+          load_b(t0 + 2, c0);
+        }
+      } else {
+        for (int it = 0; it < nk; ++it) {
+          const int tap = it / p.cchunks, cc = it - tap * p.cchunks;
+          const int c0 = cc * TC_BK;
+          load_b(tap, c0);
+          load_a(0, tap, c0);
+          load_a(1, tap, c0);
         }
       }
     }
@@ -417,34 +438,62 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
       const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      for (int it = 0; it < nk; ++it) {
-        mbar_wait(&fullB[bs], bph);
-        const uint32_t sb = smem_u32(smem_b + (size_t)bs * B_SLOT);
+      auto mma_half = [&](uint32_t sa, uint32_t rowoff, uint32_t sb, int hf, bool first) {
+        const uint64_t ah = make_desc_sw128(sa + rowoff), al = make_desc_sw128(sa + A_BYTES + rowoff);
         const uint64_t bh = make_desc_sw128(sb), bl = make_desc_sw128(sb + B_BYTES);
+        const uint32_t d = tmem_base + hf * ACC_STRIDE;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          mbar_wait(&fullA[as], aph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a + (size_t)as * A_SLOT);
-          const uint64_t ah = make_desc_sw128(sa), al = make_desc_sw128(sa + A_BYTES);
-          const uint32_t d = tmem_base + hf * ACC_STRIDE;
-#pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
-            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-            if (split3) {
-              umma_tf32(d, al + koff, bh + koff, idesc, acc);
-              umma_tf32(d, ah + koff, bl + koff, idesc, 1u);
-              umma_tf32(d, ah + koff, bh + koff, idesc, 1u);
-            } else {
-              umma_tf32(d, ah + koff, bh + koff, idesc, acc);
-            }
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+          const uint32_t acc = (!first || k > 0) ? 1u : 0u;
+          if (split3) {
+            umma_tf32(d, al + koff, bh + koff, idesc, acc);
+            umma_tf32(d, ah + koff, bl + koff, idesc, 1u);
+            umma_tf32(d, ah + koff, bh + koff, idesc, 1u);
+          } else {
+            umma_tf32(d, ah + koff, bh + koff, idesc, acc);
           }
-          umma_commit(&emptyA[as]);
-          if (++as == AS) { as = 0; aph ^= 1; }
         }
-        umma_commit(&emptyB[bs]);
-        if (++bs == BS) { bs = 0; bph ^= 1; }
+      };
+      if (TALL) {
+        const int groups = (p.taps.n / 3) * p.cchunks;
+        for (int g = 0; g < groups; ++g) {
+          const int a0 = as, a1 = (as + 1) % AS;
+          const uint32_t aph0 = aph, aph1 = (as + 1 == AS) ? (aph ^ 1) : aph;
+          for (int j = 0; j < 3; ++j) {
+            mbar_wait(&fullB[bs], bph);
+            const uint32_t sb = smem_u32(smem_b + (size_t)bs * B_SLOT);
+            if (j == 0) mbar_wait(&fullA[a0], aph0);
+            tc_fence_after();
+            mma_half(smem_u32(smem_a + (size_t)a0 * A_SLOT), j * 16 * 128, sb, 0, g == 0 && j == 0);
+            if (j == 0) {
+              mbar_wait(&fullA[a1], aph1);
+              tc_fence_after();
+            }
+            mma_half(smem_u32(smem_a + (size_t)a1 * A_SLOT), j * 16 * 128, sb, 1, g == 0 && j == 0);
+            umma_commit(&emptyB[bs]);
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+          umma_commit(&emptyA[a0]);
+          umma_commit(&emptyA[a1]);
+          for (int k = 0; k < 2; ++k)
+            if (++as == AS) { as = 0; aph ^= 1; }
+        }
+      } else {
+        for (int it = 0; it < nk; ++it) {
+          mbar_wait(&fullB[bs], bph);
+          const uint32_t sb = smem_u32(smem_b + (size_t)bs * B_SLOT);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            mbar_wait(&fullA[as], aph);
+            tc_fence_after();
+            mma_half(smem_u32(smem_a + (size_t)as * A_SLOT), 0, sb, hf, it == 0);
+            umma_commit(&emptyA[as]);
+            if (++as == AS) { as = 0; aph ^= 1; }
+          }
+          umma_commit(&emptyB[bs]);
+          if (++bs == BS) { bs = 0; bph ^= 1; }
+        }
       }
       umma_commit(&tmem_full_bar);
     }
@@ -868,17 +917,17 @@ int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap
   return (int)cudaGetLastError();
 }
 
-template <int BN>
+template <int BN, bool TALL>
 int launch_tc2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                const TcParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)3 * (2 * TC_BM * TC_BK * 4) + (size_t)2 * (2 * BN * TC_BK * 4) + 1024;
+  constexpr size_t smem = (size_t)3 * (2 * (TALL ? 160 : TC_BM) * TC_BK * 4) + (size_t)2 * (2 * BN * TC_BK * 4) + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, TALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  conv_tc2_kernel<BN><<<grid, TC_THREADS, smem, stream>>>(ah, al, bh, bl, p);
+  conv_tc2_kernel<BN, TALL><<<grid, TC_THREADS, smem, stream>>>(ah, al, bh, bl, p);
   return (int)cudaGetLastError();
 }
 
@@ -893,12 +942,14 @@ int launch_tc2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
 //   rows of the GEMM are the pixel grid N x OH x OW; output pixel (osy*h + opy, osx*w + opx)
 //   taps  : ntaps quadruples (dh, dw, dn, weight tap index): source pixel = image n + dn, (h + dh, w + dw), zero
 //           outside [0,SH)x[0,SW);  bias/act: optional epilogue (bias[K], OG_ACT_*)
+//   tap_layout = 1 promises that the taps come in groups of three with equal dw, dn and dh = d0, d0+1, d0+2 (3x3
+//           kernels listed column by column), which lets the kernel reuse one tall pixel patch for three taps
 // ------------------------------------------------------------------------------------------------
 OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH, int SW, int C, const float* wh,
                         const float* wl, int ntaps_w, int Kw, float* y, int OH, int OW, int K, long long ysn,
                         long long ysh, long long ysw, int OHf, int OWf, int osy, int osx, int opy, int opx,
-                        const int* taps_host, int ntaps, int nsplit, const float* bias, int act, float slope,
-                        cudaStream_t stream) {
+                        const int* taps_host, int ntaps, int tap_layout, int nsplit, const float* bias, int act,
+                        float slope, cudaStream_t stream) {
   if (C % 4 || K % 4 || ntaps < 1 || ntaps > TC_MAX_TAPS || (nsplit != 1 && nsplit != 3)) return (int)cudaErrorInvalidValue;
   if ((long long)N * OH * OW == 0) return 0;
   TcParams p;
@@ -913,6 +964,7 @@ OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH,
   if (SN != N && (N % TN) != 0) return (int)cudaErrorInvalidValue;
   p.TN = TN; p.TH = TH; p.TW = TW;
   p.bias = bias; p.act = act; p.slope = slope;
+  p.tall = 0;
   p.tiles_w = og_cdiv(OW, TW);
   p.tiles_h = og_cdiv(OH, TH);
   const int tiles_n = og_cdiv(N, TN);
@@ -976,8 +1028,22 @@ OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH,
   static const long long tc2_min = getenv("OG_TC2_MIN") ? atoll(getenv("OG_TC2_MIN")) : 2 * 148 * 2;
   if (!no_tc2 && p.ksplit == 1 && (BNsel == 208 || BNsel == 256) && (long long)grid.x * grid.y >= tc2_min) {
     dim3 grid2((grid.x + 1) / 2, grid.y, 1);
-    return BNsel == 208 ? launch_tc2<208>(mah, mal, mbh, mbl, p, grid2, stream)
-                        : launch_tc2<256>(mah, mal, mbh, mbl, p, grid2, stream);
+    static const bool no_tall = getenv("OG_NO_TALL") != nullptr;
+    if (!no_tall && tap_layout == 1 && ntaps % 3 == 0 && BNsel == 208 && TN == 1 && TH == 8 && TW == 16) {
+      // taps are ordered (column-major) in groups of three consecutive source rows: one tall A patch per group
+      unsigned tbox[4] = {(unsigned)TC_BK, 16u, 10u, 1u};
+      CUtensorMap tah, tal;
+      if ((rc = make_map(&tah, xh, 4, adims, astr, tbox))) return rc;
+      if (nsplit == 3) {
+        if ((rc = make_map(&tal, xl, 4, adims, astr, tbox))) return rc;
+      } else {
+        tal = tah;
+      }
+      p.tall = 1;
+      return launch_tc2<208, true>(tah, tal, mbh, mbl, p, grid2, stream);
+    }
+    return BNsel == 208 ? launch_tc2<208, false>(mah, mal, mbh, mbl, p, grid2, stream)
+                        : launch_tc2<256, false>(mah, mal, mbh, mbl, p, grid2, stream);
   }
   switch (BNsel) {
     case 32:  return launch_tc<32, 4>(mah, mal, mbh, mbl, p, grid, stream);

@@ -63,10 +63,13 @@ class PackedWeights:
         self.t = None
         self.hl = {}
 
-    def get(self, w, cip, kp, split, splitp, need_t):
+    def _refresh(self, w, cip, kp, split):
         key = (w.data_ptr(), w._version, _param_epoch[0], cip, kp, split)
         if key != self.key:
             self.key, self.f, self.t, self.hl = key, None, None, {}
+
+    def get(self, w, cip, kp, split, splitp, need_t):
+        self._refresh(w, cip, kp, split)
         co, ci, kh, kw = w.shape
         if self.f is None:
             self.f = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float32)
@@ -78,7 +81,7 @@ class PackedWeights:
 
     def get_up_hilo(self, w, cip, kp, split, splitp, transposed):
         """Pre-summed 2x2 phase weights of an upsample+conv3x3 layer, tf32 hi / lo ([16][co][ci] or [16][ci][co])."""
-        self.get(w, cip, kp, split, splitp, False)
+        self._refresh(w, cip, kp, split)
         key = ("up", transposed)
         if key not in self.hl:
             co, ci, _, _ = w.shape
@@ -90,7 +93,7 @@ class PackedWeights:
 
     def get_hilo(self, w, cip, kp, split, splitp, transposed):
         """tf32 hi / lo parts of the packed matrix ([tap][co][ci] when transposed else [tap][ci][co])."""
-        self.get(w, cip, kp, split, splitp, False)  # refresh the cache key
+        self._refresh(w, cip, kp, split)
         if transposed not in self.hl:
             co, ci, kh, kw = w.shape
             hi = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float32)
@@ -151,15 +154,15 @@ def _split_planar(x, pad=0, nshift=1, origin=0, s2d=False):
     return th, tl
 
 
-def _tc_launch(xh, xl, n, wh, wl, ntaps_w, kw_rows, y, oh, ow, k, osy, op, taps, bias=None, act=ACT_NONE):
+def _tc_launch(xh, xl, n, wh, wl, ntaps_w, kw_rows, y, oh, ow, k, osy, op, taps, bias=None, act=ACT_NONE, layout=0):
     """taps: (dh, dw, dn, widx) quadruples; xh is [SN, SH, SW, C] with SN = n or 4n (space-to-depth source)."""
     sn, sh, sw, c = xh.shape
     _, ohf, owf, kc = y.shape
     arr = _int_array(taps)
     import ctypes
     _call("og_conv2d_tc", _p(xh), _p(xl), n, sn, sh, sw, c, _p(wh), _p(wl), ntaps_w, kw_rows, _p(y), oh, ow, k,
-          ohf * owf * kc, owf * kc, kc, ohf, owf, osy, osy, op[0], op[1], ctypes.addressof(arr), len(taps), _nsplit(),
-          _p(bias), act, LRELU_SLOPE)
+          ohf * owf * kc, owf * kc, kc, ohf, owf, osy, osy, op[0], op[1], ctypes.addressof(arr), len(taps), layout,
+          _nsplit(), _p(bias), act, LRELU_SLOPE)
 
 
 def _tile_n(oh, ow):
@@ -212,13 +215,13 @@ def _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act):
     if mode == PAD_REFLECT:
         xh, xl = _split(x, 1)
         y = torch.empty((n, h, w, kp), device=dev, dtype=torch.float32)
-        taps = [(kh, kw, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
-        _tc_launch(xh, xl, n, wh, wl, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act)
+        taps = [(kh, kw, 0, kh * 3 + kw) for kw in range(3) for kh in range(3)]      # column by column (layout 1)
+        _tc_launch(xh, xl, n, wh, wl, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act, layout=1)
     elif mode == PAD_ZERO:
         xh, xl = _split(x, 0)
         y = torch.empty((n, h, w, kp), device=dev, dtype=torch.float32)
-        taps = [(kh - 1, kw - 1, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
-        _tc_launch(xh, xl, n, wh, wl, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act)
+        taps = [(kh - 1, kw - 1, 0, kh * 3 + kw) for kw in range(3) for kh in range(3)]
+        _tc_launch(xh, xl, n, wh, wl, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act, layout=1)
     else:  # UPSAMPLE2X: four output phases of 2x2 taps at low resolution, weights pre-summed per phase
         wh, wl = cache.get_up_hilo(weight, c, kp, split, splitp, 1)
         xh, xl = _split(x, 0)
@@ -250,16 +253,16 @@ def _tc_dgrad(kind, g, cache, weight, c, kp, split, splitp, mode, h, w):
     if mode == PAD_REFLECT:
         gh, gl = _split(g, 0)
         gpad = torch.empty((n, h + 2, w + 2, c), device=dev, dtype=torch.float32)
-        taps = [(-kh, -kw, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
-        _tc_launch(gh, gl, n, wh, wl, 9, c, gpad, h + 2, w + 2, c, 1, (0, 0), taps)
+        taps = [(-kh, -kw, 0, kh * 3 + kw) for kw in range(3) for kh in (2, 1, 0)]   # rows ascending: -2, -1, 0
+        _tc_launch(gh, gl, n, wh, wl, 9, c, gpad, h + 2, w + 2, c, 1, (0, 0), taps, layout=1)
         gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
         _call("og_reflect_pad_bwd", _p(gpad), n, h, w, c, _p(gx))
         return gx
     if mode == PAD_ZERO:
         gh, gl = _split(g, 0)
         gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
-        taps = [(1 - kh, 1 - kw, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
-        _tc_launch(gh, gl, n, wh, wl, 9, c, gx, h, w, c, 1, (0, 0), taps)
+        taps = [(1 - kh, 1 - kw, 0, kh * 3 + kw) for kw in range(3) for kh in (2, 1, 0)]
+        _tc_launch(gh, gl, n, wh, wl, 9, c, gx, h, w, c, 1, (0, 0), taps, layout=1)
         return gx
     # UPSAMPLE2X: adjoint of the four phase convolutions: gx[i,j] = sum_{p,q,a,b} G_pq[i - off(p,a), j - off(q,b)] Wp^T
     wh, wl = cache.get_up_hilo(weight, c, kp, split, splitp, 0)
