@@ -98,15 +98,13 @@ int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH, int SW
                  const float* wl, int ntaps_w, int Kw, float* y, int OH, int OW, int K, long long ysn, long long ysh,
                  long long ysw, int OHf, int OWf, int osy, int osx, int opy, int opx, const int* taps_host, int ntaps,
                  int tap_layout, int nsplit, const float* bias, int act, float slope, cudaStream_t stream);
-/* dw[tap][co][ci] += sum over pixels of G_copy[n,h,w,co] * X_copy[n,h+dh,w,ci]; operands are the channel-planar
- * hi/lo copies written by og_prep_split_planar ([copy][c][n][h][w], row pitch rounded up to 4 floats; pad=1 adds
- * the reflection halo; copies = w-shifted and/or space-to-depth phase versions, because a TMA box must start
- * 16-byte aligned in its innermost dimension, so a tap's w offset selects a copy instead of shifting the box).
- * entries_host: nentries quadruples (g copy, dh, x copy, output tap). */
-int og_prep_split_planar(const float* x, int N, int H, int W, int C, int pad, int nshift, int origin, int s2d,
-                         float* th, float* tl, cudaStream_t stream);
-int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int OH, int OW, int Kp, int gvariants, const float* xh,
-                       const float* xl, int SH, int SW, int C, int xvariants, float* dw, int ntaps_out,
+/* Weight gradient: dw[tap][co][ci] = sum_{n,h,w} G[n+gdn, h, w, co] * X[n+xdn, h+dh, w+dw, ci]  (X out of range = 0).
+ * Both operands are the same NHWC hi/lo tensors og_prep_split writes for the forward / input-gradient kernels
+ * (G: [GN][OH][OW][Kp], X: [XN][SH][SW][C]; GN / XN = N or 4N space-to-depth blocks), consumed MN-major by
+ * tcgen05.mma (128B swizzle with 32-byte atoms); each needs 512 readable bytes after its last element.
+ * entries_host: nentries quintuples (gdn, dh, dw, xdn, output tap); dw is [ntaps_out][Kp][C], zero-filled here. */
+int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int GN, int OH, int OW, int Kp, const float* xh,
+                       const float* xl, int XN, int SH, int SW, int C, float* dw, int ntaps_out,
                        const int* entries_host, int nentries, int nsplit, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------

@@ -563,11 +563,11 @@ EncodeTiledFn get_encode() {
 
 // fp32 tensor viewed as [d3][d2][d1][d0] (d0 contiguous); strides in elements for d1..d3
 int make_map(CUtensorMap* m, const float* base, int rank, const unsigned long long* dims,
-             const unsigned long long* strides_elems, const unsigned* box) {
+             const unsigned long long* strides_elems, const unsigned* box, bool atom32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return (int)cudaErrorNotSupported;
-  cuuint64_t gdim[4], gstr[3];
-  cuuint32_t bx[4], es[4];
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
@@ -575,8 +575,8 @@ int make_map(CUtensorMap* m, const float* base, int rank, const unsigned long lo
   }
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_elems[i] * sizeof(float);
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 1000 + (int)r;
 }
 
@@ -598,17 +598,19 @@ int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
 // ------------------------------------------------------------------------------------------------
 // weight gradient on the tensor cores.
 //   dW[t][co][ci] += sum_{n,h,w} G[n,h,w,co] * X[n, h+dh_t, w+dw_t, ci]
-// GEMM per tap: M = co, N = ci, reduction over pixels.  tcgen05.mma wants the reduction index contiguous
-// (K-major) for the proven 128B-swizzle operand path, so og_prep_split_planar first writes channel-planar
-// hi/lo copies  Gt[co][n][h][w], Xt[ci][n][h][w]  (a bandwidth pass, ~20% of the MMA time at stage 3).
-// One pipeline stage = 32 consecutive pixels of one image row: A tile = 128 co x 32 pixels, B tile = BNW ci x
-// 32 pixels, both plain 4-D TMA boxes with out-of-bounds zero fill (which also implements the tap shift at
-// the borders).  Grid: (co tiles of 128, taps, pixel splits); partial sums are reduced with fp32 atomics.
+// GEMM per tap: M = co, N = ci, reduction over pixels.  Both operands are read straight from the NHWC hi/lo
+// tensors the forward / input-gradient kernels already use, i.e. they are "MN-major" for the MMA (channel index
+// contiguous, reduction index = smem row).  For 32-bit operands tcgen05 accepts that only in the 128-byte
+// swizzle with 32-byte atoms (descriptor layout type 1; the ordinary 128B swizzle silently yields zeros --
+// tests/probes/probe_mnmajor.cu), which TMA produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  A smem operand
+// is a stack of "slabs" (32 channels x 32 pixels = 32 rows of 128 bytes, LBO = 4096 apart; 4-row groups SBO =
+// 512 apart); one 5-D TMA box (32 channels-in-slab, w, h, n, slab) fills all slabs of an operand, the tap shift
+// is a plain coordinate offset with out-of-bounds zero fill.  One MMA consumes 8 pixel rows (K = 8).
+// Grid: (co tiles x ci tiles, taps, pixel splits); partial sums are reduced with fp32 atomics.
 // ------------------------------------------------------------------------------------------------
 struct TcWgradParams {
   int N, OH, OW;        // pixel grid of G
   int cw, chh, cn;      // pixel chunk of one stage: cw x chh x cn = 32 pixels (w fastest)
-  int flatW;            // > 0: maps narrower than 32 pixels are addressed with (h, w) flattened (row length flatW)
   int wchunks, hchunks; // chunks per row / per image column
   int total_chunks;
   int chunks_per_cta;
@@ -616,19 +618,42 @@ struct TcWgradParams {
   int cotiles;          // blockIdx.x = citile * cotiles + cotile
   int nsplit;
   float* dw;            // [ntaps_out][Kp][C]
-  // entry e: dW[out[e]] += G(rows offset aoff[e]) * X(row offset dh[e], planar copy bvar[e])
-  int aoff[TC_MAX_TAPS], dh[TC_MAX_TAPS], bvar[TC_MAX_TAPS], out[TC_MAX_TAPS];
+  // entry e: dW[out[e]] += G[n + gdn[e], h, w]^T * X[n + xdn[e], h + xdh[e], w + xdw[e]]
+  int gdn[TC_MAX_TAPS], xdh[TC_MAX_TAPS], xdw[TC_MAX_TAPS], xdn[TC_MAX_TAPS], out[TC_MAX_TAPS];
 };
 
-constexpr int WG_PIX = 32;    // pixels per stage = one 128-byte swizzle row (4 MMA k-steps)
+constexpr int WG_PIX = 32;                     // pixels per stage (4 MMA k-steps)
+constexpr uint32_t WG_SLAB = WG_PIX * 128;     // bytes of one slab: 32 pixels x 32 channels
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// MN-major slab stack, 128B swizzle with 32-byte atoms: LBO = slab pitch, SBO = 4 rows * 128 B
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(WG_SLAB >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                          // layout type: SWIZZLE_128B_BASE32B
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_tf32_mn(int M, int N) {
+  return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);   // A and B both MN-major
+}
 
 template <int BNW, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_constant__ CUtensorMap map_gl,
                      const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                      const TcWgradParams p) {
-  constexpr uint32_t A_BYTES = TC_BM * WG_PIX * 4;        // 16 KB
-  constexpr uint32_t B_BYTES = BNW * WG_PIX * 4;
+  constexpr int NSB = (BNW + 31) / 32;                    // slabs of the X operand
+  constexpr uint32_t A_BYTES = 4 * WG_SLAB;               // 128 co = 4 slabs = 16 KB
+  constexpr uint32_t B_BYTES = NSB * WG_SLAB;
   constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   constexpr uint32_t TMEM_COLS = BNW <= 32 ? 32 : BNW <= 64 ? 64 : BNW <= 128 ? 128 : 256;
   extern __shared__ uint8_t smem_raw[];
@@ -664,7 +689,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int dh = p.dh[tap], brow = p.bvar[tap] * p.C + citile * BNW, arow = p.aoff[tap] + cotile * TC_BM;
+      const int gdn = p.gdn[tap], xdh = p.xdh[tap], xdw = p.xdw[tap], xdn = p.xdn[tap];
+      const int aslab = cotile * 4, bslab = citile * NSB;
       for (int it = 0; it < nk; ++it) {
         const int ch = ch_beg + it;
         const int wc = ch % p.wchunks;
@@ -674,16 +700,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
         mbar_expect_tx(&full_bar[stage], tx_bytes);
-        // the innermost TMA coordinate must stay 16-byte aligned, so the w shift of the tap selects one of the
-        // pre-shifted planar copies of X (see og_prep_split_planar) instead of moving the box; the row shift dh is
-        // a coordinate offset (flattened maps: dh * row length, still a multiple of 4 floats)
-        const int bw = p.flatW ? w0 + dh * p.flatW : w0;
-        const int bh = p.flatW ? 0 : h + dh;
-        tma_load_4d(sa, &map_gh, &full_bar[stage], w0, h, n, arow);
-        tma_load_4d(sa + 2 * A_BYTES, &map_xh, &full_bar[stage], bw, bh, n, brow);
+        tma_load_5d(sa, &map_gh, &full_bar[stage], 0, w0, h, n + gdn, aslab);
+        tma_load_5d(sa + 2 * A_BYTES, &map_xh, &full_bar[stage], 0, w0 + xdw, h + xdh, n + xdn, bslab);
         if (p.nsplit == 3) {
-          tma_load_4d(sa + A_BYTES, &map_gl, &full_bar[stage], w0, h, n, arow);
-          tma_load_4d(sa + 2 * A_BYTES + B_BYTES, &map_xl, &full_bar[stage], bw, bh, n, brow);
+          tma_load_5d(sa + A_BYTES, &map_gl, &full_bar[stage], 0, w0, h, n + gdn, aslab);
+          tma_load_5d(sa + 2 * A_BYTES + B_BYTES, &map_xl, &full_bar[stage], 0, w0 + xdw, h + xdh, n + xdn, bslab);
         }
         if (++stage == STAGES) {
           stage = 0;
@@ -693,18 +714,18 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TC_BM, BNW);
+      const uint32_t idesc = make_idesc_tf32_mn(TC_BM, BNW);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nk; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-        const uint64_t ah = make_desc_sw128(sa), al = make_desc_sw128(sa + A_BYTES);
-        const uint64_t bh = make_desc_sw128(sa + 2 * A_BYTES), bl = make_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+        const uint64_t ah = make_desc_mn(sa), al = make_desc_mn(sa + A_BYTES);
+        const uint64_t bh = make_desc_mn(sa + 2 * A_BYTES), bl = make_desc_mn(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
         for (int k = 0; k < WG_PIX / 8; ++k) {
-          const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+          const uint64_t koff = (uint64_t)((k * 8 * 128) >> 4);     // 8 pixel rows of 128 bytes
           const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
           if (p.nsplit == 3) {
             umma_tf32(tmem_base, al + koff, bh + koff, idesc, acc);
@@ -756,8 +777,9 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_c
                       const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                       const TcWgradParams p) {
   constexpr int AS = 3, BS = 2;
-  constexpr uint32_t A_BYTES = TC_BM * WG_PIX * 4;
-  constexpr uint32_t B_BYTES = BNW * WG_PIX * 4;
+  constexpr int NSB = (BNW + 31) / 32;
+  constexpr uint32_t A_BYTES = 4 * WG_SLAB;
+  constexpr uint32_t B_BYTES = NSB * WG_SLAB;
   constexpr uint32_t A_SLOT = 2 * A_BYTES, B_SLOT = 2 * B_BYTES;
   constexpr uint32_t ACC_STRIDE = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -794,54 +816,51 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_c
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      const int dh = p.dh[tap], brow = p.bvar[tap] * p.C + citile * BNW;
-      const int arow0 = p.aoff[tap] + copair * 2 * TC_BM;
+      const int gdn = p.gdn[tap], xdh = p.xdh[tap], xdw = p.xdw[tap], xdn = p.xdn[tap];
+      const int bslab = citile * NSB;
       for (int it = 0; it < nk; ++it) {
         const int ch = ch_beg + it;
         const int wc = ch % p.wchunks;
         const int t2 = ch / p.wchunks;
         const int hc = t2 % p.hchunks;
         const int w0 = wc * p.cw, h = hc * p.chh, n = (t2 / p.hchunks) * p.cn;
-        const int bw = p.flatW ? w0 + dh * p.flatW : w0;
-        const int bh = p.flatW ? 0 : h + dh;
         mbar_wait(&emptyB[bs], bph ^ 1);
         uint8_t* sb = smem_b + (size_t)bs * B_SLOT;
         mbar_expect_tx(&fullB[bs], split3 ? B_SLOT : B_BYTES);
-        tma_load_4d(sb, &map_xh, &fullB[bs], bw, bh, n, brow);
-        if (split3) tma_load_4d(sb + B_BYTES, &map_xl, &fullB[bs], bw, bh, n, brow);
+        tma_load_5d(sb, &map_xh, &fullB[bs], 0, w0 + xdw, h + xdh, n + xdn, bslab);
+        if (split3) tma_load_5d(sb + B_BYTES, &map_xl, &fullB[bs], 0, w0 + xdw, h + xdh, n + xdn, bslab);
         if (++bs == BS) { bs = 0; bph ^= 1; }
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           mbar_wait(&emptyA[as], aph ^ 1);
           uint8_t* sa = smem_a + (size_t)as * A_SLOT;
           mbar_expect_tx(&fullA[as], split3 ? A_SLOT : A_BYTES);
-          // rows past this copy's Kp rows would read the next copy: clamp by pointing fully out of range
-          const int arow = (copair * 2 + hf) < p.cotiles ? arow0 + hf * TC_BM : 0x3fffffff;
-          tma_load_4d(sa, &map_gh, &fullA[as], w0, h, n, arow);
-          if (split3) tma_load_4d(sa + A_BYTES, &map_gl, &fullA[as], w0, h, n, arow);
+          const int aslab = (copair * 2 + hf) * 4;      // past the last slab: out of bounds, zero filled
+          tma_load_5d(sa, &map_gh, &fullA[as], 0, w0, h, n + gdn, aslab);
+          if (split3) tma_load_5d(sa + A_BYTES, &map_gl, &fullA[as], 0, w0, h, n + gdn, aslab);
           if (++as == AS) { as = 0; aph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TC_BM, BNW);
+      const uint32_t idesc = make_idesc_tf32_mn(TC_BM, BNW);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int it = 0; it < nk; ++it) {
         mbar_wait(&fullB[bs], bph);
         const uint32_t sb = smem_u32(smem_b + (size_t)bs * B_SLOT);
-        const uint64_t bh = make_desc_sw128(sb), bl = make_desc_sw128(sb + B_BYTES);
+        const uint64_t bh = make_desc_mn(sb), bl = make_desc_mn(sb + B_BYTES);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           mbar_wait(&fullA[as], aph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem_a + (size_t)as * A_SLOT);
-          const uint64_t ah = make_desc_sw128(sa), al = make_desc_sw128(sa + A_BYTES);
+          const uint64_t ah = make_desc_mn(sa), al = make_desc_mn(sa + A_BYTES);
           const uint32_t d = tmem_base + hf * ACC_STRIDE;
 #pragma unroll
           for (int k = 0; k < WG_PIX / 8; ++k) {
-            const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+            const uint64_t koff = (uint64_t)((k * 8 * 128) >> 4);
             const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
             if (split3) {
               umma_tf32(d, al + koff, bh + koff, idesc, acc);
@@ -892,7 +911,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_c
 template <int BNW>
 int launch_wgrad2(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
                   const TcWgradParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)3 * (2 * TC_BM * WG_PIX * 4) + (size_t)2 * (2 * BNW * WG_PIX * 4) + 1024;
+  constexpr size_t smem = (size_t)3 * (2 * 4 * WG_SLAB) + (size_t)2 * (2 * ((BNW + 31) / 32) * WG_SLAB) + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad2_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -906,7 +925,7 @@ int launch_wgrad2(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMa
 template <int BNW, int STAGES>
 int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
                  const TcWgradParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * WG_PIX * 4 + 2 * BNW * WG_PIX * 4) + 1024;
+  constexpr size_t smem = (size_t)STAGES * (2 * 4 * WG_SLAB + 2 * ((BNW + 31) / 32) * WG_SLAB) + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<BNW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1056,36 +1075,39 @@ OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH,
 
 
 // ------------------------------------------------------------------------------------------------
-// weight gradient:  dw[t][co][ci] (fp32, [ntaps][Kp][C], zero-filled here) = sum_pixels G * X(shifted by tap t)
-//   gh/gl : output gradient hi/lo, channel-planar copies [gvariants][Kp][N][OH][OWp]  (og_prep_split_planar)
-//   xh/xl : source activations hi/lo, channel-planar copies [xvariants][C][N][SH][SWp] (w-shifted and/or
-//           space-to-depth phase copies)
-//   entries: nentries quadruples (g copy, dh, x copy, output tap): dw[tap] += G_copy^T * X_copy shifted by dh rows
+// weight gradient:  dw[t][co][ci] (fp32, [ntaps][Kp][C], zero-filled here) = sum_pixels G^T * X(shifted by tap t)
+//   gh/gl : output gradient hi/lo, NHWC [GN][OH][OW][Kp]   (og_prep_split; GN = N, or 4N space-to-depth blocks)
+//   xh/xl : source activations hi/lo, NHWC [XN][SH][SW][C] (og_prep_split: plain, reflection-padded or
+//           space-to-depth); both need 512 readable bytes after the last element (partial last channel slab)
+//   entries: nentries quintuples (g image offset, dh, dw, x image offset, output tap):
+//           dw[tap] += sum_{n,h,w} G[n + gdn, h, w, :]^T  X[n + xdn, h + dh, w + dw, :]   (out of range = 0)
 // ------------------------------------------------------------------------------------------------
-OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int OH, int OW, int Kp, int gvariants,
-                              const float* xh, const float* xl, int SH, int SW, int C, int xvariants, float* dw,
+OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int GN, int OH, int OW, int Kp,
+                              const float* xh, const float* xl, int XN, int SH, int SW, int C, float* dw,
                               int ntaps_out, const int* entries_host, int nentries, int nsplit, cudaStream_t stream) {
   if (nentries < 1 || nentries > TC_MAX_TAPS || (nsplit != 1 && nsplit != 3)) return (int)cudaErrorInvalidValue;
   OG_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)ntaps_out * Kp * C, stream));
   if ((long long)N * OH * OW == 0) return 0;
-  const int OWp = (OW + 3) / 4 * 4, SWp = (SW + 3) / 4 * 4;
   TcWgradParams p;
   p.N = N; p.OH = OH; p.OW = OW;
-  // one stage = 32 consecutive pixels of a row (a TMA box row must be one full 128-byte swizzle line).  Maps
-  // narrower than 32 pixels are addressed with (h, w) flattened, which needs unpadded planar rows on both sides.
-  const bool flat = OW < WG_PIX;
-  if (flat && !(OW == SW && OH == SH && OW % 4 == 0 && (OH * OW) % WG_PIX == 0)) return (int)cudaErrorInvalidValue;
-  p.cw = WG_PIX; p.chh = 1; p.cn = 1;
-  p.flatW = flat ? OW : 0;
-  p.wchunks = flat ? (OH * OW) / WG_PIX : og_cdiv(OW, WG_PIX);
-  p.hchunks = flat ? 1 : OH;
-  p.total_chunks = p.wchunks * p.hchunks * N;
+  // one stage = 32 pixels: a cw x chh x cn patch of the gradient grid (w fastest)
+  int cw = 1;
+  while (cw * 2 <= WG_PIX && OW % (cw * 2) == 0) cw *= 2;
+  int chh = 1;
+  while (cw * chh * 2 <= WG_PIX && OH % (chh * 2) == 0) chh *= 2;
+  const int cn = WG_PIX / (cw * chh);
+  if (N % cn != 0) return (int)cudaErrorInvalidValue;
+  p.cw = cw; p.chh = chh; p.cn = cn;
+  p.wchunks = OW / cw;
+  p.hchunks = OH / chh;
+  p.total_chunks = p.wchunks * p.hchunks * (N / cn);
   p.Kp = Kp; p.C = C; p.nsplit = nsplit; p.dw = dw;
   for (int i = 0; i < nentries; ++i) {
-    p.aoff[i] = entries_host[4 * i] * Kp;
-    p.dh[i] = entries_host[4 * i + 1];
-    p.bvar[i] = entries_host[4 * i + 2];
-    p.out[i] = entries_host[4 * i + 3];
+    p.gdn[i] = entries_host[5 * i];
+    p.xdh[i] = entries_host[5 * i + 1];
+    p.xdw[i] = entries_host[5 * i + 2];
+    p.xdn[i] = entries_host[5 * i + 3];
+    p.out[i] = entries_host[5 * i + 4];
   }
   const int cotiles = og_cdiv(Kp, TC_BM);
   const int Cr = (C + 15) / 16 * 16;
@@ -1101,25 +1123,21 @@ OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int OH, i
   splits = og_cdiv(p.total_chunks, p.chunks_per_cta);
   dim3 grid(cotiles * citiles, nentries, splits);
   CUtensorMap mgh, mgl, mxh, mxl;
-  unsigned long long gd[4] = {(unsigned long long)OW, (unsigned long long)OH, (unsigned long long)N,
-                              (unsigned long long)Kp * gvariants};
-  unsigned long long gs[3] = {(unsigned long long)OWp, (unsigned long long)OH * OWp, (unsigned long long)N * OH * OWp};
-  unsigned gb[4] = {(unsigned)WG_PIX, 1u, 1u, (unsigned)TC_BM};
-  unsigned long long xd[4] = {(unsigned long long)SW, (unsigned long long)SH, (unsigned long long)N,
-                              (unsigned long long)C * xvariants};
-  unsigned long long xs[3] = {(unsigned long long)SWp, (unsigned long long)SH * SWp, (unsigned long long)N * SH * SWp};
-  unsigned xb[4] = {(unsigned)WG_PIX, 1u, 1u, (unsigned)BNsel};
-  if (flat) {   // dims (H*W, 1, N, rows)
-    gd[0] = xd[0] = (unsigned long long)OH * OW;
-    gd[1] = xd[1] = 1;
-    gs[0] = xs[0] = (unsigned long long)OH * OW;
-  }
+  // [slab][n][h][w][32 channels of the slab]: the slab dimension strides by 32 floats inside a pixel's channel vector
+  unsigned long long gd[5] = {32ull, (unsigned long long)OW, (unsigned long long)OH, (unsigned long long)GN,
+                              (unsigned long long)og_cdiv(Kp, 32)};
+  unsigned long long gs[4] = {(unsigned long long)Kp, (unsigned long long)OW * Kp, (unsigned long long)OH * OW * Kp, 32ull};
+  unsigned gb[5] = {32u, (unsigned)cw, (unsigned)chh, (unsigned)cn, 4u};
+  unsigned long long xd[5] = {32ull, (unsigned long long)SW, (unsigned long long)SH, (unsigned long long)XN,
+                              (unsigned long long)og_cdiv(C, 32)};
+  unsigned long long xs[4] = {(unsigned long long)C, (unsigned long long)SW * C, (unsigned long long)SH * SW * C, 32ull};
+  unsigned xb[5] = {32u, (unsigned)cw, (unsigned)chh, (unsigned)cn, (unsigned)((BNsel + 31) / 32)};
   int rc;
-  if ((rc = make_map(&mgh, gh, 4, gd, gs, gb))) return rc;
-  if ((rc = make_map(&mxh, xh, 4, xd, xs, xb))) return rc;
+  if ((rc = make_map(&mgh, gh, 5, gd, gs, gb, true))) return rc;
+  if ((rc = make_map(&mxh, xh, 5, xd, xs, xb, true))) return rc;
   if (nsplit == 3) {
-    if ((rc = make_map(&mgl, gl, 4, gd, gs, gb))) return rc;
-    if ((rc = make_map(&mxl, xl, 4, xd, xs, xb))) return rc;
+    if ((rc = make_map(&mgl, gl, 5, gd, gs, gb, true))) return rc;
+    if ((rc = make_map(&mxl, xl, 5, xd, xs, xb, true))) return rc;
   } else {
     mgl = mgh;
     mxl = mxh;
@@ -1145,87 +1163,6 @@ OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int OH, i
     default:  return launch_wgrad<256, 2>(mgh, mgl, mxh, mxl, p, grid, stream);
   }
 }
-
-// channel-planar tf32 hi/lo copies for the wgrad kernel: t[s][c][n][h'][w'] = Xpad[c][n][h'][w' + s - origin]
-// (zero outside), h' in [0, H+2*pad), row pitch Wp = (W + 2*pad) rounded up to 4 floats, s in [0, nshift).
-// pad = 1 materialises the nn.ReflectionPad2d(1) halo.  s2d = 1: four space-to-depth phase blocks
-// t[phase][s][c][n][h'][w'] with phase (a*2+b) = x[:, a::2, b::2] (stride-2 convs, 2x-upsample adjoints).  The shifted copies exist because TMA needs the innermost
-// box coordinate 16-byte aligned: a tap's w offset picks a copy instead of an unaligned box.
-constexpr int PL_TW = 128;   // pixels of one row handled by a block (long contiguous runs per channel plane)
-__global__ void __launch_bounds__(256) prep_split_planar_kernel(const float* __restrict__ x, int N, int H, int W, int C,
-                                                                int pad, int Wp, int nshift, int origin, int s2d,
-                                                                float* __restrict__ th, float* __restrict__ tl) {
-  __shared__ float tile[PL_TW + 4][33];            // columns w0-1 .. w0+PL_TW+2 of the (padded / phase) row, 32 channels
-  const int Hp = s2d ? H / 2 : H + 2 * pad, Wq = s2d ? W / 2 : W + 2 * pad;
-  int nh = blockIdx.z;                             // (phase *) n * Hp + h'
-  int phase = 0;
-  if (s2d) {
-    phase = nh / (N * Hp);
-    nh -= phase * N * Hp;
-  }
-  const int n = nh / Hp, hp = nh - n * Hp;
-  int sh;
-  if (s2d) {
-    sh = 2 * hp + (phase >> 1);
-  } else {
-    sh = hp - pad;
-    if (sh < 0) sh = -sh;
-    if (sh >= H) sh = 2 * H - 2 - sh;
-  }
-  const int w0 = blockIdx.x * PL_TW, c0 = blockIdx.y * 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = warp; j < PL_TW + 4; j += 8) {      // rows = column index, lanes = c (coalesced along c)
-    int wq = w0 - 1 + j, c = c0 + lane;
-    float v = 0.f;
-    if (wq >= 0 && wq < Wq && c < C) {
-      int sw;
-      if (s2d) {
-        sw = 2 * wq + (phase & 1);
-      } else {
-        sw = wq - pad;
-        if (sw < 0) sw = -sw;
-        if (sw >= W) sw = 2 * W - 2 - sw;
-      }
-      v = x[(((long long)n * H + sh) * W + sw) * C + c];
-    }
-    tile[j][lane] = v;
-  }
-  __syncthreads();
-  const long long plane = (long long)N * Hp * Wp;
-  for (int j = warp; j < 32; j += 8) {             // one channel plane per warp: lanes run along w' (128 B per store)
-    const int c = c0 + j;
-    if (c >= C) continue;
-    for (int s = 0; s < nshift; ++s) {
-      const long long o = (((long long)phase * nshift + s) * C + c) * plane + ((long long)n * Hp + hp) * Wp;
-#pragma unroll
-      for (int k = 0; k < PL_TW / 32; ++k) {
-        const int wl = k * 32 + lane, wq = w0 + wl;
-        if (wq < Wp) {
-          const float v = tile[wl + 1 + s - origin][j];
-          const float hi = tf32_rn(v);
-          th[o + wq] = hi;
-          if (tl) tl[o + wq] = tf32_rn(v - hi);
-        }
-      }
-    }
-  }
-}
-
-OG_API int og_prep_split_planar(const float* x, int N, int H, int W, int C, int pad, int nshift, int origin, int s2d,
-                                float* th, float* tl, cudaStream_t stream) {
-  if (pad < 0 || pad > 1 || nshift < 1 || nshift > 3 || origin < 0 || origin > 1) return (int)cudaErrorInvalidValue;
-  if (s2d && (pad || (H & 1) || (W & 1))) return (int)cudaErrorInvalidValue;
-  if ((long long)N * H * W * C == 0) return 0;
-  const int Wq = s2d ? W / 2 : W + 2 * pad, Wp = (Wq + 3) / 4 * 4, Hp = s2d ? H / 2 : H + 2 * pad;
-  dim3 grid(og_cdiv(Wp, PL_TW), og_cdiv(C, 32), N * Hp * (s2d ? 4 : 1));
-  prep_split_planar_kernel<<<grid, 256, 0, stream>>>(x, N, H, W, C, pad, Wp, nshift, origin, s2d, th, tl);
-  OG_RETURN_LAST_ERROR();
-}
-
-// ------------------------------------------------------------------------------------------------
-// operand preparation: tf32 hi/lo split (+ optional reflection halo of 1 pixel)
-//   hi = rn_tf32(x), lo = rn_tf32(x - hi)
-// ------------------------------------------------------------------------------------------------
 
 __global__ void prep_split_kernel(const float* __restrict__ x, int N, int H, int W, int C4, int pad, int s2d,
                                   long long total, float* __restrict__ xh, float* __restrict__ xl) {

@@ -109,6 +109,7 @@ class PackedWeights:
 import os as _os
 CONV_ENGINE = _os.environ.get("OBJGAN_CONV", "tf32x3")
 TC_WGRAD = _os.environ.get("OBJGAN_TC_WGRAD", "1") == "1"
+KEEP_SPLIT = _os.environ.get("OBJGAN_KEEP_SPLIT", "1") == "1"   # keep x's hi/lo copies from forward for the wgrad
 TC_MIN_PIXELS = 256        # smaller problems go to the exact-fp32 SIMT kernels (the tc kernel splits K on small maps)
 
 
@@ -139,19 +140,6 @@ def _split(x, pad=0, s2d=False):
     xl = _empty_slack(shape, x.device) if CONV_ENGINE == "tf32x3" else None
     _call("og_prep_split", _p(x), n, h, w, c, pad, 1 if s2d else 0, _p(xh), _p(xl))
     return xh, xl
-
-
-def _split_planar(x, pad=0, nshift=1, origin=0, s2d=False):
-    """Channel-planar tf32 hi/lo copies [copies][C][N][H'][Wp] (row pitch rounded up to 4) for the wgrad kernel;
-    copy s holds the rows shifted by (s - origin) pixels along w (zero filled); s2d adds the 4 phase blocks."""
-    n, h, w, c = x.shape
-    hh, ww = (h // 2, w // 2) if s2d else (h + 2 * pad, w + 2 * pad)
-    wp = (ww + 3) // 4 * 4
-    shape = ((4 if s2d else 1) * nshift, c, n, hh, wp)
-    th = torch.empty(shape, device=x.device, dtype=torch.float32)
-    tl = torch.empty(shape, device=x.device, dtype=torch.float32) if CONV_ENGINE == "tf32x3" else None
-    _call("og_prep_split_planar", _p(x), n, h, w, c, pad, nshift, origin, 1 if s2d else 0, _p(th), _p(tl))
-    return th, tl
 
 
 def _tc_launch(xh, xl, n, wh, wl, ntaps_w, kw_rows, y, oh, ow, k, osy, op, taps, bias=None, act=ACT_NONE, layout=0):
@@ -197,6 +185,7 @@ _UP_OFF = ((-1, 0), (0, 1))   # low-res row/col offsets read by output phase 0 /
 
 
 def _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act):
+    """Returns (y, (xh, xl)): the output and the tf32 hi/lo operand copies of x (reused by the weight gradient)."""
     n, h, w, c = x.shape
     dev = x.device
     if mode != UPSAMPLE2X:
@@ -211,7 +200,7 @@ def _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act):
                 dw, b = divmod(kw - 1, 2)
                 taps.append((dh, dw, (a * 2 + b) * n, kh * 4 + kw))
         _tc_launch(xh, xl, n, wh, wl, 16, kp, y, h // 2, w // 2, kp, 1, (0, 0), taps, bias_p, act)
-        return y
+        return y, (xh, xl)
     if mode == PAD_REFLECT:
         xh, xl = _split(x, 1)
         y = torch.empty((n, h, w, kp), device=dev, dtype=torch.float32)
@@ -231,18 +220,28 @@ def _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act):
                 taps = [(_UP_OFF[py][a], _UP_OFF[px][b], 0, ((py * 2 + px) * 2 + a) * 2 + b)
                         for a in range(2) for b in range(2)]
                 _tc_launch(xh, xl, n, wh, wl, 16, kp, y, h, w, kp, 2, (py, px), taps, bias_p, act)
-    return y
+    return y, (xh, xl)
 
 
-def _tc_dgrad(kind, g, cache, weight, c, kp, split, splitp, mode, h, w):
-    """Input gradient on the tensor cores.  g: (N, OH, OW, kp); returns (N, h, w, c)."""
-    n = g.shape[0]
-    dev = g.device
+def _split_x(kind, x, mode):
+    """The operand copies _tc_fprop makes of x."""
+    if kind == "s2":
+        return _split(x, s2d=True)
+    return _split(x, 1 if mode == PAD_REFLECT else 0)
+
+
+def _split_g(kind, g, mode):
+    """Hi/lo copies of the output gradient shared by the input- and weight-gradient kernels."""
+    return _split(g, s2d=(kind == "s1" and mode == UPSAMPLE2X))
+
+
+def _tc_dgrad(kind, gs, n, cache, weight, c, kp, split, splitp, mode, h, w, oh, ow):
+    """Input gradient on the tensor cores.  gs: hi/lo of g (N, oh, ow, kp) from _split_g; returns (N, h, w, c)."""
+    gh, gl = gs
+    dev = gh.device
     if mode != UPSAMPLE2X:
         wh, wl = cache.get_hilo(weight, c, kp, split, splitp, 0)      # [tap][ci][co]
     if kind == "s2":
-        gh, gl = _split(g, 0)
-        oh, ow = g.shape[1], g.shape[2]
         gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
         for a in range(2):
             for b in range(2):
@@ -251,7 +250,6 @@ def _tc_dgrad(kind, g, cache, weight, c, kp, split, splitp, mode, h, w):
                 _tc_launch(gh, gl, n, wh, wl, 16, c, gx, oh, ow, c, 2, (a, b), taps)
         return gx
     if mode == PAD_REFLECT:
-        gh, gl = _split(g, 0)
         gpad = torch.empty((n, h + 2, w + 2, c), device=dev, dtype=torch.float32)
         taps = [(-kh, -kw, 0, kh * 3 + kw) for kw in range(3) for kh in (2, 1, 0)]   # rows ascending: -2, -1, 0
         _tc_launch(gh, gl, n, wh, wl, 9, c, gpad, h + 2, w + 2, c, 1, (0, 0), taps, layout=1)
@@ -259,14 +257,12 @@ def _tc_dgrad(kind, g, cache, weight, c, kp, split, splitp, mode, h, w):
         _call("og_reflect_pad_bwd", _p(gpad), n, h, w, c, _p(gx))
         return gx
     if mode == PAD_ZERO:
-        gh, gl = _split(g, 0)
         gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
         taps = [(1 - kh, 1 - kw, 0, kh * 3 + kw) for kw in range(3) for kh in (2, 1, 0)]
         _tc_launch(gh, gl, n, wh, wl, 9, c, gx, h, w, c, 1, (0, 0), taps, layout=1)
         return gx
     # UPSAMPLE2X: adjoint of the four phase convolutions: gx[i,j] = sum_{p,q,a,b} G_pq[i - off(p,a), j - off(q,b)] Wp^T
     wh, wl = cache.get_up_hilo(weight, c, kp, split, splitp, 0)
-    gh, gl = _split(g, s2d=True)
     gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
     taps = [(-_UP_OFF[p_][a], -_UP_OFF[q_][b], (p_ * 2 + q_) * n, ((p_ * 2 + q_) * 2 + a) * 2 + b)
             for p_ in range(2) for q_ in range(2) for a in range(2) for b in range(2)]
@@ -274,49 +270,46 @@ def _tc_dgrad(kind, g, cache, weight, c, kp, split, splitp, mode, h, w):
     return gx
 
 
-def _tc_wgrad_ok(kind, mode, oh, ow):
-    """The wgrad kernel streams 32 consecutive pixels per stage: rows of >= 32 pixels, or (for sources with the same
-    unpadded extent as the gradient grid) narrower maps addressed with (h, w) flattened."""
-    if mode == UPSAMPLE2X:
+def _tc_wgrad_ok(kind, mode, n, oh, ow):
+    """The wgrad kernel streams 32-pixel patches (cw x chh x cn, powers of two) of the gradient grid."""
+    if kind == "s1" and mode == UPSAMPLE2X:
         oh, ow = oh // 2, ow // 2
-    if ow >= 32:
-        return True
-    return mode != PAD_REFLECT and ow % 4 == 0 and (oh * ow) % 32 == 0
+    cw = 1
+    while cw * 2 <= 32 and ow % (cw * 2) == 0:
+        cw *= 2
+    chh = 1
+    while cw * chh * 2 <= 32 and oh % (chh * 2) == 0:
+        chh *= 2
+    return n % (32 // (cw * chh)) == 0
 
 
-def _tc_wgrad(kind, x, g, weight, c, kp, split, splitp, mode):
-    """Weight gradient on the tensor cores; returns the OIHW gradient."""
+def _tc_wgrad(kind, xs, gs, n, h, w, oh, ow, weight, c, kp, split, splitp, mode):
+    """Weight gradient on the tensor cores from the hi/lo copies of x (_split_x) and g (_split_g), both NHWC;
+    (h, w) is the extent of x, (oh, ow) of g.  Returns the OIHW gradient."""
     import ctypes
-    n, h, w, _ = x.shape
+    xh, xl = xs
+    gh, gl = gs
     co, ci, kh_, kw_ = weight.shape
     if kind == "s2":
-        xh, xl = _split_planar(x, 0, 3, 1, s2d=True)                  # 12 copies: phase * 3 + shift
-        gh, gl = _split_planar(g)
         ent = []
         for kh in range(4):
             dh, a = divmod(kh - 1, 2)
             for kw in range(4):
                 dw, b = divmod(kw - 1, 2)
-                ent.append((0, dh, (a * 2 + b) * 3 + dw + 1, kh * 4 + kw))
-        gv, xv, sh, sw, oh, ow, nt = 1, 12, h // 2, w // 2, g.shape[1], g.shape[2], 16
+                ent.append((0, dh, dw, (a * 2 + b) * n, kh * 4 + kw))
+        nt = 16
     elif mode == UPSAMPLE2X:
-        xh, xl = _split_planar(x, 0, 3, 1)                            # low-res source, shifts -1, 0, +1
-        gh, gl = _split_planar(g, s2d=True)                           # 4 phase blocks of the full-res gradient
-        ent = [(p_ * 2 + q_, _UP_OFF[p_][a], _UP_OFF[q_][b] + 1, ((p_ * 2 + q_) * 2 + a) * 2 + b)
+        ent = [((p_ * 2 + q_) * n, _UP_OFF[p_][a], _UP_OFF[q_][b], 0, ((p_ * 2 + q_) * 2 + a) * 2 + b)
                for p_ in range(2) for q_ in range(2) for a in range(2) for b in range(2)]
-        gv, xv, sh, sw, oh, ow, nt = 4, 3, h, w, h, w, 16
+        oh, ow, nt = h, w, 16
     else:
-        pad = 1 if mode == PAD_REFLECT else 0
-        origin = 0 if mode == PAD_REFLECT else 1   # zero-pad conv: taps at w-1, w, w+1 of the unpadded source
-        off = 0 if mode == PAD_REFLECT else -1
-        xh, xl = _split_planar(x, pad, 3, origin)
-        gh, gl = _split_planar(g)
-        ent = [(0, kh + off, kw, kh * 3 + kw) for kh in range(3) for kw in range(3)]
-        gv, xv, sh, sw, oh, ow, nt = 1, 3, h + 2 * pad, w + 2 * pad, g.shape[1], g.shape[2], 9
+        off = 0 if mode == PAD_REFLECT else -1     # reflect: x copy carries the halo; zero pad: TMA fills
+        ent = [(0, kh + off, kw + off, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
+        nt = 9
     arr = _int_array(ent)
-    dwp = torch.empty(nt * kp * c, device=x.device, dtype=torch.float32)
-    _call("og_conv2d_wgrad_tc", _p(gh), _p(gl), n, oh, ow, kp, gv, _p(xh), _p(xl), sh, sw, c, xv, _p(dwp), nt,
-          ctypes.addressof(arr), len(ent), _nsplit())
+    dwp = torch.empty(nt * kp * c, device=xh.device, dtype=torch.float32)
+    _call("og_conv2d_wgrad_tc", _p(gh), _p(gl), n, gh.shape[0], oh, ow, kp, _p(xh), _p(xl), xh.shape[0], xh.shape[1],
+          xh.shape[2], c, _p(dwp), nt, ctypes.addressof(arr), len(ent), _nsplit())
     gw = torch.empty_like(weight)
     if mode == UPSAMPLE2X and kind == "s1":
         _call("og_unpack_upsample_wgrad", _p(dwp), co, ci, c, kp, split, splitp, _p(gw))
@@ -368,8 +361,11 @@ class _Conv2d(torch.autograd.Function):
                 bias_p = torch.zeros(kp, device=x.device, dtype=torch.float32)
                 bias_p[:co] = bias.detach()
         narrow = kind is None and kp == 8 and mode == PAD_ZERO and n * oh * ow <= 65536
+        xs = None
         if kind:
-            y = _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act)
+            y, xs = _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act)
+            if not (KEEP_SPLIT and ctx.needs_input_grad[1] and TC_WGRAD and _tc_wgrad_ok(kind, mode, n, oh, ow)):
+                xs = None
         elif narrow:
             wf, _ = cache.get(weight, c, kp, split, splitp, False)
             y = torch.empty((n, oh, ow, 8), device=x.device, dtype=torch.float32)
@@ -380,6 +376,7 @@ class _Conv2d(torch.autograd.Function):
             y = _conv_raw(x, wf, n, h, w, c, oh, ow, kp, kh, kw, stride, pad, mode, bias_p, act,
                           splitk=(bias is None and act == ACT_NONE))
         ctx.kind = kind
+        ctx.xs = xs                      # hi/lo operand copies of x, reused by the weight gradient
         ctx.narrow = narrow
         ctx.cfg = (stride, pad, mode, act, split, splitp, kp, need_t)
         ctx.cache = cache
@@ -416,8 +413,10 @@ class _Conv2d(torch.autograd.Function):
                 gw = torch.empty_like(weight)
                 _call("og_unpack_wgrad", _p(dwp), co, ci, kh, kw, c, kp, split, splitp, _p(gw), 0, 0)
             return gx, gw, gb, None, None, None, None, None, None
+        tc_w = bool(ctx.needs_input_grad[1] and kind and TC_WGRAD and _tc_wgrad_ok(kind, mode, n, oh, ow))
+        gs = _split_g(kind, g, mode) if kind and (ctx.needs_input_grad[0] or tc_w) else None
         if ctx.needs_input_grad[0] and kind:
-            gx = _tc_dgrad(kind, g, ctx.cache, weight, c, kp, split, splitp, mode, h, w)
+            gx = _tc_dgrad(kind, gs, n, ctx.cache, weight, c, kp, split, splitp, mode, h, w, oh, ow)
         elif ctx.needs_input_grad[0]:
             _, wt = ctx.cache.get(weight, c, kp, split, splitp, True)
             if mode == PAD_ZERO:
@@ -431,8 +430,10 @@ class _Conv2d(torch.autograd.Function):
                 gu = _conv_raw(g, wt, n, oh, ow, kp, 2 * h, 2 * w, c, kh, kw, 1, pad, TRANSPOSED, None, ACT_NONE)
                 gx = torch.empty_like(x)
                 _call("og_upsample2x_bwd", _p(gu), n, h, w, c, _p(gx))
-        if ctx.needs_input_grad[1] and kind and TC_WGRAD and _tc_wgrad_ok(kind, mode, oh, ow):
-            gw = _tc_wgrad(kind, x, g, weight, c, kp, split, splitp, mode)
+        if tc_w:
+            xs = ctx.xs if ctx.xs is not None else _split_x(kind, x, mode)
+            ctx.xs = None
+            gw = _tc_wgrad(kind, xs, gs, n, h, w, oh, ow, weight, c, kp, split, splitp, mode)
         elif ctx.needs_input_grad[1]:
             dwp = torch.empty(kh * kw * c * kp, device=g.device, dtype=torch.float32)
             _call("og_conv2d_wgrad_simt", _p(x), n, h, w, c, h * w * c, w * c, c, _p(g), oh, ow, kp, oh * ow * kp,

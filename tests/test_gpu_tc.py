@@ -28,6 +28,8 @@ CASES = [
     (48, 3, PAD_ZERO, 0, 2, 64, 64),             # GET_IMAGE_G: 3 output channels (dgrad reads an 8-channel source)
     (3, 96, "s2", 0, 4, 64, 64),                 # discriminator first layer: 3 (->8) input channels
     (80, 24, PAD_REFLECT, 0, 2, 64, 64),         # G_HMAP conv3x3
+    (768, 1536, "s2", 0, 32, 8, 8),              # 4x4 outputs: wgrad pixel patch spans 2 images
+    (40, 24, PAD_REFLECT, 0, 4, 16, 16),         # reflection halo on a 16-wide map (wgrad patch = 16 x 2)
 ]
 
 
