@@ -140,21 +140,20 @@ def conv_roofline(hbm, bf16_tf, src):
     ms = e0.elapsed_time(e1) / n
     flops = 2.0 * B * H * H * (9 * C) * (2 * C)          # algorithmic, unpadded
     achieved = flops / (ms * 1e-3) / 1e12
-    peak = bf16_tf / 2.0                                   # tf32 dense = half the bf16 rate (nominal 1.1 vs 2.25 PF)
+    peak = bf16_tf                                         # kind::f16 runs at the bf16 rate
     from objgan_b200 import ops as _ops
     eng = _ops.CONV_ENGINE
-    kname = {"simt": "conv_gemm_kernel<8> (fp32 FMA)", "tf32": "conv_tc2_kernel<208> (tcgen05 kind::tf32, 1 product)",
-             "tf32x3": "conv_tc2_kernel<208> (tcgen05 kind::tf32, 3xTF32 error-compensated)"}[eng]
-    note = {"simt": "CUDA-core fp32 path", "tf32": "single TF32 product (not the parity mode)",
-            "tf32x3": "3 MMAs per algorithmic product, so frac <= 1/3 by construction; prep_split pass included"}[eng]
+    kname = {"simt": "conv_gemm_kernel<8> (fp32 FMA)", "f16": "conv_tc2_kernel<208> (tcgen05 kind::f16, 1 product)",
+             "f16x3": "conv_tc2_kernel<208> (tcgen05 kind::f16, 3xFP16 error-compensated hi/lo operands)"}[eng]
+    note = {"simt": "CUDA-core fp32 path", "f16": "single fp16 product (not the parity mode)",
+            "f16x3": "3 MMAs per algorithmic product, so frac <= 1/3 by construction; amax + prep_split passes included"}[eng]
     return {"bound": "tensor", "kernel": kname + " + prep_split: res-block conv1 194->388 3x3 @128x128, B=16",
             "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-            "traffic": 1.267e9 if eng != "simt" else None, "ms_per_launch": round(ms, 3),
+            "traffic": None, "ms_per_launch": round(ms, 3),
             "algorithmic_flops_per_launch": flops,
-            "tf32_mma_tflops": round(achieved * (3 if eng == "tf32x3" else 1), 1) if eng != "simt" else None,
-            "frac_of_peak_counting_issued_mmas": round(achieved * (3 if eng == "tf32x3" else 1) / peak, 4) if eng != "simt" else None,
-            "peak_source": f"{src} bf16 cuBLAS burst / 2 (tf32:bf16 nominal ratio); {note}; traffic = dram read+write of the "
-                           "conv kernel from profiles/r01_ncu_conv_tc_summary.md (single-tile variant)"}
+            "issued_mma_tflops": round(achieved * (3 if eng == "f16x3" else 1), 1) if eng != "simt" else None,
+            "frac_of_peak_counting_issued_mmas": round(achieved * (3 if eng == "f16x3" else 1) / peak, 4) if eng != "simt" else None,
+            "peak_source": f"{src} bf16 cuBLAS burst (kind::f16 = bf16 rate); {note}; traffic: see profiles/"}
 
 
 def attn_roofline(hbm, src):

@@ -70,42 +70,51 @@ int og_conv2d_narrow_dgrad(const float* g, int N, int H, int W, int C, const flo
 int og_conv2d_narrow_wgrad(const float* x, int N, int H, int W, int C, const float* g, float* dw_packed, int OH, int OW,
                            int KH, int KW, int stride, int pad, cudaStream_t stream);
 /* OIHW parameter (state_dict layout) <-> kernel-native matrices.  split/splitp: GLU halves of the
- * output channels are each padded to splitp.  transposed=1 gives the dgrad operand.  out_lo != NULL also writes
- * the tf32 hi/lo split used by the tensor-core path. */
+ * output channels are each padded to splitp.  transposed=1 gives the dgrad operand ([tap][co][ci] instead of
+ * [tap][ci][co]).  og_pack_weights_f16 writes the same matrices as the fp16 hi/lo operand pair of the tensor-core
+ * path, scaled by the power of two derived from *amax (og_amax over the parameter; see og_prep_split). */
 int og_pack_weights(const float* w_oihw, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split, int splitp,
-                    int transposed, float* out, float* out_lo, cudaStream_t stream);
+                    int transposed, float* out, cudaStream_t stream);
+int og_pack_weights_f16(const float* w_oihw, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split, int splitp,
+                        int transposed, const unsigned* amax, void* hi, void* lo, cudaStream_t stream);
 int og_unpack_wgrad(const float* dw_packed, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split, int splitp,
                     float* grad_oihw, int accumulate, int transposed, cudaStream_t stream);
 
 /* upBlock (nearest 2x upsample + conv3x3, ref: model.py:43-49) as four 2x2 phase convolutions with pre-summed
- * weights: Wp[16][..] (tap t = ((p*2+q)*2+a)*2+b) from the OIHW parameter, and the adjoint map for the gradient. */
+ * weights: Wp[16][..] (tap t = ((p*2+q)*2+a)*2+b) from the OIHW parameter as fp16 hi/lo operands (scale word
+ * *amax_up = 4 * *amax, the bound of the pre-sums), and the adjoint map for the gradient. */
 int og_pack_upsample_weights(const float* w_oihw, int Co, int Ci, int Cip, int Kp, int split, int splitp,
-                             int transposed, float* out, float* out_lo, cudaStream_t stream);
+                             int transposed, const unsigned* amax, unsigned* amax_up, void* hi, void* lo,
+                             cudaStream_t stream);
 int og_unpack_upsample_wgrad(const float* dwp, int Co, int Ci, int Cip, int Kp, int split, int splitp,
                              float* grad_oihw, cudaStream_t stream);
 
-/* Tensor-core path (tcgen05.mma kind::tf32, TMEM accumulators, TMA operand staging) for the stride-1
- * contractions that dominate the step (HmapResBlock / upBlock / jointConv forward and input gradients).
- * og_prep_split writes the tf32 hi/lo parts of an activation tensor (pad=1 also materialises the
- * nn.ReflectionPad2d(1) halo, ref: model.py:67; s2d=1 writes the four space-to-depth phase blocks used by the
- * stride-2 convs of the discriminators and by the adjoint of the 2x upsampling); og_conv2d_tc computes
+/* Tensor-core path (tcgen05.mma kind::f16 with fp32 accumulation in TMEM, TMA operand staging) for the
+ * contractions that dominate the step (HmapResBlock / upBlock / jointConv / discriminator convs: forward, input
+ * and weight gradients).  Operands are fp16 hi/lo pairs (22 mantissa bits; "3xFP16": a*b ~ ah*bh + al*bh + ah*bl)
+ * of x * 2^k, k = og_scale_exp(max|x|) per tensor; the word *amax holds max|x| as float bits and travels with the
+ * operand.  og_prep_split computes *amax and writes the pair for an activation tensor (pad=1 also materialises
+ * the nn.ReflectionPad2d(1) halo, ref: model.py:67; s2d=1 writes the four space-to-depth phase blocks used by
+ * the stride-2 convs of the discriminators and by the adjoint of the 2x upsampling); og_conv2d_tc computes
  *     y[n, osy*h+opy, osx*w+opx, :] = act(bias + sum_t x[n+dn_t, h+dh_t, w+dw_t, :] * W[widx_t])   (x OOB = 0)
- * with taps = ntaps host quadruples (dh, dw, dn, widx); nsplit = 3 is the error-compensated 3xTF32 product
- * (fp32-level accuracy), nsplit = 1 a single TF32 product. */
-int og_prep_split(const float* x, int N, int H, int W, int C, int pad, int s2d, float* xh, float* xl,
+ * with taps = ntaps host quadruples (dh, dw, dn, widx); nsplit = 3 is the error-compensated product (fp32-level
+ * accuracy), nsplit = 1 a single fp16 product (xl / wl unused). */
+int og_amax(const float* x, long long n, unsigned* amax, cudaStream_t stream);
+int og_prep_split(const float* x, int N, int H, int W, int C, int pad, int s2d, unsigned* amax, void* xh, void* xl,
                   cudaStream_t stream);
-int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH, int SW, int C, const float* wh,
-                 const float* wl, int ntaps_w, int Kw, float* y, int OH, int OW, int K, long long ysn, long long ysh,
-                 long long ysw, int OHf, int OWf, int osy, int osx, int opy, int opx, const int* taps_host, int ntaps,
-                 int tap_layout, int nsplit, const float* bias, int act, float slope, cudaStream_t stream);
+int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, int N, int SN, int SH, int SW, int C,
+                 const void* wh, const void* wl, const unsigned* amax_w, int ntaps_w, int Kw, float* y, int OH, int OW,
+                 int K, long long ysn, long long ysh, long long ysw, int OHf, int OWf, int osy, int osx, int opy,
+                 int opx, const int* taps_host, int ntaps, int tap_layout, int nsplit, const float* bias, int act,
+                 float slope, cudaStream_t stream);
 /* Weight gradient: dw[tap][co][ci] = sum_{n,h,w} G[n+gdn, h, w, co] * X[n+xdn, h+dh, w+dw, ci]  (X out of range = 0).
- * Both operands are the same NHWC hi/lo tensors og_prep_split writes for the forward / input-gradient kernels
+ * Both operands are the same NHWC fp16 hi/lo tensors og_prep_split writes for the forward / input-gradient kernels
  * (G: [GN][OH][OW][Kp], X: [XN][SH][SW][C]; GN / XN = N or 4N space-to-depth blocks), consumed MN-major by
- * tcgen05.mma (128B swizzle with 32-byte atoms); each needs 512 readable bytes after its last element.
+ * tcgen05.mma; each needs 512 readable bytes after its last element.
  * entries_host: nentries quintuples (gdn, dh, dw, xdn, output tap); dw is [ntaps_out][Kp][C], zero-filled here. */
-int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int GN, int OH, int OW, int Kp, const float* xh,
-                       const float* xl, int XN, int SH, int SW, int C, float* dw, int ntaps_out,
-                       const int* entries_host, int nentries, int nsplit, cudaStream_t stream);
+int og_conv2d_wgrad_tc(const void* gh, const void* gl, const unsigned* amax_g, int N, int GN, int OH, int OW, int Kp,
+                       const void* xh, const void* xl, const unsigned* amax_x, int XN, int SH, int SW, int C, float* dw,
+                       int ntaps_out, const int* entries_host, int nentries, int nsplit, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * InstanceNorm2d / BatchNorm (train mode) + fused GLU / LeakyReLU / residual

@@ -43,6 +43,16 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Per-tensor power-of-two scaling of the fp16 tensor-core operands: amax_bits = float bits of max|x| over the tensor;
+// the operand stores x * 2^k with k chosen so that max|x| * 2^k lies in [2^13, 2^14) (fp16 overflows at 65504).
+__host__ __device__ __forceinline__ int og_scale_exp(unsigned amax_bits) {
+  amax_bits &= 0x7fffffffu;
+  if (amax_bits == 0) return 0;
+  int k = 13 - ((int)(amax_bits >> 23) - 127);
+  return k < -110 ? -110 : (k > 110 ? 110 : k);
+}
+__device__ __forceinline__ float og_exp2i(int k) { return __int_as_float((k + 127) << 23); }   // |k| <= 126
+
 // activation codes shared by conv epilogues and the act-backward kernel
 enum { OG_ACT_NONE = 0, OG_ACT_LRELU = 1, OG_ACT_TANH = 2, OG_ACT_SIGMOID = 3 };
 // normalisation-apply fusions

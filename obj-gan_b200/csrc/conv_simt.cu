@@ -12,6 +12,7 @@
 // with the addressing mode (zero pad / reflection pad / nearest-2x-upsample-then-zero-pad /
 // transposed); B is a pre-packed [(kh,kw,ci)][co] matrix (og_pack_weights).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 struct ConvArgs {
   const float* x;  // source NHWC
@@ -322,9 +323,21 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
 // ---------------------------------------------------------------------------------------------
 // output-major: one thread per element of the packed matrix (coalesced writes, zero padding written in place; the
 // strided OIHW reads hit the same 32-byte sectors for neighbouring taps and stay in L1/L2)
+// F16 = true: fp16 hi/lo operands of the tensor-core path, scaled by the power of two derived from *amax
+__device__ __forceinline__ void store_hilo_f16(float v, float scale, __half* hi, __half* lo, long long o) {
+  v *= scale;
+  const __half h = __float2half_rn(v);
+  hi[o] = h;
+  if (lo) lo[o] = __float2half_rn(v - __half2float(h));
+}
+
+template <bool F16>
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Co, int Ci, int KH, int KW, int Cip, int Kp,
-                                    int split, int splitp, int transposed, float* __restrict__ out,
-                                    float* __restrict__ out_lo) {
+                                    int split, int splitp, int transposed, void* __restrict__ out_v,
+                                    void* __restrict__ out_lo_v, const unsigned* __restrict__ amax) {
+  float* out = (float*)out_v;
+  float scale = 1.f;
+  if (F16) scale = og_exp2i(og_scale_exp(__ldg(amax)));
   const long long total = (long long)KH * KW * Cip * Kp;
   const int taps = KH * KW;
   for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total;
@@ -352,16 +365,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Co, int Ci,
     }
     float v = 0.f;
     if (co >= 0 && co < Co && ci < Ci) v = __ldg(w + ((long long)co * Ci + ci) * taps + tap);
-    if (out_lo) {  // tf32 hi/lo split for the 3xTF32 tensor-core path
-      uint32_t uh, ul;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(uh) : "f"(v));
-      float hi = __uint_as_float(uh);
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul) : "f"(v - hi));
-      out[o] = hi;
-      out_lo[o] = __uint_as_float(ul);
-    } else {
-      out[o] = v;
-    }
+    if (F16) store_hilo_f16(v, scale, (__half*)out_v, (__half*)out_lo_v, o);
+    else out[o] = v;
   }
 }
 
@@ -575,12 +580,23 @@ OG_API int og_conv2d_wgrad_simt(const float* x, int N, int H, int W, int C, long
 }
 
 OG_API int og_pack_weights(const float* w_oihw, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split,
-                           int splitp, int transposed, float* out, float* out_lo, cudaStream_t stream) {
+                           int splitp, int transposed, float* out, cudaStream_t stream) {
   long long total = (long long)KH * KW * Cip * Kp;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_weights_kernel<<<blocks, 256, 0, stream>>>(w_oihw, Co, Ci, KH, KW, Cip, Kp, split, splitp, transposed, out,
-                                                  out_lo);
+  pack_weights_kernel<false><<<blocks, 256, 0, stream>>>(w_oihw, Co, Ci, KH, KW, Cip, Kp, split, splitp, transposed,
+                                                         out, nullptr, nullptr);
+  OG_RETURN_LAST_ERROR();
+}
+// fp16 hi/lo operands for og_conv2d_tc: same matrices, scaled by 2^og_scale_exp(*amax) (amax from og_amax over w)
+OG_API int og_pack_weights_f16(const float* w_oihw, int Co, int Ci, int KH, int KW, int Cip, int Kp, int split,
+                               int splitp, int transposed, const unsigned* amax, void* hi, void* lo,
+                               cudaStream_t stream) {
+  long long total = (long long)KH * KW * Cip * Kp;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weights_kernel<true><<<blocks, 256, 0, stream>>>(w_oihw, Co, Ci, KH, KW, Cip, Kp, split, splitp, transposed,
+                                                        hi, lo, amax);
   OG_RETURN_LAST_ERROR();
 }
 
@@ -631,10 +647,16 @@ OG_API int og_conv2d_narrow_wgrad(const float* x, int N, int H, int W, int C, co
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int up_row(int p, int k) { return p == 0 ? (k >= 1) : (k >= 2); }
 
+// amax_up receives 4 * amax(w): the pre-sums of up to four taps are bounded by it, and it is the scale word the conv
+// kernel is given for this operand
 __global__ void pack_upsample_weights_kernel(const float* __restrict__ w, int Co, int Ci, int Cip, int Kp, int split,
-                                             int splitp, int transposed, float* __restrict__ out,
-                                             float* __restrict__ out_lo) {
+                                             int splitp, int transposed, const unsigned* __restrict__ amax,
+                                             unsigned* __restrict__ amax_up, __half* __restrict__ out,
+                                             __half* __restrict__ out_lo) {
   long long total = (long long)16 * Co * Ci;
+  const float bound = 4.f * __uint_as_float(__ldg(amax));
+  const float scale = og_exp2i(og_scale_exp(__float_as_uint(bound)));
+  if (blockIdx.x == 0 && threadIdx.x == 0) *amax_up = __float_as_uint(bound);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int ci = (int)(i % Ci);
@@ -650,16 +672,7 @@ __global__ void pack_upsample_weights_kernel(const float* __restrict__ w, int Co
     }
     int cm = (split > 0 && co >= split) ? co + (splitp - split) : co;
     long long o = transposed ? ((long long)t * Kp + cm) * Cip + ci : ((long long)t * Cip + ci) * Kp + cm;
-    if (out_lo) {
-      uint32_t uh, ul;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(uh) : "f"(v));
-      float hi = __uint_as_float(uh);
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul) : "f"(v - hi));
-      out[o] = hi;
-      out_lo[o] = __uint_as_float(ul);
-    } else {
-      out[o] = v;
-    }
+    store_hilo_f16(v, scale, out, out_lo, o);
   }
 }
 // dW[kh][kw] = sum_{p,q} dWp[p][q][up_row(p,kh)][up_row(q,kw)]   (dWp packed [16][Kp][Cip], i.e. "transposed" layout)
@@ -685,14 +698,16 @@ __global__ void unpack_upsample_wgrad_kernel(const float* __restrict__ dwp, int 
   }
 }
 OG_API int og_pack_upsample_weights(const float* w_oihw, int Co, int Ci, int Cip, int Kp, int split, int splitp,
-                                    int transposed, float* out, float* out_lo, cudaStream_t stream) {
+                                    int transposed, const unsigned* amax, unsigned* amax_up, void* hi, void* lo,
+                                    cudaStream_t stream) {
   long long n = (long long)16 * Cip * Kp;
-  OG_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * n, stream));
-  if (out_lo) OG_CHECK(cudaMemsetAsync(out_lo, 0, sizeof(float) * n, stream));
+  OG_CHECK(cudaMemsetAsync(hi, 0, sizeof(__half) * n, stream));
+  if (lo) OG_CHECK(cudaMemsetAsync(lo, 0, sizeof(__half) * n, stream));
   long long total = (long long)16 * Co * Ci;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_upsample_weights_kernel<<<blocks, 256, 0, stream>>>(w_oihw, Co, Ci, Cip, Kp, split, splitp, transposed, out, out_lo);
+  pack_upsample_weights_kernel<<<blocks, 256, 0, stream>>>(w_oihw, Co, Ci, Cip, Kp, split, splitp, transposed, amax,
+                                                           amax_up, (__half*)hi, (__half*)lo);
   OG_RETURN_LAST_ERROR();
 }
 OG_API int og_unpack_upsample_wgrad(const float* dwp, int Co, int Ci, int Cip, int Kp, int split, int splitp,

@@ -1,5 +1,5 @@
-// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (kind::tf32) with TMEM accumulators,
-// operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle), mbarrier producer/consumer pipeline.
+// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (kind::f16, fp32 accumulate) with TMEM
+// accumulators, operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle), mbarrier producer/consumer pipeline.
 //
 // Covers every stride-1 contraction of the hot path through a "tap list":
 //     out[pix, :] = sum_t  src[pix + (dh_t, dw_t), :] * W[widx_t]          (src out-of-bounds = 0 via TMA fill)
@@ -8,34 +8,28 @@
 // gradients (taps mirrored, operand re-packed) and the four phases of nearest-2x-upsample + conv3x3
 // (upBlock, model.py:43-49: tap offsets at low resolution, strided output pixels).
 //
-// Precision: fp32 parity (1e-3 end to end) is not reachable with one TF32 product (2^-11 operand rounding,
+// Precision: fp32 parity (1e-3 end to end) is not reachable with one 11-bit product (2^-11 operand rounding,
 // ~35 stacked convs), so by default each product is error-compensated:  a*b ~= ah*bh + al*bh + ah*bl  with
-// ah = a rounded down to tf32, al = a - ah (exact), three MMAs into the same fp32 TMEM accumulator ("3xTF32").
-// nsplit = 1 runs the plain single-TF32 product (reported separately, never the parity mode).
+// ah = fp16(a), al = fp16(a - ah): 22 mantissa bits per operand, three MMAs into the same fp32 TMEM accumulator
+// ("3xFP16").  fp16 has the mantissa of tf32 at twice the MMA rate and half the operand bytes; its narrow exponent
+// range is handled by scaling every operand tensor by a power of two taken from its max|x| (og_prep_split /
+// og_pack_weights_f16 write x * 2^k; the epilogue multiplies the accumulator by 2^-(ka+kb)): elements within
+// 2^-18 of the tensor maximum keep all 22 bits, smaller ones an absolute error <= 2^-39 of the maximum.
+// nsplit = 1 runs a single fp16 product (reported separately, never the parity mode).
 //
 // GEMM tiling: one CTA = 128 output pixels (a TN x TH x TW patch) x BN output channels (BN % 16 == 0,
-// <= 256); K loop over taps x 32-channel chunks; STAGES-deep smem ring of {A_hi, A_lo, B_hi, B_lo}.
+// <= 256); K loop over taps x 64-channel chunks; STAGES-deep smem ring of {A_hi, A_lo, B_hi, B_lo}.
 // Warp roles: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one lane),
 // warps 2..5 = epilogue (TMEM -> registers -> global, one TMEM lane quadrant each).
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace {
 
-// round-to-nearest tf32 (unbiased; truncation would bias every product the same way and the bias adds up
-// linearly over the reduction).  lo = v - hi is exact in fp32 and is itself rounded to tf32 so that the tensor
-// core's own operand truncation is a no-op: |v - hi - lo| <= 2^-22 |v|.
-__device__ __forceinline__ float tf32_rn(float v) {
-  unsigned u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
-}
-__device__ __forceinline__ float tf32_hi(float v) { return tf32_rn(v); }
-__device__ __forceinline__ float tf32_lo(float v, float hi) { return tf32_rn(v - hi); }
-
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;              // tf32 elements per k-chunk = one 128-byte swizzle row
+constexpr int TC_BK = 64;              // fp16 elements per k-chunk = one 128-byte swizzle row (4 MMA k-steps of 16)
 constexpr int TC_MAX_TAPS = 36;
 constexpr int TC_THREADS = 192;
 
@@ -48,7 +42,10 @@ struct TcParams {
   int N, OH, OW;          // GEMM-row pixel grid (before the output stride/phase mapping)
   int TN, TH, TW;         // tile patch: TN*TH*TW == 128
   int tiles_h, tiles_w;   // tiles per image along h / w
-  int cchunks;            // ceil(C / 32)
+  int cchunks;            // ceil(C / 64)
+  int klast;              // MMA k-steps (16 channels each) that the last chunk really needs: 1..4
+  const unsigned* amax_a; // float bits of max|x| of the two operand tensors (power-of-two operand scaling)
+  const unsigned* amax_b;
   int K;                  // output channels actually stored (<= gridDim.y * BN)
   int nsplit;             // 1 or 3
   float* y;
@@ -118,14 +115,14 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -156,6 +153,16 @@ __device__ __forceinline__ float tc_act(float v, int act, float slope) {
   return v;
 }
 
+// accumulator -> fp32 result: undo the two power-of-two operand scales (two factors: their product may leave the
+// float exponent range although each factor and the result do not)
+struct TcScale { float fa, fb; };
+__device__ __forceinline__ TcScale tc_scale(const unsigned* amax_a, const unsigned* amax_b) {
+  TcScale s;
+  s.fa = og_exp2i(-og_scale_exp(__ldg(amax_a)));
+  s.fb = og_exp2i(-og_scale_exp(__ldg(amax_b)));
+  return s;
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1.
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
@@ -166,12 +173,10 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                          // layout type: SWIZZLE_128B
   return d;
 }
-// instruction descriptor: D = f32, A = B = tf32, both K-major, dense
-__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+// instruction descriptor: D = f32, A = B = f16 (format code 0), both K-major, dense
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
   uint32_t d = 0;
   d |= 1u << 4;                    // c_format = F32
-  d |= 2u << 7;                    // a_format = TF32
-  d |= 2u << 10;                   // b_format = TF32
   d |= (uint32_t)(N >> 3) << 17;   // n_dim
   d |= (uint32_t)(M >> 4) << 24;   // m_dim
   return d;
@@ -183,8 +188,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                const TcParams p) {
-  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
-  constexpr uint32_t B_BYTES = BN * TC_BK * 4;
+  constexpr uint32_t A_BYTES = TC_BM * 128;         // 128 rows of 128 bytes = 16 KB
+  constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   extern __shared__ uint8_t smem_raw[];
@@ -255,7 +260,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+      const uint32_t idesc = make_idesc_f16(TC_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nk; ++it) {
@@ -264,16 +269,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
         const uint64_t ah = make_desc_sw128(sa), al = make_desc_sw128(sa + A_BYTES);
         const uint64_t bh = make_desc_sw128(sa + 2 * A_BYTES), bl = make_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+        // the last channel chunk may hold fewer than 64 real channels: skip the k-steps that would multiply zeros
+        const int ks = ((it_beg + it + 1) % p.cchunks == 0) ? p.klast : 4;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);   // advance 32 bytes inside the swizzle row
+        for (int k = 0; k < 4; ++k) {
+          if (k >= ks) break;
+          const uint64_t koff = (uint64_t)((k * 32) >> 4);      // advance 32 bytes (16 fp16) inside the swizzle row
           const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
           if (p.nsplit == 3) {
-            umma_tf32(tmem_base, al + koff, bh + koff, idesc, acc);   // small terms first
-            umma_tf32(tmem_base, ah + koff, bl + koff, idesc, 1u);
-            umma_tf32(tmem_base, ah + koff, bh + koff, idesc, 1u);
+            umma_f16(tmem_base, al + koff, bh + koff, idesc, acc);   // small terms first
+            umma_f16(tmem_base, ah + koff, bl + koff, idesc, 1u);
+            umma_f16(tmem_base, ah + koff, bh + koff, idesc, 1u);
           } else {
-            umma_tf32(tmem_base, ah + koff, bh + koff, idesc, acc);
+            umma_f16(tmem_base, ah + koff, bh + koff, idesc, acc);
           }
         }
         umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
@@ -295,6 +303,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     const int oy = p.osy * h + p.opy, ox = p.osx * w + p.opx;
     const bool row_ok = (n < p.N) && (h < p.OH) && (w < p.OW) && (oy < p.OHfull) && (ox < p.OWfull);
     float* yrow = p.y + (long long)n * p.ysn + (long long)oy * p.ysh + (long long)ox * p.ysw + col0;
+    const TcScale sc = tc_scale(p.amax_a, p.amax_b);
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -305,8 +314,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           if (c + j < BN && col0 + c + j < p.K) {
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                   __uint_as_float(r[j + 3]));
+            float4 v = make_float4(__uint_as_float(r[j]) * sc.fa * sc.fb, __uint_as_float(r[j + 1]) * sc.fa * sc.fb,
+                                   __uint_as_float(r[j + 2]) * sc.fa * sc.fb, __uint_as_float(r[j + 3]) * sc.fa * sc.fb);
             if (p.bias) {
               float4 b = ldg4(p.bias + col0 + c + j);
               v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -350,8 +359,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                 const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                 const TcParams p) {
   constexpr int AS = 3, BS = 2;
-  constexpr uint32_t A_BYTES = (TALL ? 160 : TC_BM) * TC_BK * 4;   // one of hi / lo: 128 rows, or 10 x 16 patch rows
-  constexpr uint32_t B_BYTES = BN * TC_BK * 4;
+  constexpr uint32_t A_BYTES = (TALL ? 160 : TC_BM) * 128;   // one of hi / lo: 128 rows, or 10 x 16 patch rows
+  constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t A_SLOT = 2 * A_BYTES, B_SLOT = 2 * B_BYTES;
   constexpr uint32_t ACC_STRIDE = 256;               // TMEM column offset of the second accumulator
   extern __shared__ uint8_t smem_raw[];
@@ -435,23 +444,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+      const uint32_t idesc = make_idesc_f16(TC_BM, BN);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      auto mma_half = [&](uint32_t sa, uint32_t rowoff, uint32_t sb, int hf, bool first) {
+      auto mma_half = [&](uint32_t sa, uint32_t rowoff, uint32_t sb, int hf, bool first, int ks) {
         const uint64_t ah = make_desc_sw128(sa + rowoff), al = make_desc_sw128(sa + A_BYTES + rowoff);
         const uint64_t bh = make_desc_sw128(sb), bl = make_desc_sw128(sb + B_BYTES);
         const uint32_t d = tmem_base + hf * ACC_STRIDE;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+        for (int k = 0; k < 4; ++k) {
+          if (k >= ks) break;
+          const uint64_t koff = (uint64_t)((k * 32) >> 4);
           const uint32_t acc = (!first || k > 0) ? 1u : 0u;
           if (split3) {
-            umma_tf32(d, al + koff, bh + koff, idesc, acc);
-            umma_tf32(d, ah + koff, bl + koff, idesc, 1u);
-            umma_tf32(d, ah + koff, bh + koff, idesc, 1u);
+            umma_f16(d, al + koff, bh + koff, idesc, acc);
+            umma_f16(d, ah + koff, bl + koff, idesc, 1u);
+            umma_f16(d, ah + koff, bh + koff, idesc, 1u);
           } else {
-            umma_tf32(d, ah + koff, bh + koff, idesc, acc);
+            umma_f16(d, ah + koff, bh + koff, idesc, acc);
           }
         }
       };
@@ -460,17 +470,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         for (int g = 0; g < groups; ++g) {
           const int a0 = as, a1 = (as + 1) % AS;
           const uint32_t aph0 = aph, aph1 = (as + 1 == AS) ? (aph ^ 1) : aph;
+          const int ks = ((g + 1) % p.cchunks == 0) ? p.klast : 4;
           for (int j = 0; j < 3; ++j) {
             mbar_wait(&fullB[bs], bph);
             const uint32_t sb = smem_u32(smem_b + (size_t)bs * B_SLOT);
             if (j == 0) mbar_wait(&fullA[a0], aph0);
             tc_fence_after();
-            mma_half(smem_u32(smem_a + (size_t)a0 * A_SLOT), j * 16 * 128, sb, 0, g == 0 && j == 0);
+            mma_half(smem_u32(smem_a + (size_t)a0 * A_SLOT), j * 16 * 128, sb, 0, g == 0 && j == 0, ks);
             if (j == 0) {
               mbar_wait(&fullA[a1], aph1);
               tc_fence_after();
             }
-            mma_half(smem_u32(smem_a + (size_t)a1 * A_SLOT), j * 16 * 128, sb, 1, g == 0 && j == 0);
+            mma_half(smem_u32(smem_a + (size_t)a1 * A_SLOT), j * 16 * 128, sb, 1, g == 0 && j == 0, ks);
             umma_commit(&emptyB[bs]);
             if (++bs == BS) { bs = 0; bph ^= 1; }
           }
@@ -483,11 +494,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         for (int it = 0; it < nk; ++it) {
           mbar_wait(&fullB[bs], bph);
           const uint32_t sb = smem_u32(smem_b + (size_t)bs * B_SLOT);
+          const int ks = ((it + 1) % p.cchunks == 0) ? p.klast : 4;
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             mbar_wait(&fullA[as], aph);
             tc_fence_after();
-            mma_half(smem_u32(smem_a + (size_t)as * A_SLOT), 0, sb, hf, it == 0);
+            mma_half(smem_u32(smem_a + (size_t)as * A_SLOT), 0, sb, hf, it == 0, ks);
             umma_commit(&emptyA[as]);
             if (++as == AS) { as = 0; aph ^= 1; }
           }
@@ -503,6 +515,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
+    const TcScale sc = tc_scale(p.amax_a, p.amax_b);
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -519,8 +532,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             if (c + j < BN && col0 + c + j < p.K) {
-              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                     __uint_as_float(r[j + 3]));
+              float4 v = make_float4(__uint_as_float(r[j]) * sc.fa * sc.fb, __uint_as_float(r[j + 1]) * sc.fa * sc.fb,
+                                     __uint_as_float(r[j + 2]) * sc.fa * sc.fb, __uint_as_float(r[j + 3]) * sc.fa * sc.fb);
               if (p.bias) {
                 float4 b = ldg4(p.bias + col0 + c + j);
                 v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -561,9 +574,9 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// fp32 tensor viewed as [d3][d2][d1][d0] (d0 contiguous); strides in elements for d1..d3
-int make_map(CUtensorMap* m, const float* base, int rank, const unsigned long long* dims,
-             const unsigned long long* strides_elems, const unsigned* box, bool atom32 = false) {
+// fp16 tensor viewed as [d4][d3][d2][d1][d0] (d0 contiguous); strides in elements for d1..
+int make_map(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+             const unsigned long long* strides_elems, const unsigned* box) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return (int)cudaErrorNotSupported;
   cuuint64_t gdim[5], gstr[4];
@@ -573,17 +586,17 @@ int make_map(CUtensorMap* m, const float* base, int rank, const unsigned long lo
     bx[i] = box[i];
     es[i] = 1;
   }
-  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_elems[i] * sizeof(float);
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_elems[i] * sizeof(__half);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, (void*)base, gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 1000 + (int)r;
 }
 
 template <int BN, int STAGES>
 int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
               const TcParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 1024;
+  constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * 128 + 2 * BN * 128) + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -600,17 +613,16 @@ int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
 //   dW[t][co][ci] += sum_{n,h,w} G[n,h,w,co] * X[n, h+dh_t, w+dw_t, ci]
 // GEMM per tap: M = co, N = ci, reduction over pixels.  Both operands are read straight from the NHWC hi/lo
 // tensors the forward / input-gradient kernels already use, i.e. they are "MN-major" for the MMA (channel index
-// contiguous, reduction index = smem row).  For 32-bit operands tcgen05 accepts that only in the 128-byte
-// swizzle with 32-byte atoms (descriptor layout type 1; the ordinary 128B swizzle silently yields zeros --
-// tests/probes/probe_mnmajor.cu), which TMA produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  A smem operand
-// is a stack of "slabs" (32 channels x 32 pixels = 32 rows of 128 bytes, LBO = 4096 apart; 4-row groups SBO =
-// 512 apart); one 5-D TMA box (32 channels-in-slab, w, h, n, slab) fills all slabs of an operand, the tap shift
-// is a plain coordinate offset with out-of-bounds zero fill.  One MMA consumes 8 pixel rows (K = 8).
+// contiguous, reduction index = smem row; descriptor layout and strides verified by tests/probes/probe_mnmajor*.cu:
+// 16-bit operands take the ordinary 128B swizzle, 32-bit ones would need the 32-byte-atom variant).  A smem
+// operand is a stack of "slabs" (64 channels x 64 pixels = 64 rows of 128 bytes, LBO = 8192 apart; 8-row groups
+// SBO = 1024 apart); one 5-D TMA box (64 channels-in-slab, w, h, n, slab) fills all slabs of an operand, the tap
+// shift is a plain coordinate offset with out-of-bounds zero fill.  One MMA consumes 16 pixel rows (K = 16).
 // Grid: (co tiles x ci tiles, taps, pixel splits); partial sums are reduced with fp32 atomics.
 // ------------------------------------------------------------------------------------------------
 struct TcWgradParams {
   int N, OH, OW;        // pixel grid of G
-  int cw, chh, cn;      // pixel chunk of one stage: cw x chh x cn = 32 pixels (w fastest)
+  int cw, chh, cn;      // pixel chunk of one stage: cw x chh x cn = 64 pixels (w fastest)
   int wchunks, hchunks; // chunks per row / per image column
   int total_chunks;
   int chunks_per_cta;
@@ -618,12 +630,15 @@ struct TcWgradParams {
   int cotiles;          // blockIdx.x = citile * cotiles + cotile
   int nsplit;
   float* dw;            // [ntaps_out][Kp][C]
+  const unsigned* amax_g; // operand scales (see TcParams)
+  const unsigned* amax_x;
   // entry e: dW[out[e]] += G[n + gdn[e], h, w]^T * X[n + xdn[e], h + xdh[e], w + xdw[e]]
   int gdn[TC_MAX_TAPS], xdh[TC_MAX_TAPS], xdw[TC_MAX_TAPS], xdn[TC_MAX_TAPS], out[TC_MAX_TAPS];
 };
 
-constexpr int WG_PIX = 32;                     // pixels per stage (4 MMA k-steps)
-constexpr uint32_t WG_SLAB = WG_PIX * 128;     // bytes of one slab: 32 pixels x 32 channels
+constexpr int WG_PIX = 64;                     // pixels per stage (4 MMA k-steps of 16)
+constexpr int WG_CH = 64;                      // channels per slab = one 128-byte row
+constexpr uint32_t WG_SLAB = WG_PIX * 128;     // bytes of one slab: 64 pixels x 64 channels
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3, int c4) {
@@ -632,18 +647,18 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
-// MN-major slab stack, 128B swizzle with 32-byte atoms: LBO = slab pitch, SBO = 4 rows * 128 B
+// MN-major slab stack, 128B swizzle: LBO = slab pitch, SBO = 8 rows * 128 B
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)(WG_SLAB >> 4) << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;                          // layout type: SWIZZLE_128B_BASE32B
+  d |= (uint64_t)2 << 61;                          // layout type: SWIZZLE_128B
   return d;
 }
-__device__ __forceinline__ uint32_t make_idesc_tf32_mn(int M, int N) {
-  return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);   // A and B both MN-major
+__device__ __forceinline__ uint32_t make_idesc_f16_mn(int M, int N) {
+  return make_idesc_f16(M, N) | (1u << 15) | (1u << 16);   // A and B both MN-major
 }
 
 template <int BNW, int STAGES>
@@ -651,8 +666,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_constant__ CUtensorMap map_gl,
                      const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                      const TcWgradParams p) {
-  constexpr int NSB = (BNW + 31) / 32;                    // slabs of the X operand
-  constexpr uint32_t A_BYTES = 4 * WG_SLAB;               // 128 co = 4 slabs = 16 KB
+  constexpr int NSB = (BNW + WG_CH - 1) / WG_CH;          // slabs of the X operand
+  constexpr uint32_t A_BYTES = 2 * WG_SLAB;               // 128 co = 2 slabs = 16 KB
   constexpr uint32_t B_BYTES = NSB * WG_SLAB;
   constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   constexpr uint32_t TMEM_COLS = BNW <= 32 ? 32 : BNW <= 64 ? 64 : BNW <= 128 ? 128 : 256;
@@ -690,7 +705,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       const int gdn = p.gdn[tap], xdh = p.xdh[tap], xdw = p.xdw[tap], xdn = p.xdn[tap];
-      const int aslab = cotile * 4, bslab = citile * NSB;
+      const int aslab = cotile * 2, bslab = citile * NSB;
       for (int it = 0; it < nk; ++it) {
         const int ch = ch_beg + it;
         const int wc = ch % p.wchunks;
@@ -714,7 +729,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32_mn(TC_BM, BNW);
+      const uint32_t idesc = make_idesc_f16_mn(TC_BM, BNW);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nk; ++it) {
@@ -724,15 +739,15 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
         const uint64_t ah = make_desc_mn(sa), al = make_desc_mn(sa + A_BYTES);
         const uint64_t bh = make_desc_mn(sa + 2 * A_BYTES), bl = make_desc_mn(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-        for (int k = 0; k < WG_PIX / 8; ++k) {
-          const uint64_t koff = (uint64_t)((k * 8 * 128) >> 4);     // 8 pixel rows of 128 bytes
+        for (int k = 0; k < WG_PIX / 16; ++k) {
+          const uint64_t koff = (uint64_t)((k * 16 * 128) >> 4);    // 16 pixel rows of 128 bytes
           const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
           if (p.nsplit == 3) {
-            umma_tf32(tmem_base, al + koff, bh + koff, idesc, acc);
-            umma_tf32(tmem_base, ah + koff, bl + koff, idesc, 1u);
-            umma_tf32(tmem_base, ah + koff, bh + koff, idesc, 1u);
+            umma_f16(tmem_base, al + koff, bh + koff, idesc, acc);
+            umma_f16(tmem_base, ah + koff, bl + koff, idesc, 1u);
+            umma_f16(tmem_base, ah + koff, bh + koff, idesc, 1u);
           } else {
-            umma_tf32(tmem_base, ah + koff, bh + koff, idesc, acc);
+            umma_f16(tmem_base, ah + koff, bh + koff, idesc, acc);
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -749,6 +764,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
     const bool row_ok = co < p.Kp;
     float* drow = p.dw + ((long long)p.out[tap] * p.Kp + co) * p.C + citile * BNW;
     const int cleft = p.C - citile * BNW;
+    const TcScale sc = tc_scale(p.amax_g, p.amax_x);
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -758,7 +774,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_co
       if (row_ok) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (c + j < BNW && c + j < cleft) atomicAdd(drow + c + j, __uint_as_float(r[j]));
+          if (c + j < BNW && c + j < cleft) atomicAdd(drow + c + j, __uint_as_float(r[j]) * sc.fa * sc.fb);
       }
     }
     tc_fence_before();
@@ -777,8 +793,8 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_c
                       const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                       const TcWgradParams p) {
   constexpr int AS = 3, BS = 2;
-  constexpr int NSB = (BNW + 31) / 32;
-  constexpr uint32_t A_BYTES = 4 * WG_SLAB;
+  constexpr int NSB = (BNW + WG_CH - 1) / WG_CH;
+  constexpr uint32_t A_BYTES = 2 * WG_SLAB;
   constexpr uint32_t B_BYTES = NSB * WG_SLAB;
   constexpr uint32_t A_SLOT = 2 * A_BYTES, B_SLOT = 2 * B_BYTES;
   constexpr uint32_t ACC_STRIDE = 256;
@@ -835,7 +851,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_c
           mbar_wait(&emptyA[as], aph ^ 1);
           uint8_t* sa = smem_a + (size_t)as * A_SLOT;
           mbar_expect_tx(&fullA[as], split3 ? A_SLOT : A_BYTES);
-          const int aslab = (copair * 2 + hf) * 4;      // past the last slab: out of bounds, zero filled
+          const int aslab = (copair * 2 + hf) * 2;      // past the last slab: out of bounds, zero filled
           tma_load_5d(sa, &map_gh, &fullA[as], 0, w0, h, n + gdn, aslab);
           if (split3) tma_load_5d(sa + A_BYTES, &map_gl, &fullA[as], 0, w0, h, n + gdn, aslab);
           if (++as == AS) { as = 0; aph ^= 1; }
@@ -844,7 +860,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_c
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32_mn(TC_BM, BNW);
+      const uint32_t idesc = make_idesc_f16_mn(TC_BM, BNW);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int it = 0; it < nk; ++it) {
@@ -859,15 +875,15 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_c
           const uint64_t ah = make_desc_mn(sa), al = make_desc_mn(sa + A_BYTES);
           const uint32_t d = tmem_base + hf * ACC_STRIDE;
 #pragma unroll
-          for (int k = 0; k < WG_PIX / 8; ++k) {
-            const uint64_t koff = (uint64_t)((k * 8 * 128) >> 4);
+          for (int k = 0; k < WG_PIX / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 16 * 128) >> 4);
             const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
             if (split3) {
-              umma_tf32(d, al + koff, bh + koff, idesc, acc);
-              umma_tf32(d, ah + koff, bl + koff, idesc, 1u);
-              umma_tf32(d, ah + koff, bh + koff, idesc, 1u);
+              umma_f16(d, al + koff, bh + koff, idesc, acc);
+              umma_f16(d, ah + koff, bl + koff, idesc, 1u);
+              umma_f16(d, ah + koff, bh + koff, idesc, 1u);
             } else {
-              umma_tf32(d, ah + koff, bh + koff, idesc, acc);
+              umma_f16(d, ah + koff, bh + koff, idesc, acc);
             }
           }
           umma_commit(&emptyA[as]);
@@ -881,6 +897,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_c
   } else {
     const int q = warp & 3;
     const int cleft = p.C - citile * BNW;
+    const TcScale sc = tc_scale(p.amax_g, p.amax_x);
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -895,7 +912,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_c
         if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (c + j < BNW && c + j < cleft) atomicAdd(drow + c + j, __uint_as_float(r[j]));
+            if (c + j < BNW && c + j < cleft) atomicAdd(drow + c + j, __uint_as_float(r[j]) * sc.fa * sc.fb);
         }
       }
     }
@@ -911,7 +928,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_c
 template <int BNW>
 int launch_wgrad2(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
                   const TcWgradParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)3 * (2 * 4 * WG_SLAB) + (size_t)2 * (2 * ((BNW + 31) / 32) * WG_SLAB) + 1024;
+  constexpr size_t smem = (size_t)3 * (2 * 2 * WG_SLAB) + (size_t)2 * (2 * ((BNW + WG_CH - 1) / WG_CH) * WG_SLAB) + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad2_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -925,7 +942,7 @@ int launch_wgrad2(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMa
 template <int BNW, int STAGES>
 int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
                  const TcWgradParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (2 * 4 * WG_SLAB + 2 * ((BNW + 31) / 32) * WG_SLAB) + 1024;
+  constexpr size_t smem = (size_t)STAGES * (2 * 2 * WG_SLAB + 2 * ((BNW + WG_CH - 1) / WG_CH) * WG_SLAB) + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<BNW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -939,7 +956,7 @@ int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap
 template <int BN, bool TALL>
 int launch_tc2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                const TcParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)3 * (2 * (TALL ? 160 : TC_BM) * TC_BK * 4) + (size_t)2 * (2 * BN * TC_BK * 4) + 1024;
+  constexpr size_t smem = (size_t)3 * (2 * (TALL ? 160 : TC_BM) * 128) + (size_t)2 * (2 * BN * 128) + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, TALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -954,9 +971,10 @@ int launch_tc2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
 
 // ------------------------------------------------------------------------------------------------
 // C ABI.
-//   xh/xl : source activations, tf32 hi / lo parts (og_prep_split), NHWC [SN][SH][SW][C] contiguous, C % 4 == 0
+//   xh/xl : source activations, fp16 hi / lo parts (og_prep_split), NHWC [SN][SH][SW][C] contiguous, C % 8 == 0
 //           (SN = N, or 4*N for a space-to-depth source: phase block (a*2+b) holds x[:, a::2, b::2])
-//   wh/wl : weights hi / lo, [ntaps_w][Kw][C] (og_pack_weights with transposed=1 for fprop), Kw rows
+//   wh/wl : weights fp16 hi / lo, [ntaps_w][Kw][C] (og_pack_weights_f16 with transposed=1 for fprop), Kw rows
+//   amax_x / amax_w : device words holding the float bits of max|.| of the two operand tensors (their scaling)
 //   y     : output NHWC, channel count K (K % 4 == 0), element strides ysn/ysh/ysw, spatial bounds OHf x OWf
 //   rows of the GEMM are the pixel grid N x OH x OW; output pixel (osy*h + opy, osx*w + opx)
 //   taps  : ntaps quadruples (dh, dw, dn, weight tap index): source pixel = image n + dn, (h + dh, w + dw), zero
@@ -964,12 +982,13 @@ int launch_tc2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
 //   tap_layout = 1 promises that the taps come in groups of three with equal dw, dn and dh = d0, d0+1, d0+2 (3x3
 //           kernels listed column by column), which lets the kernel reuse one tall pixel patch for three taps
 // ------------------------------------------------------------------------------------------------
-OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH, int SW, int C, const float* wh,
-                        const float* wl, int ntaps_w, int Kw, float* y, int OH, int OW, int K, long long ysn,
+OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, int N, int SN, int SH, int SW, int C,
+                        const void* wh, const void* wl, const unsigned* amax_w, int ntaps_w, int Kw, float* y, int OH,
+                        int OW, int K, long long ysn,
                         long long ysh, long long ysw, int OHf, int OWf, int osy, int osx, int opy, int opx,
                         const int* taps_host, int ntaps, int tap_layout, int nsplit, const float* bias, int act,
                         float slope, cudaStream_t stream) {
-  if (C % 4 || K % 4 || ntaps < 1 || ntaps > TC_MAX_TAPS || (nsplit != 1 && nsplit != 3)) return (int)cudaErrorInvalidValue;
+  if (C % 8 || K % 4 || ntaps < 1 || ntaps > TC_MAX_TAPS || (nsplit != 1 && nsplit != 3)) return (int)cudaErrorInvalidValue;
   if ((long long)N * OH * OW == 0) return 0;
   TcParams p;
   p.N = N; p.OH = OH; p.OW = OW;
@@ -988,6 +1007,8 @@ OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH,
   p.tiles_h = og_cdiv(OH, TH);
   const int tiles_n = og_cdiv(N, TN);
   p.cchunks = og_cdiv(C, TC_BK);
+  p.klast = og_cdiv(C - (p.cchunks - 1) * TC_BK, 16);
+  p.amax_a = amax_x; p.amax_b = amax_w;
   p.K = K;
   p.nsplit = nsplit;
   p.y = y; p.ysn = ysn; p.ysh = ysh; p.ysw = ysw;
@@ -1076,21 +1097,24 @@ OG_API int og_conv2d_tc(const float* xh, const float* xl, int N, int SN, int SH,
 
 // ------------------------------------------------------------------------------------------------
 // weight gradient:  dw[t][co][ci] (fp32, [ntaps][Kp][C], zero-filled here) = sum_pixels G^T * X(shifted by tap t)
-//   gh/gl : output gradient hi/lo, NHWC [GN][OH][OW][Kp]   (og_prep_split; GN = N, or 4N space-to-depth blocks)
-//   xh/xl : source activations hi/lo, NHWC [XN][SH][SW][C] (og_prep_split: plain, reflection-padded or
+//   gh/gl : output gradient fp16 hi/lo, NHWC [GN][OH][OW][Kp] (og_prep_split; GN = N, or 4N space-to-depth blocks)
+//   xh/xl : source activations fp16 hi/lo, NHWC [XN][SH][SW][C] (og_prep_split: plain, reflection-padded or
 //           space-to-depth); both need 512 readable bytes after the last element (partial last channel slab)
+//   amax_g / amax_x : operand scales as in og_conv2d_tc
 //   entries: nentries quintuples (g image offset, dh, dw, x image offset, output tap):
 //           dw[tap] += sum_{n,h,w} G[n + gdn, h, w, :]^T  X[n + xdn, h + dh, w + dw, :]   (out of range = 0)
 // ------------------------------------------------------------------------------------------------
-OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int GN, int OH, int OW, int Kp,
-                              const float* xh, const float* xl, int XN, int SH, int SW, int C, float* dw,
+OG_API int og_conv2d_wgrad_tc(const void* gh, const void* gl, const unsigned* amax_g, int N, int GN, int OH, int OW,
+                              int Kp, const void* xh, const void* xl, const unsigned* amax_x, int XN, int SH, int SW,
+                              int C, float* dw,
                               int ntaps_out, const int* entries_host, int nentries, int nsplit, cudaStream_t stream) {
-  if (nentries < 1 || nentries > TC_MAX_TAPS || (nsplit != 1 && nsplit != 3)) return (int)cudaErrorInvalidValue;
+  if (nentries < 1 || nentries > TC_MAX_TAPS || (nsplit != 1 && nsplit != 3) || Kp % 8 || C % 8)
+    return (int)cudaErrorInvalidValue;
   OG_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)ntaps_out * Kp * C, stream));
   if ((long long)N * OH * OW == 0) return 0;
   TcWgradParams p;
   p.N = N; p.OH = OH; p.OW = OW;
-  // one stage = 32 pixels: a cw x chh x cn patch of the gradient grid (w fastest)
+  // one stage = 64 pixels: a cw x chh x cn patch of the gradient grid (w fastest)
   int cw = 1;
   while (cw * 2 <= WG_PIX && OW % (cw * 2) == 0) cw *= 2;
   int chh = 1;
@@ -1102,6 +1126,7 @@ OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int GN, i
   p.hchunks = OH / chh;
   p.total_chunks = p.wchunks * p.hchunks * (N / cn);
   p.Kp = Kp; p.C = C; p.nsplit = nsplit; p.dw = dw;
+  p.amax_g = amax_g; p.amax_x = amax_x;
   for (int i = 0; i < nentries; ++i) {
     p.gdn[i] = entries_host[5 * i];
     p.xdh[i] = entries_host[5 * i + 1];
@@ -1123,21 +1148,23 @@ OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int GN, i
   splits = og_cdiv(p.total_chunks, p.chunks_per_cta);
   dim3 grid(cotiles * citiles, nentries, splits);
   CUtensorMap mgh, mgl, mxh, mxl;
-  // [slab][n][h][w][32 channels of the slab]: the slab dimension strides by 32 floats inside a pixel's channel vector
-  unsigned long long gd[5] = {32ull, (unsigned long long)OW, (unsigned long long)OH, (unsigned long long)GN,
-                              (unsigned long long)og_cdiv(Kp, 32)};
-  unsigned long long gs[4] = {(unsigned long long)Kp, (unsigned long long)OW * Kp, (unsigned long long)OH * OW * Kp, 32ull};
-  unsigned gb[5] = {32u, (unsigned)cw, (unsigned)chh, (unsigned)cn, 4u};
-  unsigned long long xd[5] = {32ull, (unsigned long long)SW, (unsigned long long)SH, (unsigned long long)XN,
-                              (unsigned long long)og_cdiv(C, 32)};
-  unsigned long long xs[4] = {(unsigned long long)C, (unsigned long long)SW * C, (unsigned long long)SH * SW * C, 32ull};
-  unsigned xb[5] = {32u, (unsigned)cw, (unsigned)chh, (unsigned)cn, (unsigned)((BNsel + 31) / 32)};
+  // [slab][n][h][w][64 channels of the slab]: the slab dimension strides by 64 halves inside a pixel's channel vector
+  unsigned long long gd[5] = {(unsigned long long)WG_CH, (unsigned long long)OW, (unsigned long long)OH,
+                              (unsigned long long)GN, (unsigned long long)og_cdiv(Kp, WG_CH)};
+  unsigned long long gs[4] = {(unsigned long long)Kp, (unsigned long long)OW * Kp, (unsigned long long)OH * OW * Kp,
+                              (unsigned long long)WG_CH};
+  unsigned gb[5] = {(unsigned)WG_CH, (unsigned)cw, (unsigned)chh, (unsigned)cn, 2u};
+  unsigned long long xd[5] = {(unsigned long long)WG_CH, (unsigned long long)SW, (unsigned long long)SH,
+                              (unsigned long long)XN, (unsigned long long)og_cdiv(C, WG_CH)};
+  unsigned long long xs[4] = {(unsigned long long)C, (unsigned long long)SW * C, (unsigned long long)SH * SW * C,
+                              (unsigned long long)WG_CH};
+  unsigned xb[5] = {(unsigned)WG_CH, (unsigned)cw, (unsigned)chh, (unsigned)cn, (unsigned)((BNsel + WG_CH - 1) / WG_CH)};
   int rc;
-  if ((rc = make_map(&mgh, gh, 5, gd, gs, gb, true))) return rc;
-  if ((rc = make_map(&mxh, xh, 5, xd, xs, xb, true))) return rc;
+  if ((rc = make_map(&mgh, gh, 5, gd, gs, gb))) return rc;
+  if ((rc = make_map(&mxh, xh, 5, xd, xs, xb))) return rc;
   if (nsplit == 3) {
-    if ((rc = make_map(&mgl, gl, 5, gd, gs, gb, true))) return rc;
-    if ((rc = make_map(&mxl, xl, 5, xd, xs, xb, true))) return rc;
+    if ((rc = make_map(&mgl, gl, 5, gd, gs, gb))) return rc;
+    if ((rc = make_map(&mxl, xl, 5, xd, xs, xb))) return rc;
   } else {
     mgl = mgh;
     mxl = mxh;
@@ -1164,14 +1191,43 @@ OG_API int og_conv2d_wgrad_tc(const float* gh, const float* gl, int N, int GN, i
   }
 }
 
-__global__ void prep_split_kernel(const float* __restrict__ x, int N, int H, int W, int C4, int pad, int s2d,
-                                  long long total, float* __restrict__ xh, float* __restrict__ xl) {
+// max|x| over a tensor as float bits (non-negative floats order like unsigned integers)
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long n4, int tail,
+                                                   unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = ldg4(x + i * 4);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) m = fmaxf(m, fabsf(x[n4 * 4 + threadIdx.x]));
+  m = warp_max(m);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    m = sm[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+    if (threadIdx.x == 0) atomicMax(out, __float_as_uint(m));
+  }
+}
+
+__device__ __forceinline__ void split_f16(float v, float scale, __half& hi, __half& lo) {
+  v *= scale;
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+__global__ void __launch_bounds__(256) prep_split_kernel(const float* __restrict__ x, int N, int H, int W, int C8, int pad,
+                                                         int s2d, long long total, const unsigned* __restrict__ amax,
+                                                         __half* __restrict__ xh, __half* __restrict__ xl) {
   // output: [N][H+2p][W+2p][C] or, for s2d, [4][N][H/2][W/2][C] with phase block (a*2+b) = x[:, a::2, b::2]
   const int Hp = s2d ? H / 2 : H + 2 * pad, Wp = s2d ? W / 2 : W + 2 * pad;
+  const float scale = og_exp2i(og_scale_exp(__ldg(amax)));
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C4);
-    long long t = i / C4;
+    int c = (int)(i % C8);
+    long long t = i / C8;
     int w = (int)(t % Wp);
     t /= Wp;
     int h = (int)(t % Hp);
@@ -1190,21 +1246,44 @@ __global__ void prep_split_kernel(const float* __restrict__ x, int N, int H, int
       if (sw < 0) sw = -sw;
       if (sw >= W) sw = 2 * W - 2 - sw;
     }
-    float4 v = ldg4(x + (((n * H + sh) * W + sw) * C4 + c) * 4);
-    float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-    st4(xh + i * 4, hi);
-    if (xl) st4(xl + i * 4, make_float4(tf32_lo(v.x, hi.x), tf32_lo(v.y, hi.y), tf32_lo(v.z, hi.z), tf32_lo(v.w, hi.w)));
+    const float* src = x + (((n * H + sh) * W + sw) * C8 + c) * 8;
+    const float4 v0 = ldg4(src), v1 = ldg4(src + 4);
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_f16(v[j], scale, hi[j], lo[j]);
+    *reinterpret_cast<uint4*>(xh + i * 8) = *reinterpret_cast<const uint4*>(hi);
+    if (xl) *reinterpret_cast<uint4*>(xl + i * 8) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
-// pad = 0: plain split; pad = 1: nn.ReflectionPad2d(1) halo (model.py:67) materialised while splitting
-OG_API int og_prep_split(const float* x, int N, int H, int W, int C, int pad, int s2d, float* xh, float* xl,
-                         cudaStream_t stream) {
-  if (C % 4 || pad < 0 || pad > 1 || (s2d && (pad || (H & 1) || (W & 1)))) return (int)cudaErrorInvalidValue;
-  long long total = s2d ? (long long)N * H * W * (C / 4) : (long long)N * (H + 2 * pad) * (W + 2 * pad) * (C / 4);
-  if (total == 0) return 0;
+// fp16 hi/lo operand copies of an NHWC fp32 tensor, scaled by the power of two that og_scale_exp derives from
+// max|x| (written to *amax as float bits).  pad = 0: plain; pad = 1: nn.ReflectionPad2d(1) halo (model.py:67)
+// materialised while splitting; s2d = 1: four space-to-depth phase blocks.  xl may be null (single-product mode).
+OG_API int og_prep_split(const float* x, int N, int H, int W, int C, int pad, int s2d, unsigned* amax, void* xh,
+                         void* xl, cudaStream_t stream) {
+  if (C % 8 || pad < 0 || pad > 1 || (s2d && (pad || (H & 1) || (W & 1)))) return (int)cudaErrorInvalidValue;
+  OG_CHECK(cudaMemsetAsync(amax, 0, sizeof(unsigned), stream));
+  const long long n4 = (long long)N * H * W * C / 4;
+  if (n4 == 0) return 0;
+  long long ab = (n4 + 255) / 256;
+  if (ab > 148LL * 8) ab = 148LL * 8;
+  amax_kernel<<<(int)ab, 256, 0, stream>>>(x, n4, 0, amax);
+  long long total = s2d ? (long long)N * H * W * (C / 8) : (long long)N * (H + 2 * pad) * (W + 2 * pad) * (C / 8);
   long long b = (total + 255) / 256;
   if (b > 148LL * 32) b = 148LL * 32;
-  prep_split_kernel<<<(int)b, 256, 0, stream>>>(x, N, H, W, C / 4, pad, s2d, total, xh, xl);
+  prep_split_kernel<<<(int)b, 256, 0, stream>>>(x, N, H, W, C / 8, pad, s2d, total, amax, (__half*)xh, (__half*)xl);
+  OG_RETURN_LAST_ERROR();
+}
+
+// *amax = float bits of max|x[0..n)| (x 16-byte aligned); used for the weight tensors before og_pack_weights_f16
+OG_API int og_amax(const float* x, long long n, unsigned* amax, cudaStream_t stream) {
+  OG_CHECK(cudaMemsetAsync(amax, 0, sizeof(unsigned), stream));
+  if (n == 0) return 0;
+  const long long n4 = n / 4;
+  long long ab = (n4 + 255) / 256;
+  if (ab < 1) ab = 1;
+  if (ab > 148LL * 8) ab = 148LL * 8;
+  amax_kernel<<<(int)ab, 256, 0, stream>>>(x, n4, (int)(n - n4 * 4), amax);
   OG_RETURN_LAST_ERROR();
 }

@@ -62,52 +62,64 @@ class PackedWeights:
         self.f = None
         self.t = None
         self.hl = {}
+        self.amax = None
 
     def _refresh(self, w, cip, kp, split):
         key = (w.data_ptr(), w._version, _param_epoch[0], cip, kp, split)
         if key != self.key:
-            self.key, self.f, self.t, self.hl = key, None, None, {}
+            self.key, self.f, self.t, self.hl, self.amax = key, None, None, {}, None
+
+    def _amax(self, w):
+        """Device word with the float bits of max|w| (the power-of-two scale of the fp16 operand copies)."""
+        if self.amax is None:
+            self.amax = torch.empty(1, device=w.device, dtype=torch.int32)
+            _call("og_amax", _p(w), w.numel(), _p(self.amax))
+        return self.amax
 
     def get(self, w, cip, kp, split, splitp, need_t):
         self._refresh(w, cip, kp, split)
         co, ci, kh, kw = w.shape
         if self.f is None:
             self.f = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float32)
-            _call("og_pack_weights", _p(w), co, ci, kh, kw, cip, kp, split, splitp, 0, _p(self.f), 0)
+            _call("og_pack_weights", _p(w), co, ci, kh, kw, cip, kp, split, splitp, 0, _p(self.f))
         if need_t and self.t is None:
             self.t = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float32)
-            _call("og_pack_weights", _p(w), co, ci, kh, kw, cip, kp, split, splitp, 1, _p(self.t), 0)
+            _call("og_pack_weights", _p(w), co, ci, kh, kw, cip, kp, split, splitp, 1, _p(self.t))
         return self.f, self.t
 
     def get_up_hilo(self, w, cip, kp, split, splitp, transposed):
-        """Pre-summed 2x2 phase weights of an upsample+conv3x3 layer, tf32 hi / lo ([16][co][ci] or [16][ci][co])."""
+        """Pre-summed 2x2 phase weights of an upsample+conv3x3 layer as (fp16 hi, fp16 lo, scale word), laid out
+        [16][co][ci] (transposed) or [16][ci][co]."""
         self._refresh(w, cip, kp, split)
         key = ("up", transposed)
         if key not in self.hl:
             co, ci, _, _ = w.shape
-            hi = torch.empty(16 * cip * kp, device=w.device, dtype=torch.float32)
-            lo = torch.empty_like(hi)
-            _call("og_pack_upsample_weights", _p(w), co, ci, cip, kp, split, splitp, transposed, _p(hi), _p(lo))
-            self.hl[key] = (hi, lo)
+            hi = torch.empty(16 * cip * kp, device=w.device, dtype=torch.float16)
+            lo = torch.empty_like(hi) if _nsplit() == 3 else None
+            amax_up = torch.empty(1, device=w.device, dtype=torch.int32)
+            _call("og_pack_upsample_weights", _p(w), co, ci, cip, kp, split, splitp, transposed, _p(self._amax(w)),
+                  _p(amax_up), _p(hi), _p(lo))
+            self.hl[key] = (hi, lo, amax_up)
         return self.hl[key]
 
     def get_hilo(self, w, cip, kp, split, splitp, transposed):
-        """tf32 hi / lo parts of the packed matrix ([tap][co][ci] when transposed else [tap][ci][co])."""
+        """(fp16 hi, fp16 lo, scale word) of the packed matrix ([tap][co][ci] when transposed else [tap][ci][co])."""
         self._refresh(w, cip, kp, split)
         if transposed not in self.hl:
             co, ci, kh, kw = w.shape
-            hi = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float32)
-            lo = torch.empty_like(hi)
-            _call("og_pack_weights", _p(w), co, ci, kh, kw, cip, kp, split, splitp, transposed, _p(hi), _p(lo))
-            self.hl[transposed] = (hi, lo)
+            hi = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float16)
+            lo = torch.empty_like(hi) if _nsplit() == 3 else None
+            _call("og_pack_weights_f16", _p(w), co, ci, kh, kw, cip, kp, split, splitp, transposed,
+                  _p(self._amax(w)), _p(hi), _p(lo))
+            self.hl[transposed] = (hi, lo, self._amax(w))
         return self.hl[transposed]
 
 
-# Contraction engine for the convolutions: "tf32x3" = tcgen05 tensor cores with the error-compensated
-# three-product TF32 split (fp32-level accuracy, the default and the parity mode), "tf32" = one TF32 product
+# Contraction engine for the convolutions: "f16x3" = tcgen05 tensor cores with the error-compensated
+# three-product fp16 hi/lo split (22-bit operands, fp32-level accuracy: the default and the parity mode), "f16" = one fp16 product
 # (faster, outside the 1e-3 parity budget), "simt" = exact fp32 FMA on the CUDA cores.
 import os as _os
-CONV_ENGINE = _os.environ.get("OBJGAN_CONV", "tf32x3")
+CONV_ENGINE = _os.environ.get("OBJGAN_CONV", "f16x3")
 TC_WGRAD = _os.environ.get("OBJGAN_TC_WGRAD", "1") == "1"
 KEEP_SPLIT = _os.environ.get("OBJGAN_KEEP_SPLIT", "1") == "1"   # keep x's hi/lo copies from forward for the wgrad
 TC_MIN_PIXELS = 256        # smaller problems go to the exact-fp32 SIMT kernels (the tc kernel splits K on small maps)
@@ -120,35 +132,41 @@ def _int_array(rows):
 
 
 def _empty_slack(shape, device):
-    """Buffer with 512 bytes of readable slack after the last element."""
+    """fp16 buffer with 512 bytes of readable slack after the last element."""
     n = 1
     for d in shape:
         n *= d
-    flat = torch.empty(n + 128, device=device, dtype=torch.float32)
+    flat = torch.empty(n + 256, device=device, dtype=torch.float16)
     return flat[:n].view(shape)
 
 
 def _nsplit():
-    return 3 if CONV_ENGINE == "tf32x3" else 1
+    return 3 if CONV_ENGINE == "f16x3" else 1
 
 
 def _split(x, pad=0, s2d=False):
-    """tf32 hi/lo parts of an NHWC tensor; pad=1 adds the reflection halo; s2d gives [4N, H/2, W/2, C]."""
+    """(fp16 hi, fp16 lo, scale word) of an NHWC tensor scaled by a power of two from its max|x|; pad=1 adds the
+    reflection halo; s2d gives [4N, H/2, W/2, C]."""
     n, h, w, c = x.shape
     shape = (4 * n, h // 2, w // 2, c) if s2d else (n, h + 2 * pad, w + 2 * pad, c)
     xh = _empty_slack(shape, x.device)
-    xl = _empty_slack(shape, x.device) if CONV_ENGINE == "tf32x3" else None
-    _call("og_prep_split", _p(x), n, h, w, c, pad, 1 if s2d else 0, _p(xh), _p(xl))
-    return xh, xl
+    xl = _empty_slack(shape, x.device) if CONV_ENGINE == "f16x3" else None
+    amax = torch.empty(1, device=x.device, dtype=torch.int32)
+    _call("og_prep_split", _p(x), n, h, w, c, pad, 1 if s2d else 0, _p(amax), _p(xh), _p(xl))
+    return xh, xl, amax
 
 
-def _tc_launch(xh, xl, n, wh, wl, ntaps_w, kw_rows, y, oh, ow, k, osy, op, taps, bias=None, act=ACT_NONE, layout=0):
-    """taps: (dh, dw, dn, widx) quadruples; xh is [SN, SH, SW, C] with SN = n or 4n (space-to-depth source)."""
+def _tc_launch(xs, n, ws, ntaps_w, kw_rows, y, oh, ow, k, osy, op, taps, bias=None, act=ACT_NONE, layout=0):
+    """xs / ws: (hi, lo, scale word) operand triples; taps: (dh, dw, dn, widx) quadruples; the source is
+    [SN, SH, SW, C] with SN = n or 4n (space-to-depth)."""
+    xh, xl, ax = xs
+    wh, wl, aw = ws
     sn, sh, sw, c = xh.shape
     _, ohf, owf, kc = y.shape
     arr = _int_array(taps)
     import ctypes
-    _call("og_conv2d_tc", _p(xh), _p(xl), n, sn, sh, sw, c, _p(wh), _p(wl), ntaps_w, kw_rows, _p(y), oh, ow, k,
+    _call("og_conv2d_tc", _p(xh), _p(xl), _p(ax), n, sn, sh, sw, c, _p(wh), _p(wl), _p(aw), ntaps_w, kw_rows, _p(y),
+          oh, ow, k,
           ohf * owf * kc, owf * kc, kc, ohf, owf, osy, osy, op[0], op[1], ctypes.addressof(arr), len(taps), layout,
           _nsplit(), _p(bias), act, LRELU_SLOPE)
 
@@ -165,7 +183,7 @@ def _tile_n(oh, ow):
 
 def _tc_kind(n, h, w, c, kh, kw, stride, pad, mode):
     """Which tensor-core formulation (if any) applies to this convolution."""
-    if CONV_ENGINE not in ("tf32x3", "tf32") or _lib.DRY_RUN:
+    if CONV_ENGINE not in ("f16x3", "f16") or _lib.DRY_RUN:
         return None
     if kh == 3 and kw == 3 and stride == 1 and pad == 1:
         oh, ow = (2 * h, 2 * w) if mode == UPSAMPLE2X else (h, w)
@@ -185,13 +203,13 @@ _UP_OFF = ((-1, 0), (0, 1))   # low-res row/col offsets read by output phase 0 /
 
 
 def _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act):
-    """Returns (y, (xh, xl)): the output and the tf32 hi/lo operand copies of x (reused by the weight gradient)."""
+    """Returns (y, xs): the output and the fp16 operand triple of x (reused by the weight gradient)."""
     n, h, w, c = x.shape
     dev = x.device
     if mode != UPSAMPLE2X:
-        wh, wl = cache.get_hilo(weight, c, kp, split, splitp, 1)      # [tap][co][ci]
+        ws = cache.get_hilo(weight, c, kp, split, splitp, 1)      # [tap][co][ci]
     if kind == "s2":                                                   # 4x4 stride 2 pad 1 on space-to-depth phases
-        xh, xl = _split(x, s2d=True)
+        xs = _split(x, s2d=True)
         y = torch.empty((n, h // 2, w // 2, kp), device=dev, dtype=torch.float32)
         taps = []
         for kh in range(4):
@@ -199,28 +217,28 @@ def _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act):
             for kw in range(4):
                 dw, b = divmod(kw - 1, 2)
                 taps.append((dh, dw, (a * 2 + b) * n, kh * 4 + kw))
-        _tc_launch(xh, xl, n, wh, wl, 16, kp, y, h // 2, w // 2, kp, 1, (0, 0), taps, bias_p, act)
-        return y, (xh, xl)
+        _tc_launch(xs, n, ws, 16, kp, y, h // 2, w // 2, kp, 1, (0, 0), taps, bias_p, act)
+        return y, xs
     if mode == PAD_REFLECT:
-        xh, xl = _split(x, 1)
+        xs = _split(x, 1)
         y = torch.empty((n, h, w, kp), device=dev, dtype=torch.float32)
         taps = [(kh, kw, 0, kh * 3 + kw) for kw in range(3) for kh in range(3)]      # column by column (layout 1)
-        _tc_launch(xh, xl, n, wh, wl, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act, layout=1)
+        _tc_launch(xs, n, ws, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act, layout=1)
     elif mode == PAD_ZERO:
-        xh, xl = _split(x, 0)
+        xs = _split(x, 0)
         y = torch.empty((n, h, w, kp), device=dev, dtype=torch.float32)
         taps = [(kh - 1, kw - 1, 0, kh * 3 + kw) for kw in range(3) for kh in range(3)]
-        _tc_launch(xh, xl, n, wh, wl, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act, layout=1)
+        _tc_launch(xs, n, ws, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act, layout=1)
     else:  # UPSAMPLE2X: four output phases of 2x2 taps at low resolution, weights pre-summed per phase
-        wh, wl = cache.get_up_hilo(weight, c, kp, split, splitp, 1)
-        xh, xl = _split(x, 0)
+        ws = cache.get_up_hilo(weight, c, kp, split, splitp, 1)
+        xs = _split(x, 0)
         y = torch.empty((n, 2 * h, 2 * w, kp), device=dev, dtype=torch.float32)
         for py in range(2):
             for px in range(2):
                 taps = [(_UP_OFF[py][a], _UP_OFF[px][b], 0, ((py * 2 + px) * 2 + a) * 2 + b)
                         for a in range(2) for b in range(2)]
-                _tc_launch(xh, xl, n, wh, wl, 16, kp, y, h, w, kp, 2, (py, px), taps, bias_p, act)
-    return y, (xh, xl)
+                _tc_launch(xs, n, ws, 16, kp, y, h, w, kp, 2, (py, px), taps, bias_p, act)
+    return y, xs
 
 
 def _split_x(kind, x, mode):
@@ -237,58 +255,57 @@ def _split_g(kind, g, mode):
 
 def _tc_dgrad(kind, gs, n, cache, weight, c, kp, split, splitp, mode, h, w, oh, ow):
     """Input gradient on the tensor cores.  gs: hi/lo of g (N, oh, ow, kp) from _split_g; returns (N, h, w, c)."""
-    gh, gl = gs
-    dev = gh.device
+    dev = gs[0].device
     if mode != UPSAMPLE2X:
-        wh, wl = cache.get_hilo(weight, c, kp, split, splitp, 0)      # [tap][ci][co]
+        ws = cache.get_hilo(weight, c, kp, split, splitp, 0)      # [tap][ci][co]
     if kind == "s2":
         gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
         for a in range(2):
             for b in range(2):
                 taps = [((a + 1 - kh) // 2, (b + 1 - kw) // 2, 0, kh * 4 + kw)
                         for kh in ((1, 3) if a == 0 else (0, 2)) for kw in ((1, 3) if b == 0 else (0, 2))]
-                _tc_launch(gh, gl, n, wh, wl, 16, c, gx, oh, ow, c, 2, (a, b), taps)
+                _tc_launch(gs, n, ws, 16, c, gx, oh, ow, c, 2, (a, b), taps)
         return gx
     if mode == PAD_REFLECT:
         gpad = torch.empty((n, h + 2, w + 2, c), device=dev, dtype=torch.float32)
         taps = [(-kh, -kw, 0, kh * 3 + kw) for kw in range(3) for kh in (2, 1, 0)]   # rows ascending: -2, -1, 0
-        _tc_launch(gh, gl, n, wh, wl, 9, c, gpad, h + 2, w + 2, c, 1, (0, 0), taps, layout=1)
+        _tc_launch(gs, n, ws, 9, c, gpad, h + 2, w + 2, c, 1, (0, 0), taps, layout=1)
         gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
         _call("og_reflect_pad_bwd", _p(gpad), n, h, w, c, _p(gx))
         return gx
     if mode == PAD_ZERO:
         gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
         taps = [(1 - kh, 1 - kw, 0, kh * 3 + kw) for kw in range(3) for kh in (2, 1, 0)]
-        _tc_launch(gh, gl, n, wh, wl, 9, c, gx, h, w, c, 1, (0, 0), taps, layout=1)
+        _tc_launch(gs, n, ws, 9, c, gx, h, w, c, 1, (0, 0), taps, layout=1)
         return gx
     # UPSAMPLE2X: adjoint of the four phase convolutions: gx[i,j] = sum_{p,q,a,b} G_pq[i - off(p,a), j - off(q,b)] Wp^T
-    wh, wl = cache.get_up_hilo(weight, c, kp, split, splitp, 0)
+    ws = cache.get_up_hilo(weight, c, kp, split, splitp, 0)
     gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
     taps = [(-_UP_OFF[p_][a], -_UP_OFF[q_][b], (p_ * 2 + q_) * n, ((p_ * 2 + q_) * 2 + a) * 2 + b)
             for p_ in range(2) for q_ in range(2) for a in range(2) for b in range(2)]
-    _tc_launch(gh, gl, n, wh, wl, 16, c, gx, h, w, c, 1, (0, 0), taps)
+    _tc_launch(gs, n, ws, 16, c, gx, h, w, c, 1, (0, 0), taps)
     return gx
 
 
 def _tc_wgrad_ok(kind, mode, n, oh, ow):
-    """The wgrad kernel streams 32-pixel patches (cw x chh x cn, powers of two) of the gradient grid."""
+    """The wgrad kernel streams 64-pixel patches (cw x chh x cn, powers of two) of the gradient grid."""
     if kind == "s1" and mode == UPSAMPLE2X:
         oh, ow = oh // 2, ow // 2
     cw = 1
-    while cw * 2 <= 32 and ow % (cw * 2) == 0:
+    while cw * 2 <= 64 and ow % (cw * 2) == 0:
         cw *= 2
     chh = 1
-    while cw * chh * 2 <= 32 and oh % (chh * 2) == 0:
+    while cw * chh * 2 <= 64 and oh % (chh * 2) == 0:
         chh *= 2
-    return n % (32 // (cw * chh)) == 0
+    return n % (64 // (cw * chh)) == 0
 
 
 def _tc_wgrad(kind, xs, gs, n, h, w, oh, ow, weight, c, kp, split, splitp, mode):
     """Weight gradient on the tensor cores from the hi/lo copies of x (_split_x) and g (_split_g), both NHWC;
     (h, w) is the extent of x, (oh, ow) of g.  Returns the OIHW gradient."""
     import ctypes
-    xh, xl = xs
-    gh, gl = gs
+    xh, xl, ax = xs
+    gh, gl, ag = gs
     co, ci, kh_, kw_ = weight.shape
     if kind == "s2":
         ent = []
@@ -308,8 +325,8 @@ def _tc_wgrad(kind, xs, gs, n, h, w, oh, ow, weight, c, kp, split, splitp, mode)
         nt = 9
     arr = _int_array(ent)
     dwp = torch.empty(nt * kp * c, device=xh.device, dtype=torch.float32)
-    _call("og_conv2d_wgrad_tc", _p(gh), _p(gl), n, gh.shape[0], oh, ow, kp, _p(xh), _p(xl), xh.shape[0], xh.shape[1],
-          xh.shape[2], c, _p(dwp), nt, ctypes.addressof(arr), len(ent), _nsplit())
+    _call("og_conv2d_wgrad_tc", _p(gh), _p(gl), _p(ag), n, gh.shape[0], oh, ow, kp, _p(xh), _p(xl), _p(ax),
+          xh.shape[0], xh.shape[1], xh.shape[2], c, _p(dwp), nt, ctypes.addressof(arr), len(ent), _nsplit())
     gw = torch.empty_like(weight)
     if mode == UPSAMPLE2X and kind == "s1":
         _call("og_unpack_upsample_wgrad", _p(dwp), co, ci, c, kp, split, splitp, _p(gw))

@@ -386,9 +386,9 @@ def test_g_net_forward_parity():
             assert int(sd2[k]) == int(sd[k]) == 1
 
 
-@pytest.mark.parametrize("engine,l2,mx", [("simt", 5e-3, 3e-2), ("tf32x3", 3e-2, 1e-1)])
+@pytest.mark.parametrize("engine,l2,mx", [("simt", 5e-3, 3e-2), ("f16x3", 3e-2, 1e-1)])
 def test_pat_d_loss_parity(engine, l2, mx, monkeypatch):
-    """simt = exact fp32 contractions (strict); tf32x3 = tensor cores, whose ~1e-5 per-conv rounding is amplified by
+    """simt = exact fp32 contractions (strict); f16x3 = tensor cores, whose ~1e-5 per-conv rounding is amplified by
     the LeakyReLU / BatchNorm(B=4) chain like any other perturbation (DESIGN.md "Parity budget")."""
     monkeypatch.setattr(ops, "CONV_ENGINE", engine)
     torch.manual_seed(12)
@@ -426,12 +426,12 @@ def test_adam_ema_kernel():
         assert ((ag.cpu() - avg).abs() / avg.abs().clamp(min=1.0)).max().item() < 1e-6
 
 
-@pytest.mark.parametrize("engine,cos_min,l2_max", [("simt", 0.9999, 5e-2), ("tf32x3", 0.999, 0.2)])
+@pytest.mark.parametrize("engine,cos_min,l2_max", [("simt", 0.9999, 5e-2), ("f16x3", 0.999, 0.2)])
 def test_step_a_parity(engine, cos_min, l2_max, monkeypatch):
     """One full Step-A step (B=4, ragged captions / roi counts) against oracle.step_a.
 
     engine "simt": every contraction in exact fp32 FMA arithmetic -- the strict end-to-end check.
-    engine "tf32x3": the tensor-core path (3xTF32, ~5x fp32 rounding per product).  Forward images, losses and
+    engine "f16x3": the tensor-core path (3xFP16, ~5x fp32 rounding per product).  Forward images, losses and
     the optimiser update are held to the same bounds; the end-to-end gradient direction is held to cos > 0.999
     because the G -> D -> BCE chain amplifies rounding by ~1e4 through LeakyReLU / max / BatchNorm sign flips
     (the reference moves its own gradients by ~1e-2 when only its thread count changes; DESIGN.md "Parity budget")."""
