@@ -100,8 +100,8 @@ int og_unpack_upsample_wgrad(const float* dwp, int Co, int Ci, int Cip, int Kp, 
  * with taps = ntaps host quadruples (dh, dw, dn, widx); nsplit = 3 is the error-compensated product (fp32-level
  * accuracy), nsplit = 1 a single fp16 product (xl / wl unused). */
 int og_amax(const float* x, long long n, unsigned* amax, cudaStream_t stream);
-int og_prep_split(const float* x, int N, int H, int W, int C, int pad, int s2d, unsigned* amax, void* xh, void* xl,
-                  cudaStream_t stream);
+int og_prep_split(const float* x, int N, int H, int W, int C, int pad, int s2d, unsigned* amax, int amax_ready,
+                  void* xh, void* xl, cudaStream_t stream);
 int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, int N, int SN, int SH, int SW, int C,
                  const void* wh, const void* wl, const unsigned* amax_w, int ntaps_w, int Kw, float* y, int OH, int OW,
                  int K, long long ysn, long long ysh, long long ysw, int OHf, int OWf, int osy, int osx, int opy,
@@ -120,16 +120,19 @@ int og_conv2d_wgrad_tc(const void* gh, const void* gl, const unsigned* amax_g, i
  * InstanceNorm2d / BatchNorm (train mode) + fused GLU / LeakyReLU / residual
  * -- replaces ref: model.py:19-27 (GLU), 47, 70, 75, 497, 602, 992, 1011 (norm layers).
  * groups = N (instance norm) or 1 (batch norm); P pixels per group; contiguous rows of C channels.
+ * amax_out / amax_dy (optional): receive max|out| / max|dy| as float bits, so that a convolution consuming the
+ * tensor can skip the amax pass of og_prep_split (amax_ready = 1).
  * ---------------------------------------------------------------------------------------------------- */
 int og_norm_stats(const float* x, int groups, long long P, int C, float eps, double* stats, float* mean, float* rstd,
                   float* running_mean, float* running_var, float momentum, int real_c, long long* num_batches_tracked,
                   cudaStream_t stream);
 int og_norm_apply(const float* y, int groups, long long P, int Cy, const float* mean, const float* rstd,
                   const float* gamma, const float* beta, const float* res, int act, float slope, float* out,
-                  cudaStream_t stream);
+                  unsigned* amax_out, cudaStream_t stream);
 int og_norm_backward(const float* y, const float* g, int groups, long long P, int Cy, const float* mean,
                      const float* rstd, const float* gamma, const float* beta, int act, float slope, double* bstats,
-                     float* dy, float* dgamma, float* dbeta, int accumulate_param_grads, cudaStream_t stream);
+                     float* dy, float* dgamma, float* dbeta, int accumulate_param_grads, unsigned* amax_dy,
+                     cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Attention -- replaces ref: GlobalAttention.py:32-70 (func_attention), 73-122 (GlobalAttentionGeneral),

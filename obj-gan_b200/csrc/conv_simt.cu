@@ -441,6 +441,84 @@ __global__ void __launch_bounds__(256) conv_narrow_fwd_kernel(const float* __res
   }
 }
 
+// Long reductions (the logit heads: 16 taps x 768 channels for a few hundred output pixels): one block = 8 output
+// pixels, its 8 warps split the (tap, channel) range, so every weight vector is read once per 8 pixels and the
+// reduction is 256-way parallel; partial sums meet in shared memory.
+__global__ void __launch_bounds__(256) conv_narrow_fwd_long_kernel(const float* __restrict__ x, int N, int H, int W, int C,
+                                                                   const float* __restrict__ w, float* __restrict__ y,
+                                                                   int OH, int OW, int KH, int KW, int stride, int pad,
+                                                                   const float* __restrict__ bias, int act, float slope) {
+  constexpr int PPB = 8;
+  __shared__ float red[8][PPB * 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long npix = (long long)N * OH * OW;
+  const long long pix0 = (long long)blockIdx.x * PPB;
+  int ih0[PPB], iw0[PPB];
+  long long xoff[PPB];
+#pragma unroll
+  for (int p = 0; p < PPB; ++p) {
+    const long long pix = pix0 + p;
+    if (pix < npix) {
+      const int n = (int)(pix / (OH * OW));
+      const int rem = (int)(pix - (long long)n * OH * OW);
+      const int oh = rem / OW, ow = rem - oh * OW;
+      ih0[p] = oh * stride - pad;
+      iw0[p] = ow * stride - pad;
+      xoff[p] = (long long)n * H * W * C;
+    } else {
+      ih0[p] = -(1 << 20);     // never in range
+      iw0[p] = 0;
+      xoff[p] = 0;
+    }
+  }
+  float acc[PPB][8];
+#pragma unroll
+  for (int p = 0; p < PPB; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+  const int C4 = C >> 2, items = KH * KW * C4;
+  for (int i = threadIdx.x; i < items; i += 256) {
+    const int tap = i / C4, c4 = i - tap * C4;
+    const int kh = tap / KW, kw = tap - kh * KW;
+    const float* wp = w + ((long long)tap * C + c4 * 4) * 8;
+    float4 wv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wv[k] = ldg4(wp + k * 4);      // rows c4*4 .. c4*4+3, 8 outputs each
+#pragma unroll
+    for (int p = 0; p < PPB; ++p) {
+      const int ih = ih0[p] + kh, iw = iw0[p] + kw;
+      if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+      const float4 xv = ldg4(x + xoff[p] + ((long long)ih * W + iw) * C + c4 * 4);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[p][0] = fmaf(xs[k], wv[2 * k].x, acc[p][0]); acc[p][1] = fmaf(xs[k], wv[2 * k].y, acc[p][1]);
+        acc[p][2] = fmaf(xs[k], wv[2 * k].z, acc[p][2]); acc[p][3] = fmaf(xs[k], wv[2 * k].w, acc[p][3]);
+        acc[p][4] = fmaf(xs[k], wv[2 * k + 1].x, acc[p][4]); acc[p][5] = fmaf(xs[k], wv[2 * k + 1].y, acc[p][5]);
+        acc[p][6] = fmaf(xs[k], wv[2 * k + 1].z, acc[p][6]); acc[p][7] = fmaf(xs[k], wv[2 * k + 1].w, acc[p][7]);
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < PPB; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = warp_sum(acc[p][j]);
+      if (lane == 0) red[warp][p * 8 + j] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < PPB * 8) {
+    float v = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 8; ++wi) v += red[wi][threadIdx.x];
+    const int p = threadIdx.x >> 3, j = threadIdx.x & 7;
+    if (pix0 + p < npix) {
+      if (bias) v += bias[j];
+      y[(pix0 + p) * 8 + j] = apply_act(v, act, slope);
+    }
+  }
+}
+
 // gx[n,ih,iw,ci] = sum_{kh,kw: (ih+pad-kh) % stride == 0} sum_co g[n,oh,ow,co] * w[(kh,kw,ci)][co]
 __global__ void conv_narrow_dgrad_kernel(const float* __restrict__ g, int N, int H, int W, int C,
                                          const float* __restrict__ w, float* __restrict__ gx, int OH, int OW, int KH,
@@ -475,31 +553,36 @@ __global__ void conv_narrow_dgrad_kernel(const float* __restrict__ g, int N, int
   }
 }
 
-// dw[(kh,kw,ci)][co] = sum_{n,oh,ow} x[n,ih,iw,ci] * g[n,oh,ow,co]
+// dw[(kh,kw,ci)][co] = sum_{n,oh,ow} x[n,ih,iw,ci] * g[n,oh,ow,co]: one thread per weight row and slice of the output
+// pixels (blockIdx.y), slices combined with atomics (dw zero-filled by the launcher)
 __global__ void conv_narrow_wgrad_kernel(const float* __restrict__ x, int N, int H, int W, int C,
                                          const float* __restrict__ g, float* __restrict__ dw, int OH, int OW, int KH,
-                                         int KW, int stride, int pad, int R) {
+                                         int KW, int stride, int pad, int R, int pix_per_slice) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   const int ci = r % C, tap = r / C, kh = tap / KW, kw = tap - kh * KW;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int n = 0; n < N; ++n)
-    for (int oh = 0; oh < OH; ++oh) {
-      const int ih = oh * stride + kh - pad;
-      if (ih < 0 || ih >= H) continue;
-      for (int ow = 0; ow < OW; ++ow) {
-        const int iw = ow * stride + kw - pad;
-        if (iw < 0 || iw >= W) continue;
-        const float xv = __ldg(x + (((long long)n * H + ih) * W + iw) * C + ci);
-        const float* gp = g + (((long long)n * OH + oh) * OW + ow) * 8;
-        const float4 g0 = ldg4(gp), g1 = ldg4(gp + 4);
-        acc[0] = fmaf(xv, g0.x, acc[0]); acc[1] = fmaf(xv, g0.y, acc[1]); acc[2] = fmaf(xv, g0.z, acc[2]);
-        acc[3] = fmaf(xv, g0.w, acc[3]); acc[4] = fmaf(xv, g1.x, acc[4]); acc[5] = fmaf(xv, g1.y, acc[5]);
-        acc[6] = fmaf(xv, g1.z, acc[6]); acc[7] = fmaf(xv, g1.w, acc[7]);
-      }
+  const int npix = N * OH * OW;
+  const int p0 = blockIdx.y * pix_per_slice, p1 = min(npix, p0 + pix_per_slice);
+  int n = p0 / (OH * OW), rem = p0 - n * OH * OW;
+  int oh = rem / OW, ow = rem - oh * OW;
+  for (int p = p0; p < p1; ++p) {
+    const int ih = oh * stride + kh - pad, iw = ow * stride + kw - pad;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      const float xv = __ldg(x + (((long long)n * H + ih) * W + iw) * C + ci);
+      const float* gp = g + (long long)p * 8;
+      const float4 g0 = ldg4(gp), g1 = ldg4(gp + 4);
+      acc[0] = fmaf(xv, g0.x, acc[0]); acc[1] = fmaf(xv, g0.y, acc[1]); acc[2] = fmaf(xv, g0.z, acc[2]);
+      acc[3] = fmaf(xv, g0.w, acc[3]); acc[4] = fmaf(xv, g1.x, acc[4]); acc[5] = fmaf(xv, g1.y, acc[5]);
+      acc[6] = fmaf(xv, g1.z, acc[6]); acc[7] = fmaf(xv, g1.w, acc[7]);
     }
-  st4(dw + (long long)r * 8, make_float4(acc[0], acc[1], acc[2], acc[3]));
-  st4(dw + (long long)r * 8 + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    if (++ow == OW) {
+      ow = 0;
+      if (++oh == OH) { oh = 0; ++n; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(dw + (long long)r * 8 + j, acc[j]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -617,8 +700,12 @@ OG_API int og_conv2d_narrow_fwd(const float* x, int N, int H, int W, int C, cons
   if (C % 4) return (int)cudaErrorInvalidValue;
   long long pix = (long long)N * OH * OW;
   if (pix == 0) return 0;
-  conv_narrow_fwd_kernel<<<og_cdiv(pix, 8), 256, 0, stream>>>(x, N, H, W, C, wpacked, y, OH, OW, KH, KW, stride, pad,
-                                                              bias, act, slope);
+  if ((long long)KH * KW * (C / 4) >= 512)     // long reduction: split it over the block
+    conv_narrow_fwd_long_kernel<<<og_cdiv(pix, 8), 256, 0, stream>>>(x, N, H, W, C, wpacked, y, OH, OW, KH, KW, stride,
+                                                                     pad, bias, act, slope);
+  else
+    conv_narrow_fwd_kernel<<<og_cdiv(pix, 8), 256, 0, stream>>>(x, N, H, W, C, wpacked, y, OH, OW, KH, KW, stride, pad,
+                                                                bias, act, slope);
   OG_RETURN_LAST_ERROR();
 }
 OG_API int og_conv2d_narrow_dgrad(const float* g, int N, int H, int W, int C, const float* wpacked, float* gx, int OH,
@@ -632,8 +719,19 @@ OG_API int og_conv2d_narrow_dgrad(const float* g, int N, int H, int W, int C, co
 }
 OG_API int og_conv2d_narrow_wgrad(const float* x, int N, int H, int W, int C, const float* g, float* dw_packed, int OH,
                                   int OW, int KH, int KW, int stride, int pad, cudaStream_t stream) {
-  int R = KH * KW * C;
-  conv_narrow_wgrad_kernel<<<og_cdiv(R, 128), 128, 0, stream>>>(x, N, H, W, C, g, dw_packed, OH, OW, KH, KW, stride, pad, R);
+  const int R = KH * KW * C;
+  const long long npix = (long long)N * OH * OW;
+  OG_CHECK(cudaMemsetAsync(dw_packed, 0, sizeof(float) * (size_t)R * 8, stream));
+  if (npix == 0) return 0;
+  // ~4 waves of 128-thread blocks over the GPU, at least 16 pixels per slice
+  const int rb = og_cdiv(R, 128);
+  long long slices = (148LL * 16 + rb - 1) / rb;
+  if (slices > npix / 16) slices = npix / 16;
+  if (slices < 1) slices = 1;
+  if (slices > 65535) slices = 65535;
+  const int pps = og_cdiv(npix, slices);
+  dim3 grid(rb, og_cdiv(npix, pps));
+  conv_narrow_wgrad_kernel<<<grid, 128, 0, stream>>>(x, N, H, W, C, g, dw_packed, OH, OW, KH, KW, stride, pad, R, pps);
   OG_RETURN_LAST_ERROR();
 }
 

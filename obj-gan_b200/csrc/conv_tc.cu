@@ -1139,8 +1139,10 @@ OG_API int og_conv2d_wgrad_tc(const void* gh, const void* gl, const unsigned* am
   const int BNsel = Cr <= 32 ? 32 : Cr <= 64 ? 64 : Cr <= 112 ? 112 : Cr <= 208 ? 208 : 256;
   const int citiles = og_cdiv(C, BNsel);
   p.cotiles = cotiles;
-  // pixel splits: ~2 waves of CTAs over 148 SMs, at least 8 chunks per CTA
-  int splits = og_cdiv(296, cotiles * citiles * nentries);
+  // pixel splits: the CTAs are equal-sized and run one per SM, so fill at most two full waves of 148 (one CTA more
+  // would cost a whole extra round); at least 8 chunks per CTA
+  int splits = 296 / (cotiles * citiles * nentries);
+  if (splits < 1) splits = 1;
   int maxs = p.total_chunks / 8;
   if (maxs < 1) maxs = 1;
   if (splits > maxs) splits = maxs;
@@ -1173,7 +1175,7 @@ OG_API int og_conv2d_wgrad_tc(const void* gh, const void* gl, const unsigned* am
   if (!no_tc2 && cotiles >= 2 && (BNsel == 208 || BNsel == 256)) {
     // two co-tiles per CTA share every X stage (L2 -> SM traffic is the bound of this kernel)
     const int copairs = (cotiles + 1) / 2;
-    int sp = og_cdiv(296, copairs * citiles * nentries);
+    int sp = 296 / (copairs * citiles * nentries);
     if (sp > maxs) sp = maxs;
     if (sp < 1) sp = 1;
     p.chunks_per_cta = og_cdiv(p.total_chunks, sp);
@@ -1258,17 +1260,20 @@ __global__ void __launch_bounds__(256) prep_split_kernel(const float* __restrict
 }
 
 // fp16 hi/lo operand copies of an NHWC fp32 tensor, scaled by the power of two that og_scale_exp derives from
-// max|x| (written to *amax as float bits).  pad = 0: plain; pad = 1: nn.ReflectionPad2d(1) halo (model.py:67)
+// max|x| (*amax as float bits: computed here, or, with amax_ready, left there by the kernel that produced x --
+// any upper bound of max|x| is valid, it only positions the 22-bit window).  pad = 0: plain; pad = 1: nn.ReflectionPad2d(1) halo (model.py:67)
 // materialised while splitting; s2d = 1: four space-to-depth phase blocks.  xl may be null (single-product mode).
-OG_API int og_prep_split(const float* x, int N, int H, int W, int C, int pad, int s2d, unsigned* amax, void* xh,
-                         void* xl, cudaStream_t stream) {
+OG_API int og_prep_split(const float* x, int N, int H, int W, int C, int pad, int s2d, unsigned* amax, int amax_ready,
+                         void* xh, void* xl, cudaStream_t stream) {
   if (C % 8 || pad < 0 || pad > 1 || (s2d && (pad || (H & 1) || (W & 1)))) return (int)cudaErrorInvalidValue;
-  OG_CHECK(cudaMemsetAsync(amax, 0, sizeof(unsigned), stream));
   const long long n4 = (long long)N * H * W * C / 4;
+  if (!amax_ready) OG_CHECK(cudaMemsetAsync(amax, 0, sizeof(unsigned), stream));
   if (n4 == 0) return 0;
-  long long ab = (n4 + 255) / 256;
-  if (ab > 148LL * 8) ab = 148LL * 8;
-  amax_kernel<<<(int)ab, 256, 0, stream>>>(x, n4, 0, amax);
+  if (!amax_ready) {      // the producer of x did not leave max|x| behind: one extra read pass
+    long long ab = (n4 + 255) / 256;
+    if (ab > 148LL * 8) ab = 148LL * 8;
+    amax_kernel<<<(int)ab, 256, 0, stream>>>(x, n4, 0, amax);
+  }
   long long total = s2d ? (long long)N * H * W * (C / 8) : (long long)N * (H + 2 * pad) * (W + 2 * pad) * (C / 8);
   long long b = (total + 255) / 256;
   if (b > 148LL * 32) b = 148LL * 32;

@@ -75,6 +75,24 @@ __global__ void norm_finalize_kernel(const double* __restrict__ stats, int group
 
 // forward apply.  y: conv output [G*P][Cy];  out: [G*P][Co] where Co = Cy (none / lrelu) or Cy/2 (GLU).
 // gamma/beta (BatchNorm affine) may be null (InstanceNorm).  res (same shape as out) is added when non-null.
+// max|.| of the values a 256-thread block has written, merged into *amax (float bits; non-negative floats order like
+// unsigned integers).  The consumer convolution scales its fp16 operand copies by it (og_prep_split).
+__device__ __forceinline__ float amax4(float m, const float4& o) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+}
+__device__ __forceinline__ void block_amax_256(float m, unsigned* amax) {
+  __shared__ float sm_amax[8];
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) sm_amax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    m = sm_amax[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+    if (threadIdx.x == 0) atomicMax(amax, __float_as_uint(m));
+  }
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict__ y, int Cy, long long P,
                                                          long long total_pix, const float* __restrict__ mean,
@@ -82,10 +100,11 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta,
                                                          const float* __restrict__ res, float slope,
-                                                         float* __restrict__ out) {
+                                                         float* __restrict__ out, unsigned* __restrict__ amax) {
   const int Co = (ACT == OG_NA_GLU) ? Cy / 2 : Cy;
   const int Co4 = Co >> 2;
   const long long total = total_pix * Co4;
+  float mx = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long p = i / Co4;
@@ -125,7 +144,9 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
       o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
     }
     st4(out + p * Co + c, o);
+    mx = amax4(mx, o);
   }
+  if (amax) block_amax_256(mx, amax);
 }
 
 // gradient of the fused activation w.r.t. the normalised (+affine) values n, for 4 channels.
@@ -228,10 +249,11 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __rest
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float slope,
                                                              const double* __restrict__ bstats, double inv_count,
-                                                             float* __restrict__ dy) {
+                                                             float* __restrict__ dy, unsigned* __restrict__ amax) {
   const int Co = (ACT == OG_NA_GLU) ? Cy / 2 : Cy;
   const int Co4 = Co >> 2;
   const long long total = total_pix * Co4;
+  float mx = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long p = i / Co4;
@@ -251,6 +273,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __rest
       o.z = r.z * ga.z * (dn.z - (float)(bs[4] * inv_count) - xh.z * (float)(bs[5] * inv_count));
       o.w = r.w * ga.w * (dn.w - (float)(bs[6] * inv_count) - xh.w * (float)(bs[7] * inv_count));
       st4(dy + p * Cy + c, o);
+      mx = amax4(mx, o);
     }
     if (ACT == OG_NA_GLU) {
       const double* bs = bstats + (grp * Cy + Co + c) * 2;
@@ -262,8 +285,10 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __rest
       o.z = r.z * ga.z * (dn2.z - (float)(bs[4] * inv_count) - xh2.z * (float)(bs[5] * inv_count));
       o.w = r.w * ga.w * (dn2.w - (float)(bs[6] * inv_count) - xh2.w * (float)(bs[7] * inv_count));
       st4(dy + p * Cy + Co + c, o);
+      mx = amax4(mx, o);
     }
   }
+  if (amax) block_amax_256(mx, amax);
 }
 
 // dgamma = S2, dbeta = S1 for batch norm (groups == 1): copy fp64 sums to fp32 parameter-gradient vectors
@@ -308,17 +333,18 @@ OG_API int og_norm_stats(const float* x, int groups, long long P, int C, float e
 
 OG_API int og_norm_apply(const float* y, int groups, long long P, int Cy, const float* mean, const float* rstd,
                          const float* gamma, const float* beta, const float* res, int act, float slope, float* out,
-                         cudaStream_t stream) {
+                         unsigned* amax_out, cudaStream_t stream) {
   long long tp = (long long)groups * P;
   int Co = act == OG_NA_GLU ? Cy / 2 : Cy;
   if (Cy % 4 || Co % 4) return (int)cudaErrorInvalidValue;
+  if (amax_out) OG_CHECK(cudaMemsetAsync(amax_out, 0, sizeof(unsigned), stream));
   int blocks = elem_blocks(tp * (Co / 4));
   if (act == OG_NA_GLU)
-    norm_apply_kernel<OG_NA_GLU><<<blocks, 256, 0, stream>>>(y, Cy, P, tp, mean, rstd, gamma, beta, res, slope, out);
+    norm_apply_kernel<OG_NA_GLU><<<blocks, 256, 0, stream>>>(y, Cy, P, tp, mean, rstd, gamma, beta, res, slope, out, amax_out);
   else if (act == OG_NA_LRELU)
-    norm_apply_kernel<OG_NA_LRELU><<<blocks, 256, 0, stream>>>(y, Cy, P, tp, mean, rstd, gamma, beta, res, slope, out);
+    norm_apply_kernel<OG_NA_LRELU><<<blocks, 256, 0, stream>>>(y, Cy, P, tp, mean, rstd, gamma, beta, res, slope, out, amax_out);
   else
-    norm_apply_kernel<OG_NA_NONE><<<blocks, 256, 0, stream>>>(y, Cy, P, tp, mean, rstd, gamma, beta, res, slope, out);
+    norm_apply_kernel<OG_NA_NONE><<<blocks, 256, 0, stream>>>(y, Cy, P, tp, mean, rstd, gamma, beta, res, slope, out, amax_out);
   OG_RETURN_LAST_ERROR();
 }
 
@@ -327,11 +353,12 @@ OG_API int og_norm_apply(const float* y, int groups, long long P, int Cy, const 
 OG_API int og_norm_backward(const float* y, const float* g, int groups, long long P, int Cy, const float* mean,
                             const float* rstd, const float* gamma, const float* beta, int act, float slope,
                             double* bstats, float* dy, float* dgamma, float* dbeta, int accumulate_param_grads,
-                            cudaStream_t stream) {
+                            unsigned* amax_dy, cudaStream_t stream) {
   long long tp = (long long)groups * P;
   int Co = act == OG_NA_GLU ? Cy / 2 : Cy;
   if (Cy % 4 || Co % 4) return (int)cudaErrorInvalidValue;
   OG_CHECK(cudaMemsetAsync(bstats, 0, sizeof(double) * 2 * groups * Cy, stream));
+  if (amax_dy) OG_CHECK(cudaMemsetAsync(amax_dy, 0, sizeof(unsigned), stream));
   int cg = og_cdiv(Co / 4, 32);
   int ppb = pix_chunk(P, cg, groups);
   dim3 grid(cg, og_cdiv(P, ppb), groups), block(32, 8);
@@ -339,7 +366,7 @@ OG_API int og_norm_backward(const float* y, const float* g, int groups, long lon
   double inv = 1.0 / (double)P;
 #define OG_LAUNCH_BWD(A)                                                                                           \
   norm_bwd_reduce_kernel<A><<<grid, block, 0, stream>>>(y, g, Cy, P, ppb, mean, rstd, gamma, beta, slope, bstats); \
-  norm_bwd_apply_kernel<A><<<blocks, 256, 0, stream>>>(y, g, Cy, P, tp, mean, rstd, gamma, beta, slope, bstats, inv, dy);
+  norm_bwd_apply_kernel<A><<<blocks, 256, 0, stream>>>(y, g, Cy, P, tp, mean, rstd, gamma, beta, slope, bstats, inv, dy, amax_dy);
   if (act == OG_NA_GLU) {
     OG_LAUNCH_BWD(OG_NA_GLU)
   } else if (act == OG_NA_LRELU) {

@@ -121,6 +121,7 @@ class PackedWeights:
 import os as _os
 CONV_ENGINE = _os.environ.get("OBJGAN_CONV", "f16x3")
 TC_WGRAD = _os.environ.get("OBJGAN_TC_WGRAD", "1") == "1"
+FUSED_AMAX = _os.environ.get("OBJGAN_FUSED_AMAX", "1") == "1"   # producers leave max|x| for the consuming conv
 KEEP_SPLIT = _os.environ.get("OBJGAN_KEEP_SPLIT", "1") == "1"   # keep x's hi/lo copies from forward for the wgrad
 TC_MIN_PIXELS = 256        # smaller problems go to the exact-fp32 SIMT kernels (the tc kernel splits K on small maps)
 
@@ -151,9 +152,27 @@ def _split(x, pad=0, s2d=False):
     shape = (4 * n, h // 2, w // 2, c) if s2d else (n, h + 2 * pad, w + 2 * pad, c)
     xh = _empty_slack(shape, x.device)
     xl = _empty_slack(shape, x.device) if CONV_ENGINE == "f16x3" else None
-    amax = torch.empty(1, device=x.device, dtype=torch.int32)
-    _call("og_prep_split", _p(x), n, h, w, c, pad, 1 if s2d else 0, _p(amax), _p(xh), _p(xl))
+    amax = _known_amax(x)
+    ready = amax is not None
+    if not ready:
+        amax = torch.empty(1, device=x.device, dtype=torch.int32)
+    _call("og_prep_split", _p(x), n, h, w, c, pad, 1 if s2d else 0, _p(amax), 1 if ready else 0, _p(xh), _p(xl))
     return xh, xl, amax
+
+
+def _tag_amax(t):
+    """Attach a fresh max|t| word to a tensor some kernel is about to produce (the kernel fills it); a consuming
+    convolution then skips its own amax pass.  The tag is void once the tensor is modified in place."""
+    word = torch.empty(1, device=t.device, dtype=torch.int32)
+    t.og_amax = (word, t._version)
+    return word
+
+
+def _known_amax(t):
+    tag = getattr(t, "og_amax", None)
+    if tag is not None and tag[1] == t._version and FUSED_AMAX:
+        return tag[0]
+    return None
 
 
 def _tc_launch(xs, n, ws, ntaps_w, kw_rows, y, oh, ow, k, osy, op, taps, bias=None, act=ACT_NONE, layout=0):
@@ -491,7 +510,7 @@ class _NormAct(torch.autograd.Function):
             res = res.contiguous()
             assert res.shape == out.shape
         _call("og_norm_apply", _p(y), groups, P, cy, _p(mean), _p(rstd), _p(gamma), _p(beta), _p(res), act,
-              LRELU_SLOPE, _p(out))
+              LRELU_SLOPE, _p(out), _p(_tag_amax(out)))
         ctx.cfg = (groups, P, cy, act, res is not None)
         ctx.save_for_backward(y, mean, rstd, gamma, beta)
         return out
@@ -508,7 +527,7 @@ class _NormAct(torch.autograd.Function):
             dgamma = torch.empty_like(gamma)
             dbeta = torch.empty_like(beta)
         _call("og_norm_backward", _p(y), _p(g), groups, P, cy, _p(mean), _p(rstd), _p(gamma), _p(beta), act,
-              LRELU_SLOPE, _p(bstats), _p(dy), _p(dgamma), _p(dbeta), 0)
+              LRELU_SLOPE, _p(bstats), _p(dy), _p(dgamma), _p(dbeta), 0, _p(_tag_amax(dy)))
         return dy, dgamma, dbeta, (g if has_res else None), None, None, None
 
 
