@@ -211,7 +211,7 @@ def _tc_kind(n, h, w, c, kh, kw, stride, pad, mode):
         if mode == UPSAMPLE2X and n % _tile_n(h, w) != 0:
             return None
         return "s1"
-    if kh == 4 and kw == 4 and stride == 2 and pad == 1 and mode == PAD_ZERO and h % 2 == 0 and w % 2 == 0:
+    if kh == kw and kh in (3, 4) and stride == 2 and pad == 1 and mode == PAD_ZERO and h % 2 == 0 and w % 2 == 0:
         if n * (h // 2) * (w // 2) < TC_MIN_PIXELS or n % _tile_n(h // 2, w // 2) != 0:
             return None
         return "s2"
@@ -227,16 +227,17 @@ def _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act):
     dev = x.device
     if mode != UPSAMPLE2X:
         ws = cache.get_hilo(weight, c, kp, split, splitp, 1)      # [tap][co][ci]
-    if kind == "s2":                                                   # 4x4 stride 2 pad 1 on space-to-depth phases
+    if kind == "s2":                                 # 4x4 / 3x3 stride 2 pad 1 on space-to-depth phases
+        k = weight.shape[2]
         xs = _split(x, s2d=True)
         y = torch.empty((n, h // 2, w // 2, kp), device=dev, dtype=torch.float32)
         taps = []
-        for kh in range(4):
+        for kh in range(k):
             dh, a = divmod(kh - 1, 2)
-            for kw in range(4):
+            for kw in range(k):
                 dw, b = divmod(kw - 1, 2)
-                taps.append((dh, dw, (a * 2 + b) * n, kh * 4 + kw))
-        _tc_launch(xs, n, ws, 16, kp, y, h // 2, w // 2, kp, 1, (0, 0), taps, bias_p, act)
+                taps.append((dh, dw, (a * 2 + b) * n, kh * k + kw))
+        _tc_launch(xs, n, ws, k * k, kp, y, h // 2, w // 2, kp, 1, (0, 0), taps, bias_p, act)
         return y, xs
     if mode == PAD_REFLECT:
         xs = _split(x, 1)
@@ -278,12 +279,13 @@ def _tc_dgrad(kind, gs, n, cache, weight, c, kp, split, splitp, mode, h, w, oh, 
     if mode != UPSAMPLE2X:
         ws = cache.get_hilo(weight, c, kp, split, splitp, 0)      # [tap][ci][co]
     if kind == "s2":
+        k = weight.shape[2]
         gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
-        for a in range(2):
+        for a in range(2):                       # input pixel (2i + a, 2j + b) <- kernel rows with kh = a + 1 (mod 2)
             for b in range(2):
-                taps = [((a + 1 - kh) // 2, (b + 1 - kw) // 2, 0, kh * 4 + kw)
-                        for kh in ((1, 3) if a == 0 else (0, 2)) for kw in ((1, 3) if b == 0 else (0, 2))]
-                _tc_launch(gs, n, ws, 16, c, gx, oh, ow, c, 2, (a, b), taps)
+                taps = [((a + 1 - kh) // 2, (b + 1 - kw) // 2, 0, kh * k + kw)
+                        for kh in range(k) if (a + 1 - kh) % 2 == 0 for kw in range(k) if (b + 1 - kw) % 2 == 0]
+                _tc_launch(gs, n, ws, k * k, c, gx, oh, ow, c, 2, (a, b), taps)
         return gx
     if mode == PAD_REFLECT:
         gpad = torch.empty((n, h + 2, w + 2, c), device=dev, dtype=torch.float32)
@@ -328,12 +330,12 @@ def _tc_wgrad(kind, xs, gs, n, h, w, oh, ow, weight, c, kp, split, splitp, mode)
     co, ci, kh_, kw_ = weight.shape
     if kind == "s2":
         ent = []
-        for kh in range(4):
+        for kh in range(kh_):
             dh, a = divmod(kh - 1, 2)
-            for kw in range(4):
+            for kw in range(kw_):
                 dw, b = divmod(kw - 1, 2)
-                ent.append((0, dh, dw, (a * 2 + b) * n, kh * 4 + kw))
-        nt = 16
+                ent.append((0, dh, dw, (a * 2 + b) * n, kh * kw_ + kw))
+        nt = kh_ * kw_
     elif mode == UPSAMPLE2X:
         ent = [((p_ * 2 + q_) * n, _UP_OFF[p_][a], _UP_OFF[q_][b], 0, ((p_ * 2 + q_) * 2 + a) * 2 + b)
                for p_ in range(2) for q_ in range(2) for a in range(2) for b in range(2)]

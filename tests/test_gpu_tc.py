@@ -30,11 +30,12 @@ CASES = [
     (80, 24, PAD_REFLECT, 0, 2, 64, 64),         # G_HMAP conv3x3
     (768, 1536, "s2", 0, 32, 8, 8),              # 4x4 outputs: wgrad pixel patch spans 2 images
     (40, 24, PAD_REFLECT, 0, 4, 16, 16),         # reflection halo on a 16-wide map (wgrad patch = 16 x 2)
+    (24, 48, "s2k3", 0, 4, 64, 64),              # conv3x3 stride 2 (heat-map encoder) through the same phase blocks
 ]
 
 
 def _ref(x, w, mode):
-    if mode == "s2":
+    if mode in ("s2", "s2k3"):
         return F.conv2d(x, w, None, 2, 1)
     if mode == PAD_REFLECT:
         return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w)
@@ -55,8 +56,8 @@ def test_tc_conv_fwd_dgrad(case, engine, tol, monkeypatch):
     cin, cout, mode, split, N, H, W = case
     monkeypatch.setattr(ops, "CONV_ENGINE", engine)
     torch.manual_seed(cin + cout + H)
-    if mode == "s2":
-        m = model.Conv2dP(cin, cout, 4, 2, 1).to(DEV)
+    if mode in ("s2", "s2k3"):
+        m = model.Conv2dP(cin, cout, 4 if mode == "s2" else 3, 2, 1).to(DEV)
     else:
         m = model.Conv2dP(cin, cout, 3, 1, 1, mode=mode, split=split).to(DEV)
     x = torch.randn(N, cin, H, W)
@@ -67,8 +68,8 @@ def test_tc_conv_fwd_dgrad(case, engine, tol, monkeypatch):
     gy = torch.randn_like(yr)
     gxr, gwr = torch.autograd.grad(yr, (xr, wr), gy)
     xg = x.to(DEV).requires_grad_(True)
-    k, st = (4, 2) if mode == "s2" else (3, 1)
-    assert ops._tc_kind(N, H, W, ops.cpad(cin), k, k, st, 1, PAD_ZERO if mode == "s2" else mode)
+    k, st = (4, 2) if mode == "s2" else (3, 2) if mode == "s2k3" else (3, 1)
+    assert ops._tc_kind(N, H, W, ops.cpad(cin), k, k, st, 1, PAD_ZERO if st == 2 else mode)
     y_nhwc = m(ops.to_nhwc(xg))
     if split:
         sp = ops.cpad(split)
