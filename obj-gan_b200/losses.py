@@ -36,18 +36,29 @@ def patD_loss(netPatD, real_imgs, fake_imgs, conditions):
     return ops.bce(cond_real, 1.0, tl) + ops.bce(cond_fake, 0.0, tl / 2.0) + ops.bce(cond_wrong, 0.0, tl / 2.0)
 
 
-def G_loss_pat(netsPatD, fake_imgs, sent_emb):
-    """Patch-discriminator terms of ``G_loss`` (ref: miscc/losses.py:372-399)."""
+def G_loss_pat(netsPatD, fake_imgs, sent_emb, streams=None):
+    """Patch-discriminator terms of ``G_loss`` (ref: miscc/losses.py:372-399).  ``streams``: optional CUDA streams, one
+    per discriminator: the three branches are independent until their losses are summed, so they may run
+    concurrently (autograd replays each branch's backward on the stream of its forward)."""
+    import contextlib
     ul, tl = cfg.TRAIN.SMOOTH.UNCOND_LAMBDA, cfg.TRAIN.SMOOTH.TXT_LAMBDA
-    total, per = None, []
+    per = []
+    main = torch.cuda.current_stream() if streams else None
     for i in range(len(netsPatD)):
-        features = netsPatD[i](fake_imgs[i])
-        cond, uncond = _heads(netsPatD[i])
-        cond_err = ops.bce(cond(features, sent_emb), 1.0, tl if uncond is not None else 1.0)
-        loss = cond_err
-        if uncond is not None:
-            loss = loss + ops.bce(uncond(features), 1.0, ul)
-        per.append(loss)
+        if streams:
+            streams[i].wait_stream(main)
+        with (torch.cuda.stream(streams[i]) if streams else contextlib.nullcontext()):
+            features = netsPatD[i](fake_imgs[i])
+            cond, uncond = _heads(netsPatD[i])
+            cond_err = ops.bce(cond(features, sent_emb), 1.0, tl if uncond is not None else 1.0)
+            loss = cond_err
+            if uncond is not None:
+                loss = loss + ops.bce(uncond(features), 1.0, ul)
+            per.append(loss)
+    total = None
+    for i, loss in enumerate(per):
+        if streams:
+            main.wait_stream(streams[i])
         total = loss if total is None else total + loss
     return total, per
 

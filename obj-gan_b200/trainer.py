@@ -12,9 +12,13 @@ What is different from the reference by design (B200-first, results identical):
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 import torch.distributed as dist
 
+from . import lib as _lib
 from . import losses, model, ops
 from .config import cfg
 
@@ -111,6 +115,14 @@ class StepATrainer:
                     dist.broadcast(buf, src=0, group=self.pg)
             ops.bump_param_epoch()
 
+    def _branch_streams(self):
+        """Side streams for the three independent discriminator branches (None: run them in sequence)."""
+        if os.environ.get("OBJGAN_D_STREAMS", "1") != "1" or not torch.cuda.is_available() or _lib.DRY_RUN:
+            return None
+        if not hasattr(self, "_dstreams"):
+            self._dstreams = [torch.cuda.Stream() for _ in self.netsPatD]
+        return self._dstreams
+
     def _allreduce(self, bucket):
         if self.world > 1:
             return dist.all_reduce(bucket.grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
@@ -205,13 +217,25 @@ class StepATrainer:
         out = {}
         # (3-1) update the patch discriminators
         works = []
-        for i, (d, b) in enumerate(zip(self.netsPatD, self.bD)):
+        streams = self._branch_streams()
+        main = torch.cuda.current_stream() if streams else None
+        for b in self.bD:
             b.requires_grad_(True)
             b.zero_grad()
-            err = losses.patD_loss(d, inp["imgs"][i], fake_imgs[i], sent)
-            err.backward()
+        for i, (d, b) in enumerate(zip(self.netsPatD, self.bD)):
+            # the three discriminator updates are independent: each runs on its own stream (forked from and joined to
+            # the step's stream, so a CUDA-graph capture records them as parallel branches) and their many small
+            # kernels fill the GPU together
+            if streams:
+                streams[i].wait_stream(main)
+            with (torch.cuda.stream(streams[i]) if streams else contextlib.nullcontext()):
+                err = losses.patD_loss(d, inp["imgs"][i], fake_imgs[i], sent)
+                err.backward()
+                out[f"errPatD{i}"] = err.detach()
+        for i, b in enumerate(self.bD):
+            if streams:
+                main.wait_stream(streams[i])
             works.append(self._allreduce(b))
-            out[f"errPatD{i}"] = err.detach()
         for w, b in zip(works, self.bD):
             if w is not None:
                 w.wait()
@@ -220,7 +244,7 @@ class StepATrainer:
         for b in self.bD:
             b.requires_grad_(False)
         self.bG.zero_grad()
-        err_g, _ = losses.G_loss_pat(self.netsPatD, fake_imgs, sent)
+        err_g, _ = losses.G_loss_pat(self.netsPatD, fake_imgs, sent, streams)
         kl = losses.KL_loss(mu, logvar)
         total = err_g + kl
         total.backward()
