@@ -179,7 +179,7 @@ def attn_roofline(hbm, src):
     ms = sum(times) / len(times)
     byts = 4.0 * Q * (2 * C + L) * B
     ach = byts / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "att_general_fwd_kernel (Q=16384, L=18, C=48, B=16)", "achieved": round(ach, 1),
+    return {"bound": "hbm", "kernel": "att_general_fwd_kernel<20,2> (Q=16384, L=18, C=48, B=16)", "achieved": round(ach, 1),
             "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None, "ms_per_launch": round(ms, 4),
             "peak_source": f"{src} copy bandwidth"}
 

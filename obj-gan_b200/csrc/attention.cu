@@ -86,57 +86,74 @@ OG_API int og_words_proj_bwd(const float* words, const float* W, const float* gs
 // mask: [B][L] bytes (1 = padding word) or null.  wc: [B][Q][cs] (pad lanes zeroed), attn: [B][L][Q].
 // Mask quirk (ref: GlobalAttention.py:108): row (b, q) uses the caption mask of sample (b*Q + q) mod B.
 // ---------------------------------------------------------------------------------------------
-template <int LM>
-__global__ void __launch_bounds__(ATT_Q, 7) att_general_fwd_kernel(const float* __restrict__ h,
-                                                                const float* __restrict__ src,
-                                                                const unsigned char* __restrict__ mask, int B, int Q,
-                                                                int idf, int cs, int L, float* __restrict__ wc,
-                                                                float* __restrict__ attn) {
+// QPT queries per thread (rows t, t + ATT_Q, ... of the block's tile): every 128-bit broadcast load of a word-projection
+// row feeds QPT queries.  With one query per thread the kernel is bound by the shared-memory return path (each
+// LDS.128 writes 512 bytes of registers per warp: 5 of them per 10 FFMA2), not by HBM; QPT = 2 halves that.
+template <int LM, int QPT>
+__global__ void __launch_bounds__(ATT_Q, (QPT == 1 ? 7 : 4))
+att_general_fwd_kernel(const float* __restrict__ h, const float* __restrict__ src,
+                       const unsigned char* __restrict__ mask, int B, int Q, int idf, int cs, int L,
+                       float* __restrict__ wc, float* __restrict__ attn) {
   // The word projections src[c][0..L) live in shared memory as rows of LM floats (zero padded) and are read with
-  // 128-bit broadcast loads: one LDS.128 feeds four FMAs, otherwise the kernel is LSU-issue bound, not HBM bound.
+  // 128-bit broadcast loads: one LDS.128 feeds four FMAs per query.
   extern __shared__ __align__(16) float smem[];
+  constexpr int TQ = ATT_Q * QPT;        // queries per block
   const int pitch = cs + 1;
   float* ssrc = smem;                    // [idf][LM]
-  float* tile = smem + idf * LM;         // [ATT_Q][pitch]
-  const int b = blockIdx.y, q0 = blockIdx.x * ATT_Q, t = threadIdx.x;
-  const int nq = min(ATT_Q, Q - q0);
+  float* tile = smem + idf * LM;         // [TQ][pitch]
+  const int b = blockIdx.y, q0 = blockIdx.x * TQ, t = threadIdx.x;
+  const int nq = min(TQ, Q - q0);
   for (int i = t; i < idf * LM; i += ATT_Q) {
     int c = i / LM, l = i - c * LM;
     ssrc[i] = l < L ? src[((long long)b * idf + c) * L + l] : 0.f;
   }
   const float* hb = h + ((long long)b * Q + q0) * cs;
-  for (int i = t; i < nq * cs / 4; i += ATT_Q) {
+  const int cs4 = cs >> 2;
+  for (int r = t / cs4, c4 = t - (t / cs4) * cs4, i = t; i < nq * cs4; i += ATT_Q) {
     float4 v = ldg4(hb + i * 4);
-    int r = (i * 4) / cs, c = (i * 4) - r * cs;
-    float* d = tile + r * pitch + c;
+    float* d = tile + r * pitch + c4 * 4;
     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    c4 += ATT_Q % cs4;                   // advance (r, c4) by ATT_Q elements without a division
+    r += ATT_Q / cs4;
+    if (c4 >= cs4) { c4 -= cs4; ++r; }
   }
   __syncthreads();
-  if (t < nq) {
-    float s[LM];
-    float2 s2[LM / 2];
+  float2 s2[QPT][LM / 2];
 #pragma unroll
-    for (int l = 0; l < LM / 2; ++l) s2[l] = make_float2(0.f, 0.f);
-    float* row = tile + t * pitch;
-    for (int c = 0; c < idf; ++c) {
-      const float hv = row[c];
-      const float2 hv2 = make_float2(hv, hv);
-      const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
+  for (int u = 0; u < QPT; ++u)
 #pragma unroll
-      for (int l4 = 0; l4 < LM / 4; ++l4) {
-        const float4 w = sr[l4];
-        s2[2 * l4] = ffma2(hv2, make_float2(w.x, w.y), s2[2 * l4]);
-        s2[2 * l4 + 1] = ffma2(hv2, make_float2(w.z, w.w), s2[2 * l4 + 1]);
+    for (int l = 0; l < LM / 2; ++l) s2[u][l] = make_float2(0.f, 0.f);
+  // rows past nq hold stale shared memory: they are computed but never stored
+  for (int c = 0; c < idf; ++c) {
+    float2 hv2[QPT];
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+      const float hv = tile[(t + u * ATT_Q) * pitch + c];
+      hv2[u] = make_float2(hv, hv);
+    }
+    const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
+#pragma unroll
+    for (int l4 = 0; l4 < LM / 4; ++l4) {
+      const float4 w = sr[l4];
+#pragma unroll
+      for (int u = 0; u < QPT; ++u) {
+        s2[u][2 * l4] = ffma2(hv2[u], make_float2(w.x, w.y), s2[u][2 * l4]);
+        s2[u][2 * l4 + 1] = ffma2(hv2[u], make_float2(w.z, w.w), s2[u][2 * l4 + 1]);
       }
     }
+  }
+#pragma unroll
+  for (int u = 0; u < QPT; ++u) {
+    const int q = q0 + t + u * ATT_Q;
+    const bool live = t + u * ATT_Q < nq;
+    float s[LM];
 #pragma unroll
     for (int l = 0; l < LM / 2; ++l) {
-      s[2 * l] = s2[l].x;
-      s[2 * l + 1] = s2[l].y;
+      s[2 * l] = s2[u][l].x;
+      s[2 * l + 1] = s2[u][l].y;
     }
-    const int q = q0 + t;
     float mx = -INFINITY;
-    if (mask) {
+    if (mask && live) {
       const unsigned char* mr = mask + (((long long)b * Q + q) % B) * L;
 #pragma unroll
       for (int l = 0; l < LM; ++l)
@@ -155,32 +172,43 @@ __global__ void __launch_bounds__(ATT_Q, 7) att_general_fwd_kernel(const float* 
 #pragma unroll
     for (int l = 0; l < LM; ++l) {
       s[l] *= inv;
-      if (l < L) attn[((long long)b * L + l) * Q + q] = s[l];
+      if (l < L && live) attn[((long long)b * L + l) * Q + q] = s[l];
     }
 #pragma unroll
-    for (int l = 0; l < LM / 2; ++l) s2[l] = make_float2(s[2 * l], s[2 * l + 1]);
-    for (int c = 0; c < cs; ++c) {
-      float acc = 0.f;
-      if (c < idf) {
-        const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
-        float2 a2 = make_float2(0.f, 0.f);   // two interleaved partial sums (even / odd words)
+    for (int l = 0; l < LM / 2; ++l) s2[u][l] = make_float2(s[2 * l], s[2 * l + 1]);
+  }
+  for (int c = 0; c < cs; ++c) {
+    float acc[QPT];
 #pragma unroll
-        for (int l4 = 0; l4 < LM / 4; ++l4) {
-          const float4 w = sr[l4];
-          a2 = ffma2(make_float2(w.x, w.y), s2[2 * l4], a2);
-          a2 = ffma2(make_float2(w.z, w.w), s2[2 * l4 + 1], a2);
+    for (int u = 0; u < QPT; ++u) acc[u] = 0.f;
+    if (c < idf) {
+      const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
+      float2 a2[QPT];                      // two interleaved partial sums (even / odd words) per query
+#pragma unroll
+      for (int u = 0; u < QPT; ++u) a2[u] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int l4 = 0; l4 < LM / 4; ++l4) {
+        const float4 w = sr[l4];
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+          a2[u] = ffma2(make_float2(w.x, w.y), s2[u][2 * l4], a2[u]);
+          a2[u] = ffma2(make_float2(w.z, w.w), s2[u][2 * l4 + 1], a2[u]);
         }
-        acc = a2.x + a2.y;
       }
-      row[c] = acc;
+#pragma unroll
+      for (int u = 0; u < QPT; ++u) acc[u] = a2[u].x + a2[u].y;
     }
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) tile[(t + u * ATT_Q) * pitch + c] = acc[u];
   }
   __syncthreads();
   float* wb = wc + ((long long)b * Q + q0) * cs;
-  for (int i = t; i < nq * cs / 4; i += ATT_Q) {
-    int r = (i * 4) / cs, c = (i * 4) - r * cs;
-    const float* d = tile + r * pitch + c;
+  for (int r = t / cs4, c4 = t - (t / cs4) * cs4, i = t; i < nq * cs4; i += ATT_Q) {
+    const float* d = tile + r * pitch + c4 * 4;
     st4(wb + i * 4, make_float4(d[0], d[1], d[2], d[3]));
+    c4 += ATT_Q % cs4;
+    r += ATT_Q / cs4;
+    if (c4 >= cs4) { c4 -= cs4; ++r; }
   }
 }
 
@@ -188,16 +216,28 @@ OG_API int og_att_general_fwd(const float* h, const float* src, const unsigned c
                               int cs, int L, float* wc, float* attn, cudaStream_t stream) {
   if (L > LMAX || cs % 4 || idf > cs) return (int)cudaErrorInvalidValue;
   if (B == 0 || Q == 0) return 0;
+  if (L <= 20 && Q >= 4096) {   // the large maps of the hot path: two queries per thread
+    constexpr int QPT = 2;
+    const size_t sm = sizeof(float) * (ATT_Q * QPT * (cs + 1) + idf * 20);
+    static size_t configured = 0;
+    if (sm > configured) {
+      OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel<20, QPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      configured = sm;
+    }
+    dim3 grid2(og_cdiv(Q, ATT_Q * QPT), B);
+    att_general_fwd_kernel<20, QPT><<<grid2, ATT_Q, sm, stream>>>(h, src, mask, B, Q, idf, cs, L, wc, attn);
+    OG_RETURN_LAST_ERROR();
+  }
   const int LMsel = L <= 20 ? 20 : LMAX;
   size_t sm = sizeof(float) * (ATT_Q * (cs + 1) + idf * LMsel);
   dim3 grid(og_cdiv(Q, ATT_Q), B);
   if (L <= 20) {   // captions of the hot path have 12..18 words: keep the per-thread score vector small
     if (sm > 48 * 1024)
-      OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    att_general_fwd_kernel<20><<<grid, ATT_Q, sm, stream>>>(h, src, mask, B, Q, idf, cs, L, wc, attn);
+      OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel<20, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    att_general_fwd_kernel<20, 1><<<grid, ATT_Q, sm, stream>>>(h, src, mask, B, Q, idf, cs, L, wc, attn);
   } else {
-    OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    att_general_fwd_kernel<LMAX><<<grid, ATT_Q, sm, stream>>>(h, src, mask, B, Q, idf, cs, L, wc, attn);
+    OG_CHECK(cudaFuncSetAttribute(att_general_fwd_kernel<LMAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    att_general_fwd_kernel<LMAX, 1><<<grid, ATT_Q, sm, stream>>>(h, src, mask, B, Q, idf, cs, L, wc, attn);
   }
   OG_RETURN_LAST_ERROR();
 }
