@@ -179,6 +179,13 @@ int og_copy_channels(const float* src, int sstride, int soff, float* dst, int ds
                      int accumulate, cudaStream_t stream);
 int og_broadcast_channels(const float* c, int B, int Cc, float* dst, int dstride, int doff, long long pix_per_img,
                           cudaStream_t stream);
+/* Row gather out[i,:] = x[idx[i],:] (idx: int64 device array) and its adjoint (gx zero-filled, then += g rows):
+ * the roi compaction of feat_select (ref: miscc/utils.py:465-499) and the raw_conditions[classes] lookup of
+ * objD_loss (ref: miscc/losses.py:280-281) without per-roi host loops. */
+int og_gather_rows(const float* x, const long long* idx, long long n_out, long long rowlen, float* out,
+                   cudaStream_t stream);
+int og_scatter_rows_add(const float* g, const long long* idx, long long n_out, long long n_in, long long rowlen,
+                        float* gx, cudaStream_t stream);
 int og_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
 /* F.interpolate(bilinear, align_corners=True) on NHWC (ref: model.py:1217-1218, 1283-1284) and its adjoint */
 int og_bilinear_fwd(const float* x, int N, int IH, int IW, int C, int OH, int OW, float* y, cudaStream_t stream);

@@ -183,20 +183,20 @@ att_general_fwd_kernel(const float* __restrict__ h, const float* __restrict__ sr
     for (int u = 0; u < QPT; ++u) acc[u] = 0.f;
     if (c < idf) {
       const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
-      float2 a2[QPT];                      // two interleaved partial sums (even / odd words) per query
+      float2 a2[QPT], b2[QPT];             // four interleaved partial sums per query: short dependent FMA chains
 #pragma unroll
-      for (int u = 0; u < QPT; ++u) a2[u] = make_float2(0.f, 0.f);
+      for (int u = 0; u < QPT; ++u) a2[u] = b2[u] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int l4 = 0; l4 < LM / 4; ++l4) {
         const float4 w = sr[l4];
 #pragma unroll
         for (int u = 0; u < QPT; ++u) {
           a2[u] = ffma2(make_float2(w.x, w.y), s2[u][2 * l4], a2[u]);
-          a2[u] = ffma2(make_float2(w.z, w.w), s2[u][2 * l4 + 1], a2[u]);
+          b2[u] = ffma2(make_float2(w.z, w.w), s2[u][2 * l4 + 1], b2[u]);
         }
       }
 #pragma unroll
-      for (int u = 0; u < QPT; ++u) acc[u] = a2[u].x + a2[u].y;
+      for (int u = 0; u < QPT; ++u) acc[u] = (a2[u].x + b2[u].x) + (a2[u].y + b2[u].y);
     }
 #pragma unroll
     for (int u = 0; u < QPT; ++u) tile[(t + u * ATT_Q) * pitch + c] = acc[u];

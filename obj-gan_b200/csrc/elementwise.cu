@@ -250,6 +250,41 @@ OG_API int og_copy_channels(const float* src, int sstride, int soff, float* dst,
   OG_RETURN_LAST_ERROR();
 }
 
+// row gather out[i, :] = x[idx[i], :] and its adjoint gx[idx[i], :] += g[i, :]  (feat_select's roi compaction,
+// ref: miscc/utils.py:465-499, and the raw_conditions[classes] lookup, miscc/losses.py:280-281, without host loops)
+__global__ void gather_rows_kernel(const float* __restrict__ x, const long long* __restrict__ idx, long long n_out,
+                                   long long rowlen, float* __restrict__ out) {
+  const long long total = n_out * rowlen;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / rowlen, c = i - r * rowlen;
+    out[i] = x[idx[r] * rowlen + c];
+  }
+}
+__global__ void scatter_rows_add_kernel(const float* __restrict__ g, const long long* __restrict__ idx, long long n_out,
+                                        long long rowlen, float* __restrict__ gx) {
+  const long long total = n_out * rowlen;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / rowlen, c = i - r * rowlen;
+    atomicAdd(gx + idx[r] * rowlen + c, g[i]);
+  }
+}
+OG_API int og_gather_rows(const float* x, const long long* idx, long long n_out, long long rowlen, float* out,
+                          cudaStream_t stream) {
+  if (n_out * rowlen == 0) return 0;
+  gather_rows_kernel<<<eblocks(n_out * rowlen), 256, 0, stream>>>(x, idx, n_out, rowlen, out);
+  OG_RETURN_LAST_ERROR();
+}
+// gx ([n_in][rowlen]) is zero-filled here, then receives the scattered rows
+OG_API int og_scatter_rows_add(const float* g, const long long* idx, long long n_out, long long n_in, long long rowlen,
+                               float* gx, cudaStream_t stream) {
+  OG_CHECK(cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)(n_in * rowlen), stream));
+  if (n_out * rowlen == 0) return 0;
+  scatter_rows_add_kernel<<<eblocks(n_out * rowlen), 256, 0, stream>>>(g, idx, n_out, rowlen, gx);
+  OG_RETURN_LAST_ERROR();
+}
+
 // c_code (B, Cc) broadcast over each image's pixels into a channel slice (D_GET_LOGITS, model.py:1037-1041)
 __global__ void broadcast_channels_kernel(const float* __restrict__ c, int Cc, float* __restrict__ dst, int dstride,
                                           int doff, long long pix_per_img, long long total) {

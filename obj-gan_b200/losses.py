@@ -111,3 +111,85 @@ def shpD_loss(netShpD, real_imgs, fake_imgs, seg_conditions, rois, num_rois):
         wrong = netShpD(real_imgs[idx], fake_seg[idx])
         return err + (fake_err + ops.bce(net.UNCOND_DNET(wrong), 0.0, 1.0)) / 2.0
     return err + fake_err
+
+
+def feat_select(pooled_feat, raw_bt_c_codes, fm_rois, num_rois, is_large_scale=False):
+    """ref: miscc/utils.py:465-499 -- keep the rois of the requested scale class.  The box filter runs on the host
+    copy of ``fm_rois`` like the reference; the kept rows are compacted on the device by ONE gather per tensor
+    (the reference concatenates per-sample slices).  Returns (features (R', C, h, w), classes (host int array),
+    bt_c_codes (R', D)); three empty lists when nothing is kept."""
+    import numpy as np
+    fm = fm_rois.detach().cpu().numpy() if torch.is_tensor(fm_rois) else np.asarray(fm_rois)
+    nums = num_rois.detach().cpu().numpy().tolist() if torch.is_tensor(num_rois) else list(num_rois)
+    boxes = pooled_feat.shape[1]
+    flat, classes = [], []
+    for b in range(len(nums)):
+        for r in range(int(nums[b])):
+            _, _, width, height = fm[b, r, :4]
+            if width < 1.25 and height < 1.25:
+                continue
+            big = max(width, height) >= cfg.ROI.ROI_SIZE_THRS
+            if big != bool(is_large_scale):
+                continue
+            flat.append(b * boxes + r)
+            classes.append(int(fm[b, r, 4]))
+    if not flat:
+        return [], [], []
+    idx = torch.as_tensor(flat, dtype=torch.int64, device=pooled_feat.device)
+    feats = ops.gather_rows(pooled_feat.reshape((-1,) + tuple(pooled_feat.shape[2:])), idx)
+    codes = ops.gather_rows(raw_bt_c_codes.reshape(-1, raw_bt_c_codes.shape[-1]), idx)
+    return feats, np.asarray(classes, dtype=np.int64), codes
+
+
+def objD_loss(netObjD, real_imgs, fake_imgs, seg_conditions, raw_conditions, raw_bt_c_codes, fm_rois, num_rois,
+              is_large_scale=False):
+    """ref: miscc/losses.py:254-361 -- object discriminator loss: real / fake / mismatched-condition / permuted-shape
+    terms over the rois of one scale class.  Reproduces the reference's use of ``classes`` (not ``classes2``) for the
+    permuted-shape conditions (losses.py:307-311)."""
+    net = netObjD.module if hasattr(netObjD, "module") else netObjD
+    dev = real_imgs.device
+
+    def lookup(cls_idx, codes):
+        idx = torch.as_tensor(cls_idx, dtype=torch.int64, device=dev)
+        return ops.cat_rows_const(ops.gather_rows(raw_conditions.detach(), idx), codes)
+
+    real_pooled = netObjD(real_imgs, seg_conditions, fm_rois, num_rois)
+    real_features, classes, bt_c_codes = feat_select(real_pooled, raw_bt_c_codes, fm_rois, num_rois, is_large_scale)
+    fake_pooled = netObjD(fake_imgs.detach(), seg_conditions, fm_rois, num_rois)
+    fake_features, _, _ = feat_select(fake_pooled, raw_bt_c_codes, fm_rois, num_rois, is_large_scale)
+    fake_seg, valid = permute_seg(seg_conditions, fm_rois, num_rois)
+    classes2 = []
+    if len(valid) > 0:
+        vi = torch.as_tensor(valid, device=dev)
+        fm_t = fm_rois if torch.is_tensor(fm_rois) else torch.as_tensor(fm_rois)
+        nr_t = num_rois if torch.is_tensor(num_rois) else torch.as_tensor(num_rois)
+        pooled2 = netObjD(real_imgs[vi], fake_seg[vi], fm_t[vi.to(fm_t.device)], nr_t[vi.to(nr_t.device)])
+        fake_features2, classes2, bt_c_codes2 = feat_select(pooled2, raw_bt_c_codes, fm_t[vi.to(fm_t.device)],
+                                                            nr_t[vi.to(nr_t.device)], is_large_scale)
+    n = len(classes)
+    if n == 0:
+        return 0
+    conditions = lookup(classes, bt_c_codes)
+    cond_real = ops.bce(net.COND_DNET(real_features, conditions), 1.0, 1.0)
+    cond_fake = ops.bce(net.COND_DNET(fake_features, conditions), 0.0, 1.0)
+    cond_wrong = None
+    if n > 1:
+        cond_wrong = ops.bce(net.COND_DNET(real_features[:n - 1], conditions[1:n]), 0.0, 1.0)
+    cond_wrong2 = None
+    if len(valid) > 0 and len(classes2) > 0:
+        conditions2 = lookup(classes[:len(classes2)], bt_c_codes2)
+        cond_wrong2 = ops.bce(net.COND_DNET(fake_features2, conditions2), 0.0, 1.0)
+    if net.UNCOND_DNET is not None:
+        err = (ops.bce(net.UNCOND_DNET(real_features), 1.0, 1.0) + cond_real) / 2.0
+        tmp = ops.bce(net.UNCOND_DNET(fake_features), 0.0, 1.0) + cond_fake
+        denorm = 3.0
+    else:
+        err = cond_real
+        tmp = cond_fake
+        denorm = 2.0
+    if cond_wrong is not None:
+        tmp = tmp + cond_wrong
+    if cond_wrong2 is not None:
+        tmp = tmp + cond_wrong2
+        denorm += 1.0
+    return err + tmp / denorm

@@ -654,6 +654,48 @@ def cat_channels(xs, reals):
     return _CatChannels.apply(tuple(reals), *xs)
 
 
+class _GatherRows(torch.autograd.Function):
+    """out[i] = x[idx[i]] over the leading dimension (idx: int64 device tensor)."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        _chk(x, idx)
+        x = x.contiguous()
+        n_in = x.shape[0]
+        rowlen = x.numel() // max(n_in, 1)
+        out = torch.empty((idx.numel(),) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+        _call("og_gather_rows", _p(x), _p(idx), idx.numel(), rowlen, _p(out))
+        ctx.save_for_backward(idx)
+        ctx.shape = tuple(x.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = g.contiguous()
+        gx = torch.empty(ctx.shape, device=g.device, dtype=torch.float32)
+        n_in = ctx.shape[0]
+        rowlen = gx.numel() // max(n_in, 1)
+        _call("og_scatter_rows_add", _p(g), _p(idx), idx.numel(), n_in, rowlen, _p(gx))
+        return gx, None
+
+
+def gather_rows(x, idx):
+    return _GatherRows.apply(x, idx)
+
+
+def cat_rows_const(a, b):
+    """torch.cat((a, b), dim=1) for two constant (no-grad) 2-D tensors: two strided row copies."""
+    _chk(a, b)
+    a, b = a.detach().contiguous(), b.detach().contiguous()
+    r, ca, cb = a.shape[0], a.shape[1], b.shape[1]
+    assert b.shape[0] == r
+    out = torch.empty((r, ca + cb), device=a.device, dtype=torch.float32)
+    _call("og_copy_channels", _p(a), ca, 0, _p(out), ca + cb, 0, ca, r, 0)
+    _call("og_copy_channels", _p(b), cb, 0, _p(out), ca + cb, ca, cb, r, 0)
+    return out
+
+
 class _BroadcastCat(torch.autograd.Function):
     """D_GET_LOGITS conditioning: cat(h, c_code broadcast over the grid) along channels (no grad to c_code,
     which is the detached sentence embedding in every caller: miscc/losses.py:169-190, 375-377)."""

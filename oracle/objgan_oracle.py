@@ -440,6 +440,88 @@ def obj_d_net_forward(sd, x, s, fm_rois, n_layer, img_size=512, update=True, box
     return out.view(x.shape[0], boxes_num, out.shape[1], out.shape[2], out.shape[3])
 
 
+def permute_seg(seg, rois, num_rois):
+    """ref: miscc/utils.py:445-462 -- per sample with rois, shuffle (host ``random.shuffle``) the segmentation channels
+    of the classes present; returns the permuted maps and the indices of the samples whose order changed."""
+    import random
+    from copy import deepcopy
+    new_seg = seg.clone()
+    rois = np.asarray(rois)
+    valid = []
+    for b in range(seg.shape[0]):
+        if int(num_rois[b]) == 0:
+            continue
+        classes = list(np.unique(rois[b, :int(num_rois[b]), 4]).astype(int))
+        shuffled = deepcopy(classes)
+        random.shuffle(shuffled)
+        if classes != shuffled:
+            valid.append(b)
+            new_seg[b, classes] = seg[b, shuffled]
+    return new_seg, valid
+
+
+def feat_select(pooled, raw_bt_c_codes, fm_rois, num_rois, is_large_scale=False, size_thrs=16.0):
+    """ref: miscc/utils.py:465-499 -- rois of one scale class: drop boxes smaller than 1.25 x 1.25 feature-map cells,
+    keep max(w, h) >= ROI_SIZE_THRS for the large-scale net and < ROI_SIZE_THRS for the small-scale one."""
+    fm = np.asarray(fm_rois)
+    feats, classes, codes = [], [], []
+    for b in range(len(num_rois)):
+        keep = []
+        for r in range(int(num_rois[b])):
+            _, _, w, h = fm[b, r, :4]
+            if w < 1.25 and h < 1.25:
+                continue
+            if (max(w, h) >= size_thrs) != bool(is_large_scale):
+                continue
+            keep.append(r)
+        if not keep:
+            continue
+        feats.append(pooled[b, keep])
+        classes.append(fm[b, keep, 4].astype(int))
+        codes.append(raw_bt_c_codes[b, keep])
+    if not classes:
+        return [], [], []
+    return torch.cat(feats, 0), np.concatenate(classes), torch.cat(codes, 0)
+
+
+def obj_d_loss(sd, real, fake, seg, raw_conditions, raw_bt_c_codes, fm_rois, num_rois, n_layer, *,
+               is_large_scale=False, update=True, size_thrs=16.0):
+    """ref: miscc/losses.py:254-361 (objD_loss) on top of obj_d_net_forward / d_get_logits.  ``fm_rois``: host array
+    (B, 10, >= 5) [x, y, w, h, class, ...]; ``num_rois``: host ints.  The permuted-shape conditions index ``classes``
+    (not ``classes2``) exactly like the reference (losses.py:307-311)."""
+    fm = np.asarray(fm_rois)
+    nums = [int(v) for v in num_rois]
+    real_pooled = obj_d_net_forward(sd, real, seg, fm, n_layer, update=update)
+    rf, classes, codes = feat_select(real_pooled, raw_bt_c_codes, fm, nums, is_large_scale, size_thrs)
+    fake_pooled = obj_d_net_forward(sd, fake.detach(), seg, fm, n_layer, update=update)
+    ff, _, _ = feat_select(fake_pooled, raw_bt_c_codes, fm, nums, is_large_scale, size_thrs)
+    fake_seg, valid = permute_seg(seg, fm, nums)
+    classes2 = []
+    if len(valid) > 0:
+        pooled2 = obj_d_net_forward(sd, real[valid], fake_seg[valid], fm[valid], n_layer, update=update)
+        ff2, classes2, codes2 = feat_select(pooled2, raw_bt_c_codes, fm[valid], [nums[v] for v in valid],
+                                            is_large_scale, size_thrs)
+    n = len(classes)
+    if n == 0:
+        return 0
+    cond = torch.cat((raw_conditions[torch.as_tensor(classes)], codes), 1)
+    c_real = bce(d_get_logits(rf, sd, "COND_DNET", cond, update), 1)
+    c_fake = bce(d_get_logits(ff, sd, "COND_DNET", cond, update), 0)
+    tmp = c_fake
+    if n > 1:
+        tmp = tmp + bce(d_get_logits(rf[:n - 1], sd, "COND_DNET", cond[1:n], update), 0)
+    extra = 0.0
+    if len(valid) > 0 and len(classes2) > 0:
+        cond2 = torch.cat((raw_conditions[torch.as_tensor(classes[:len(classes2)])], codes2), 1)
+        tmp = tmp + bce(d_get_logits(ff2, sd, "COND_DNET", cond2, update), 0)
+        extra = 1.0
+    if "UNCOND_DNET.outlogits.0.weight" in sd:
+        err = (bce(d_get_logits(rf, sd, "UNCOND_DNET", None, update), 1) + c_real) / 2.0
+        tmp = tmp + bce(d_get_logits(ff, sd, "UNCOND_DNET", None, update), 0)
+        return err + tmp / (3.0 + extra)
+    return c_real + tmp / (2.0 + extra)
+
+
 # --------------------------------------------------------------------------------------
 # optimiser (trainer.py:197-224, 461-462)
 # --------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@ import torch
 import torch.nn.functional as F
 
 from objgan_b200 import lib, model, ops, synth, trainer
+from objgan_b200.config import cfg
 from objgan_b200.lib import (ACT_LRELU, ACT_NONE, ACT_SIGMOID, ACT_TANH, NA_GLU, NA_LRELU, NA_NONE, PAD_REFLECT,
                              PAD_ZERO, UPSAMPLE2X)
 from oracle import objgan_oracle as O
@@ -565,3 +566,41 @@ def test_shp_d_net_parity(monkeypatch):
         if k == "shp_code.1.bias":
             continue
         close_grad(params[k].grad, gr, what=k)
+
+
+@pytest.mark.parametrize("cls,n_layer,large", [("OBJ_SS_D_NET", 3, False), ("OBJ_LS_D_NET", 4, True)])
+def test_obj_d_loss_parity(cls, n_layer, large, monkeypatch):
+    """objD_loss (ref: miscc/losses.py:254-361): device-side roi compaction (feat_select), permuted-shape branch,
+    COND / UNCOND heads and the loss weights, value and parameter gradients against the oracle (exact-fp32 engine)."""
+    import random
+    from objgan_b200 import losses
+    monkeypatch.setattr(ops, "CONV_ENGINE", "simt")
+    torch.manual_seed(16)
+    net = getattr(model, cls)(80)
+    net.apply(model.weights_init)
+    net.to(DEV)
+    sd = _cpu_sd(net)
+    inp = synth.make_inputs(3, seed=8, parity=True)
+    real, seg, fm, nr = inp["imgs"][2], inp["hmaps"][2], inp["fm_rois"].clone(), inp["num_rois"]
+    fm[..., 2:4] *= torch.tensor([1.0, 3.0, 0.2]).view(3, 1, 1)       # boxes on both sides of the size threshold
+    fake = torch.tanh(torch.randn_like(real))
+    raw_cond = inp["clabels_emb"]
+    raw_bt = torch.randn(3, 10, cfg.GAN.GF_DIM)
+    keys = O.trainable_keys(sd)
+    live, leaves = O._with_grad(sd, keys)
+    random.seed(12)
+    loss_r = O.obj_d_loss(live, real, fake, seg, raw_cond, raw_bt, fm.numpy(), nr.tolist(), n_layer, is_large_scale=large)
+    grads = torch.autograd.grad(loss_r, [leaves[k] for k in keys], allow_unused=True)
+    random.seed(12)
+    loss = losses.objD_loss(net, real.to(DEV), fake.to(DEV), seg.to(DEV), raw_cond.to(DEV), raw_bt.to(DEV), fm, nr,
+                            is_large_scale=large)
+    assert abs(float(loss) - float(loss_r)) < 1e-4 * max(1.0, abs(float(loss_r))), (float(loss), float(loss_r))
+    loss.backward()
+    params = dict(net.named_parameters())
+    checked = 0
+    for k, gr in zip(keys, grads):
+        if gr is None or k == "shp_code.1.bias":
+            continue
+        close_grad(params[k].grad, gr, what=k)
+        checked += 1
+    assert checked >= 10
