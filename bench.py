@@ -149,11 +149,12 @@ def conv_roofline(hbm, bf16_tf, src):
             "f16x3": "3 MMAs per algorithmic product, so frac <= 1/3 by construction; amax + prep_split passes included"}[eng]
     return {"bound": "tensor", "kernel": kname + " + prep_split: res-block conv1 194->388 3x3 @128x128, B=16",
             "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-            "traffic": None, "ms_per_launch": round(ms, 3),
+            "traffic": 816.9e6 if eng == "f16x3" else None, "ms_per_launch": round(ms, 3),
             "algorithmic_flops_per_launch": flops,
             "issued_mma_tflops": round(achieved * (3 if eng == "f16x3" else 1), 1) if eng != "simt" else None,
             "frac_of_peak_counting_issued_mmas": round(achieved * (3 if eng == "f16x3" else 1) / peak, 4) if eng != "simt" else None,
-            "peak_source": f"{src} bf16 cuBLAS burst (kind::f16 = bf16 rate); {note}; traffic: see profiles/"}
+            "peak_source": f"{src} bf16 cuBLAS burst (kind::f16 = bf16 rate); {note}; traffic = dram read+write of "
+                           "conv_tc2_kernel<208,1> in profiles/r01_final_kernels.ncu-rep (algorithmic: 635 MB)"}
 
 
 def attn_roofline(hbm, src):
@@ -180,8 +181,9 @@ def attn_roofline(hbm, src):
     byts = 4.0 * Q * (2 * C + L) * B
     ach = byts / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "att_general_fwd_kernel<20,2> (Q=16384, L=18, C=48, B=16)", "achieved": round(ach, 1),
-            "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None, "ms_per_launch": round(ms, 4),
-            "peak_source": f"{src} copy bandwidth"}
+            "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": 62.96e6, "ms_per_launch": round(ms, 4),
+            "peak_source": f"{src} copy bandwidth; traffic = dram read+write in profiles/r01_final_attention.ncu-rep (50.4 MB read; "
+                           "most of the 69 MB written is still dirty in the 126 MB L2 when the kernel ends)"}
 
 
 def _best_cpu_threads():

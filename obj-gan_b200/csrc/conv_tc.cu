@@ -1086,8 +1086,9 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
                         : launch_tc2<256, false>(mah, mal, mbh, mbl, p, grid2, stream);
   }
   switch (BNsel) {
-    case 32:  return launch_tc<32, 4>(mah, mal, mbh, mbl, p, grid, stream);
-    case 64:  return launch_tc<64, 4>(mah, mal, mbh, mbl, p, grid, stream);
+    // narrow output tiles are latency bound (tiny MMAs): two shallow-pipelined CTAs per SM instead of one deep one
+    case 32:  return launch_tc<32, 2>(mah, mal, mbh, mbl, p, grid, stream);
+    case 64:  return launch_tc<64, 2>(mah, mal, mbh, mbl, p, grid, stream);
     case 112: return launch_tc<112, 3>(mah, mal, mbh, mbl, p, grid, stream);
     case 208: return launch_tc<208, 2>(mah, mal, mbh, mbl, p, grid, stream);
     default:  return launch_tc<256, 2>(mah, mal, mbh, mbl, p, grid, stream);
@@ -1185,8 +1186,8 @@ OG_API int og_conv2d_wgrad_tc(const void* gh, const void* gl, const unsigned* am
                         : launch_wgrad2<256>(mgh, mgl, mxh, mxl, p, grid2, stream);
   }
   switch (BNsel) {
-    case 32:  return launch_wgrad<32, 4>(mgh, mgl, mxh, mxl, p, grid, stream);
-    case 64:  return launch_wgrad<64, 4>(mgh, mgl, mxh, mxl, p, grid, stream);
+    case 32:  return launch_wgrad<32, 2>(mgh, mgl, mxh, mxl, p, grid, stream);
+    case 64:  return launch_wgrad<64, 2>(mgh, mgl, mxh, mxl, p, grid, stream);
     case 112: return launch_wgrad<112, 3>(mgh, mgl, mxh, mxl, p, grid, stream);
     case 208: return launch_wgrad<208, 2>(mgh, mgl, mxh, mxl, p, grid, stream);
     default:  return launch_wgrad<256, 2>(mgh, mgl, mxh, mxl, p, grid, stream);
