@@ -321,7 +321,16 @@ def _tc_wgrad_ok(kind, mode, n, oh, ow):
     return n % (64 // (cw * chh)) == 0
 
 
-def _tc_wgrad(kind, xs, gs, n, h, w, oh, ow, weight, c, kp, split, splitp, mode):
+def _grad_sink(param):
+    """Persistent gradient buffer a trainer attached to a parameter (``param.og_grad_sink``): the backward kernels
+    then accumulate into it directly and hand autograd no gradient (one kernel and one temporary less per use)."""
+    sink = getattr(param, "og_grad_sink", None)
+    if sink is not None and sink.shape == param.shape and sink.is_contiguous():
+        return sink
+    return None
+
+
+def _tc_wgrad(kind, xs, gs, n, h, w, oh, ow, weight, c, kp, split, splitp, mode, sink=None):
     """Weight gradient on the tensor cores from the hi/lo copies of x (_split_x) and g (_split_g), both NHWC;
     (h, w) is the extent of x, (oh, ow) of g.  Returns the OIHW gradient."""
     import ctypes
@@ -348,11 +357,15 @@ def _tc_wgrad(kind, xs, gs, n, h, w, oh, ow, weight, c, kp, split, splitp, mode)
     dwp = torch.empty(nt * kp * c, device=xh.device, dtype=torch.float32)
     _call("og_conv2d_wgrad_tc", _p(gh), _p(gl), _p(ag), n, gh.shape[0], oh, ow, kp, _p(xh), _p(xl), _p(ax),
           xh.shape[0], xh.shape[1], xh.shape[2], c, _p(dwp), nt, ctypes.addressof(arr), len(ent), _nsplit())
-    gw = torch.empty_like(weight)
     if mode == UPSAMPLE2X and kind == "s1":
+        gw = torch.empty_like(weight)
         _call("og_unpack_upsample_wgrad", _p(dwp), co, ci, c, kp, split, splitp, _p(gw))
-    else:
-        _call("og_unpack_wgrad", _p(dwp), co, ci, kh_, kw_, c, kp, split, splitp, _p(gw), 0, 1)
+        return gw
+    if sink is not None:
+        _call("og_unpack_wgrad", _p(dwp), co, ci, kh_, kw_, c, kp, split, splitp, _p(sink), 1, 1)
+        return None
+    gw = torch.empty_like(weight)
+    _call("og_unpack_wgrad", _p(dwp), co, ci, kh_, kw_, c, kp, split, splitp, _p(gw), 0, 1)
     return gw
 
 
@@ -414,6 +427,8 @@ class _Conv2d(torch.autograd.Function):
             y = _conv_raw(x, wf, n, h, w, c, oh, ow, kp, kh, kw, stride, pad, mode, bias_p, act,
                           splitk=(bias is None and act == ACT_NONE))
         ctx.kind = kind
+        ctx.wsink = _grad_sink(weight)
+        ctx.bsink = _grad_sink(bias) if bias is not None else None
         ctx.xs = xs                      # hi/lo operand copies of x, reused by the weight gradient
         ctx.narrow = narrow
         ctx.cfg = (stride, pad, mode, act, split, splitp, kp, need_t)
@@ -437,8 +452,11 @@ class _Conv2d(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             scratch = torch.empty(kp, device=g.device, dtype=torch.float64)
-            gb = torch.empty(co, device=g.device, dtype=torch.float32)
-            _call("og_channel_sum", _p(g), n * oh * ow, kp, _p(scratch), _p(gb), co, 0)
+            if ctx.bsink is not None:
+                _call("og_channel_sum", _p(g), n * oh * ow, kp, _p(scratch), _p(ctx.bsink), co, 1)
+            else:
+                gb = torch.empty(co, device=g.device, dtype=torch.float32)
+                _call("og_channel_sum", _p(g), n * oh * ow, kp, _p(scratch), _p(gb), co, 0)
         kind = ctx.kind
         if ctx.narrow:
             wf, _ = ctx.cache.get(weight, c, kp, split, splitp, False)
@@ -448,8 +466,11 @@ class _Conv2d(torch.autograd.Function):
             if ctx.needs_input_grad[1]:
                 dwp = torch.empty(kh * kw * c * 8, device=g.device, dtype=torch.float32)
                 _call("og_conv2d_narrow_wgrad", _p(x), n, h, w, c, _p(g), _p(dwp), oh, ow, kh, kw, stride, pad)
-                gw = torch.empty_like(weight)
-                _call("og_unpack_wgrad", _p(dwp), co, ci, kh, kw, c, kp, split, splitp, _p(gw), 0, 0)
+                if ctx.wsink is not None:
+                    _call("og_unpack_wgrad", _p(dwp), co, ci, kh, kw, c, kp, split, splitp, _p(ctx.wsink), 1, 0)
+                else:
+                    gw = torch.empty_like(weight)
+                    _call("og_unpack_wgrad", _p(dwp), co, ci, kh, kw, c, kp, split, splitp, _p(gw), 0, 0)
             return gx, gw, gb, None, None, None, None, None, None
         tc_w = bool(ctx.needs_input_grad[1] and kind and TC_WGRAD and _tc_wgrad_ok(kind, mode, n, oh, ow))
         gs = _split_g(kind, g, mode) if kind and (ctx.needs_input_grad[0] or tc_w) else None
@@ -471,13 +492,16 @@ class _Conv2d(torch.autograd.Function):
         if tc_w:
             xs = ctx.xs if ctx.xs is not None else _split_x(kind, x, mode)
             ctx.xs = None
-            gw = _tc_wgrad(kind, xs, gs, n, h, w, oh, ow, weight, c, kp, split, splitp, mode)
+            gw = _tc_wgrad(kind, xs, gs, n, h, w, oh, ow, weight, c, kp, split, splitp, mode, ctx.wsink)
         elif ctx.needs_input_grad[1]:
             dwp = torch.empty(kh * kw * c * kp, device=g.device, dtype=torch.float32)
             _call("og_conv2d_wgrad_simt", _p(x), n, h, w, c, h * w * c, w * c, c, _p(g), oh, ow, kp, oh * ow * kp,
                   ow * kp, kp, _p(dwp), kh, kw, stride, pad, mode)
-            gw = torch.empty_like(weight)
-            _call("og_unpack_wgrad", _p(dwp), co, ci, kh, kw, c, kp, split, splitp, _p(gw), 0, 0)
+            if ctx.wsink is not None:
+                _call("og_unpack_wgrad", _p(dwp), co, ci, kh, kw, c, kp, split, splitp, _p(ctx.wsink), 1, 0)
+            else:
+                gw = torch.empty_like(weight)
+                _call("og_unpack_wgrad", _p(dwp), co, ci, kh, kw, c, kp, split, splitp, _p(gw), 0, 0)
         return gx, gw, gb, None, None, None, None, None, None
 
 
@@ -514,6 +538,7 @@ class _NormAct(torch.autograd.Function):
         _call("og_norm_apply", _p(y), groups, P, cy, _p(mean), _p(rstd), _p(gamma), _p(beta), _p(res), act,
               LRELU_SLOPE, _p(out), _p(_tag_amax(out)))
         ctx.cfg = (groups, P, cy, act, res is not None)
+        ctx.sinks = (_grad_sink(gamma), _grad_sink(beta)) if gamma is not None else (None, None)
         ctx.save_for_backward(y, mean, rstd, gamma, beta)
         return out
 
@@ -525,11 +550,16 @@ class _NormAct(torch.autograd.Function):
         bstats = torch.empty(groups * cy * 2, device=g.device, dtype=torch.float64)
         dy = torch.empty_like(y)
         dgamma = dbeta = None
-        if gamma is not None:
+        direct = gamma is not None and ctx.sinks[0] is not None and ctx.sinks[1] is not None
+        if direct:
+            dgamma, dbeta = ctx.sinks
+        elif gamma is not None:
             dgamma = torch.empty_like(gamma)
             dbeta = torch.empty_like(beta)
         _call("og_norm_backward", _p(y), _p(g), groups, P, cy, _p(mean), _p(rstd), _p(gamma), _p(beta), act,
-              LRELU_SLOPE, _p(bstats), _p(dy), _p(dgamma), _p(dbeta), 0, _p(_tag_amax(dy)))
+              LRELU_SLOPE, _p(bstats), _p(dy), _p(dgamma), _p(dbeta), 1 if direct else 0, _p(_tag_amax(dy)))
+        if direct:
+            dgamma = dbeta = None
         return dy, dgamma, dbeta, (g if has_res else None), None, None, None
 
 

@@ -46,6 +46,7 @@ class FlatBucket:
             self.flat[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat[o:o + n].view(p.shape)
             p.grad = self.grad[o:o + n].view(p.shape)
+            p.og_grad_sink = p.grad          # the backward kernels accumulate here directly (ops._grad_sink)
         self.avg = self.flat.clone() if ema else None
         self.offsets = offs
         self.step = 0
