@@ -38,6 +38,26 @@ def sub(t, s):
     return t[..., ::s, ::s].contiguous().numpy()
 
 
+def obj_d_case(ref, cls, seed=303):
+    """Seeded object-discriminator case shared by the fixture generator (ref given: returns the reference net with the
+    weights loaded) and the golden test (ref None: returns the state_dict)."""
+    torch.manual_seed(seed)
+    mine = getattr(model, cls)(80)
+    mine.apply(model.weights_init)
+    sd = {k: v.clone() for k, v in mine.state_dict().items()}
+    inp = synth.make_inputs(3, seed=seed + 1, parity=True)
+    real, seg, fm, nr = inp["imgs"][2], inp["hmaps"][2], inp["fm_rois"].clone(), inp["num_rois"]
+    fm[..., 2:4] *= torch.tensor([1.0, 3.0, 0.2]).view(3, 1, 1)       # boxes on both sides of the size threshold
+    gen = torch.Generator().manual_seed(seed + 2)
+    fake = torch.tanh(torch.randn(real.shape, generator=gen))
+    raw_bt = torch.randn(3, 10, mine.COND_DNET.ef_dim - inp["clabels_emb"].shape[1], generator=gen)
+    if ref is None:
+        return sd, real, fake, seg, fm, nr, inp["clabels_emb"], raw_bt
+    net = getattr(ref.model, cls)(80)
+    net.load_state_dict(sd, strict=True)
+    return net, real, fake, seg, fm, nr, inp["clabels_emb"], raw_bt
+
+
 def main():
     ref = refimport.load()
     g_sd, d_sds = build_weights()
@@ -99,6 +119,39 @@ def main():
     lib.ROIAlignForwardCpu(feat.ctypes.data_as(fp), ctypes.c_float(1.0 / 16), 12, 16, 16, 5, 6, 6,
                            rois.ctypes.data_as(fp), outp.ctypes.data_as(fp))
     np.savez_compressed(os.path.join(HERE, "roi_align.npz"), feat=feat, rois=rois, out=outp)
+    # ---- objD_loss: the reference's own loss / feat_select / permute_seg code (miscc/losses.py:254-361) on a net whose
+    # body is built from the reference's sub-modules and its roi_align.c (model.py:1227-1241 uses a Variable/resize_
+    # idiom that no longer runs; it is replaced by the three lines it stands for) ----------------------------------
+    import random
+    import torch.nn.functional as F
+    res = {}
+    for cls, n_layer, large in (("OBJ_SS_D_NET", 3, False), ("OBJ_LS_D_NET", 4, True)):
+        net, real, fake, seg, fm, nr, raw_cond, raw_bt = obj_d_case(ref, cls)
+
+        class Net:
+            COND_DNET, UNCOND_DNET = net.COND_DNET, net.UNCOND_DNET
+
+            def __call__(self, x, s, f, n):
+                x5 = F.interpolate(x, size=(512, 512), mode="bilinear", align_corners=True)
+                s5 = F.interpolate(s, size=(512, 512), mode="bilinear", align_corners=True)
+                code = net.img_code(torch.cat([x5, net.shp_code(s5)], 1))
+                fmn = f.numpy().copy()
+                fmn[:, :, [2, 3]] = fmn[:, :, [0, 1]] + fmn[:, :, [2, 3]]
+                nroi = fmn.shape[0] * fmn.shape[1]
+                rois_ = ref.utils._get_rois_blob(fmn.reshape(nroi, fmn.shape[2])[:, :4], np.array([1] * nroi))
+                featc = np.ascontiguousarray(code.detach().numpy())
+                c, hw = featc.shape[1], featc.shape[2]
+                o6 = np.zeros((nroi, c, 6, 6), dtype=np.float32)
+                lib.ROIAlignForwardCpu(featc.ctypes.data_as(fp), ctypes.c_float(1 / 16), nroi, hw, hw, c, 6, 6,
+                                       np.ascontiguousarray(rois_).ctypes.data_as(fp), o6.ctypes.data_as(fp))
+                out_ = net.roi_code(F.avg_pool2d(torch.from_numpy(o6), 2, 1))
+                return out_.view(fmn.shape[0], fmn.shape[1], out_.size(1), out_.size(2), out_.size(3))
+
+        with torch.no_grad():
+            random.seed(21)
+            err = ref.losses.objD_loss(Net(), real, fake, seg, raw_cond, raw_bt, fm, nr, is_large_scale=large)
+        res[cls] = float(err)
+    np.savez_compressed(os.path.join(HERE, "obj_d_loss.npz"), err_ss=res["OBJ_SS_D_NET"], err_ls=res["OBJ_LS_D_NET"])
     print("golden fixtures written to", HERE)
 
 

@@ -63,6 +63,22 @@ def test_pat_d_loss_golden():
     _close(np.array([g.norm().item() for g in grads]), gold["grad_norms"], 1e-3)
 
 
+@pytest.mark.parametrize("cls,n_layer,large,key", [("OBJ_SS_D_NET", 3, False, "err_ss"), ("OBJ_LS_D_NET", 4, True, "err_ls")])
+def test_obj_d_loss_golden(cls, n_layer, large, key):
+    """oracle.obj_d_loss (body + feat_select + permute_seg + heads + weights) against the value the reference's own
+    objD_loss produced on its own sub-modules and roi_align.c (fixture made by make_golden.py)."""
+    import random
+    gold = np.load(os.path.join(GOLD, "obj_d_loss.npz"))
+    sd, real, fake, seg, fm, nr, raw_cond, raw_bt = make_golden.obj_d_case(None, cls)
+    with torch.no_grad():
+        random.seed(21)
+        got = O.obj_d_loss(sd, real, fake, seg, raw_cond, raw_bt, fm.numpy(), nr.tolist(), n_layer,
+                           is_large_scale=large, update=False)
+    want = float(gold[key])
+    assert want > 0
+    assert abs(float(got) - want) <= 2e-5 * max(1.0, abs(want)), (float(got), want)
+
+
 def test_attention_golden():
     gold = np.load(os.path.join(GOLD, "attention.npz"))
     W = torch.randn(48, 256, 1, 1, generator=torch.Generator().manual_seed(1)) * 0.1
