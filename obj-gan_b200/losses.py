@@ -193,3 +193,50 @@ def objD_loss(netObjD, real_imgs, fake_imgs, seg_conditions, raw_conditions, raw
         tmp = tmp + cond_wrong2
         denorm += 1.0
     return err + tmp / denorm
+
+
+def _class_masks(class_ids, batch_size, device):
+    """ref: miscc/losses.py:27-38 -- mask[i, j] = 1 where caption j comes from the same class as sample i (j != i)."""
+    if class_ids is None:
+        return None
+    import numpy as np
+    ids = np.asarray(class_ids)
+    m = (ids.reshape(-1, 1) == ids.reshape(1, -1)).astype(np.uint8)
+    np.fill_diagonal(m, 0)
+    return torch.from_numpy(m[:batch_size, :batch_size].copy()).to(device)
+
+
+def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8, top1=True, is_training=True):
+    """ref: miscc/losses.py:22-71 (DAMSM sentence matching): scaled cosine matrix between the image codes and the
+    sentence codes, two cross-entropy directions.  ``rnn_code`` is a constant here (trainer.py:369 detaches it).
+    Returns (loss0, loss1, accuracy) with the accuracy a device scalar (percent)."""
+    if cnn_code.dim() == 3:
+        cnn_code, rnn_code = cnn_code[0], rnn_code[0]
+    sim = ops.cosine_matrix(cnn_code, rnn_code, eps)
+    mask = _class_masks(class_ids, batch_size, cnn_code.device)
+    loss0, loss1, correct = ops.ce_pair(sim, mask, labels, cfg.TRAIN.SMOOTH.GAMMA3)
+    accuracy = correct * (100.0 / (batch_size * 2.0)) if top1 else sim.detach() * cfg.TRAIN.SMOOTH.GAMMA3
+    return loss0, loss1, accuracy
+
+
+def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size, top1=True, is_training=True):
+    """ref: miscc/losses.py:74-159 (DAMSM word-region matching).  img_features (B, nef, 17, 17) carries the gradient;
+    words_emb (B, nef, T) is a constant.  Per caption i: fused func_attention of its words against every image,
+    cosine similarity word / attended context, Eq. (10) pooling; then the two cross-entropy directions over the
+    B x B similarity matrix.  Returns (loss0, loss1, att_maps, accuracy)."""
+    lens = cap_lens.detach().cpu().tolist() if torch.is_tensor(cap_lens) else list(cap_lens)
+    words_emb = words_emb.detach()
+    sims, att_maps = [], []
+    for i in range(batch_size):
+        n = int(lens[i])
+        word = words_emb[i, :, :n].contiguous()                                  # (nef, n)
+        query = word.unsqueeze(0).expand(batch_size, -1, -1).contiguous()         # the caption against every image
+        wei, attn = ops.func_attention(query, img_features, cfg.TRAIN.SMOOTH.GAMMA1)
+        att_maps.append(attn[i].unsqueeze(0).contiguous())
+        row = ops.cosine_cl(word, wei)                                            # (B, n)
+        sims.append(ops.expsumlog(row, cfg.TRAIN.SMOOTH.GAMMA2).view(batch_size, 1))
+    sim = torch.cat(sims, 1)                                                      # (image, caption)
+    mask = _class_masks(class_ids, batch_size, img_features.device)
+    loss0, loss1, correct = ops.ce_pair(sim, mask, labels, cfg.TRAIN.SMOOTH.GAMMA3)
+    accuracy = correct * (100.0 / (batch_size * 2.0)) if top1 else None
+    return loss0, loss1, att_maps, accuracy

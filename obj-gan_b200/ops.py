@@ -40,7 +40,11 @@ def _p(t):
 
 def _call(name, *args):
     if _lib.DRY_RUN:  # host-logic tracing only (tests): kernels are NOT executed, outputs stay uninitialised
-        _lib.get().launches += 1
+        lib = _lib.get()
+        want = len(lib.protos[name]) - 1          # every prototype ends with the stream
+        if len(args) != want:
+            raise TypeError(f"{name}: {len(args)} arguments passed, the header declares {want} (+ stream)")
+        lib.launches += 1
         return
     _lib.get().call(name, *args, _lib.stream())
 
@@ -1020,6 +1024,125 @@ class _FuncAttention(torch.autograd.Function):
 
 def func_attention(query, context, gamma1):
     return _FuncAttention.apply(query, context, gamma1)
+
+
+class _CosineCL(torch.autograd.Function):
+    """out[b, l] = cosine_similarity(word[:, l], wei[b, :, l]) (ref: miscc/losses.py:13-19 as used at 101-108).
+    ``word`` (D, L) is one caption's embedding shared by all images and is treated as a constant."""
+
+    @staticmethod
+    def forward(ctx, word, wei, eps):
+        _chk(word, wei)
+        word, wei = word.detach().contiguous(), wei.contiguous()
+        b, d, l = wei.shape
+        assert word.shape == (d, l)
+        out = torch.empty((b, l), device=wei.device, dtype=torch.float32)
+        _call("og_cosine_cl_fwd", _p(word), _p(wei), b, d, l, float(eps), _p(out))
+        ctx.eps = float(eps)
+        ctx.save_for_backward(word, wei)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        word, wei = ctx.saved_tensors
+        b, d, l = wei.shape
+        gwei = torch.empty_like(wei)
+        _call("og_cosine_cl_bwd", _p(word), _p(wei), _p(g.contiguous()), b, d, l, ctx.eps, _p(gwei))
+        return None, gwei, None
+
+
+def cosine_cl(word, wei, eps=1e-8):
+    return _CosineCL.apply(word, wei, eps)
+
+
+class _ExpSumLog(torch.autograd.Function):
+    """out[b] = log(sum_l exp(gamma * s[b, l]))  (ref: miscc/losses.py:112-115)."""
+
+    @staticmethod
+    def forward(ctx, s, gamma):
+        _chk(s)
+        s = s.contiguous()
+        b, l = s.shape
+        out = torch.empty((b,), device=s.device, dtype=torch.float32)
+        _call("og_expsumlog_fwd", _p(s), b, l, float(gamma), _p(out))
+        ctx.gamma = float(gamma)
+        ctx.save_for_backward(s)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (s,) = ctx.saved_tensors
+        b, l = s.shape
+        gs = torch.empty_like(s)
+        _call("og_expsumlog_bwd", _p(s), _p(g.contiguous()), b, l, ctx.gamma, _p(gs))
+        return gs, None
+
+
+def expsumlog(s, gamma):
+    return _ExpSumLog.apply(s, gamma)
+
+
+class _CosineMatrix(torch.autograd.Function):
+    """out[i, j] = <a_i, b_j> / max(|a_i| |b_j|, eps) (ref: miscc/losses.py:43-50); ``b`` is a constant."""
+
+    @staticmethod
+    def forward(ctx, a, b, eps):
+        _chk(a, b)
+        a, b = a.contiguous(), b.detach().contiguous()
+        out = torch.empty((a.shape[0], b.shape[0]), device=a.device, dtype=torch.float32)
+        _call("og_cosine_matrix_fwd", _p(a), _p(b), a.shape[0], b.shape[0], a.shape[1], float(eps), _p(out))
+        ctx.eps = float(eps)
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ga = torch.empty_like(a)
+        _call("og_cosine_matrix_bwd", _p(a), _p(b), _p(g.contiguous()), a.shape[0], b.shape[0], a.shape[1], ctx.eps,
+              _p(ga))
+        return ga, None, None
+
+
+def cosine_matrix(a, b, eps=1e-8):
+    return _CosineMatrix.apply(a, b, eps)
+
+
+class _CEPair(torch.autograd.Function):
+    """(CrossEntropyLoss(scores, labels), CrossEntropyLoss(scores^T, labels), top-1 hits) with scores = gamma3 * sim and
+    the masked entries at -inf (ref: miscc/losses.py:50-68, 131-147)."""
+
+    @staticmethod
+    def forward(ctx, sim, mask, labels, gamma3):
+        _chk(sim, mask, labels)
+        sim = sim.contiguous()
+        b = sim.shape[0]
+        assert sim.shape == (b, b)
+        dev = sim.device
+        l0 = torch.empty((), device=dev, dtype=torch.float32)
+        l1 = torch.empty((), device=dev, dtype=torch.float32)
+        hits = torch.empty((), device=dev, dtype=torch.float32)
+        g0 = torch.empty((b, b), device=dev, dtype=torch.float32)
+        g1 = torch.empty((b, b), device=dev, dtype=torch.float32)
+        m = mask.contiguous() if mask is not None else None
+        _call("og_ce_pair", _p(sim), _p(m), _p(labels.contiguous()), b, float(gamma3), _p(l0), _p(l1), _p(g0), _p(g1),
+              _p(hits))
+        ctx.save_for_backward(g0, g1)
+        ctx.mark_non_differentiable(hits)
+        return l0, l1, hits
+
+    @staticmethod
+    def backward(ctx, gl0, gl1, _gc):
+        g0, g1 = ctx.saved_tensors
+        gsim = torch.empty_like(g0)
+        a = gl0.contiguous() if gl0 is not None else None
+        b = gl1.contiguous() if gl1 is not None else None
+        _call("og_ce_pair_bwd", _p(g0), _p(g1), _p(a), _p(b), g0.numel(), _p(gsim))
+        return gsim, None, None, None
+
+
+def ce_pair(sim, mask, labels, gamma3):
+    return _CEPair.apply(sim, mask, labels, gamma3)
 
 
 class _Bilinear(torch.autograd.Function):

@@ -523,6 +523,75 @@ def obj_d_loss(sd, real, fake, seg, raw_conditions, raw_bt_c_codes, fm_rois, num
 
 
 # --------------------------------------------------------------------------------------
+# DAMSM matching losses (miscc/losses.py:13-159)
+# --------------------------------------------------------------------------------------
+def cosine_similarity(x1, x2, dim=1, eps=1e-8):
+    """ref: miscc/losses.py:13-19."""
+    w12 = torch.sum(x1 * x2, dim)
+    w1 = torch.norm(x1, 2, dim)
+    w2 = torch.norm(x2, 2, dim)
+    return (w12 / (w1 * w2).clamp(min=eps)).squeeze()
+
+
+def _class_masks(class_ids, batch_size):
+    """ref: miscc/losses.py:27-38 / 86-89."""
+    if class_ids is None:
+        return None
+    ids = np.asarray(class_ids)
+    masks = []
+    for i in range(batch_size):
+        m = (ids == ids[i]).astype(np.uint8)
+        m[i] = 0
+        masks.append(m.reshape(1, -1))
+    return torch.from_numpy(np.concatenate(masks, 0)).bool()
+
+
+def _two_ce(scores0, labels, batch_size):
+    scores1 = scores0.transpose(0, 1)
+    loss0 = F.cross_entropy(scores0, labels)
+    loss1 = F.cross_entropy(scores1, labels)
+    correct = (scores0.max(1)[1] == labels).sum().item() + (scores1.max(1)[1] == labels).sum().item()
+    return loss0, loss1, 100.0 * correct / (batch_size * 2.0)
+
+
+def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, *, gamma3=10.0, eps=1e-8):
+    """ref: miscc/losses.py:22-71."""
+    masks = _class_masks(class_ids, batch_size)
+    if cnn_code.dim() == 2:
+        cnn_code, rnn_code = cnn_code.unsqueeze(0), rnn_code.unsqueeze(0)
+    cn = torch.norm(cnn_code, 2, dim=2, keepdim=True)
+    rn = torch.norm(rnn_code, 2, dim=2, keepdim=True)
+    scores0 = torch.bmm(cnn_code, rnn_code.transpose(1, 2))
+    norm0 = torch.bmm(cn, rn.transpose(1, 2))
+    scores0 = (scores0 / norm0.clamp(min=eps) * gamma3).squeeze(0)
+    if masks is not None:
+        scores0 = scores0.masked_fill(masks, -float("inf"))
+    return _two_ce(scores0, labels, batch_size)
+
+
+def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size, *, gamma1=4.0, gamma2=5.0,
+               gamma3=10.0):
+    """ref: miscc/losses.py:74-159.  Returns (loss0, loss1, att_maps, accuracy)."""
+    masks = _class_masks(class_ids, batch_size)
+    att_maps, sims = [], []
+    for i in range(batch_size):
+        n = int(cap_lens[i])
+        word = words_emb[i, :, :n].unsqueeze(0).contiguous().repeat(batch_size, 1, 1)
+        wei, attn = func_attention(word, img_features, gamma1)
+        att_maps.append(attn[i].unsqueeze(0).contiguous())
+        w = word.transpose(1, 2).contiguous().view(batch_size * n, -1)
+        c = wei.transpose(1, 2).contiguous().view(batch_size * n, -1)
+        row = cosine_similarity(w, c).view(batch_size, n)
+        row = torch.log((row * gamma2).exp().sum(dim=1, keepdim=True))
+        sims.append(row)
+    sim = torch.cat(sims, 1) * gamma3
+    if masks is not None:
+        sim = sim.masked_fill(masks, -float("inf"))
+    loss0, loss1, acc = _two_ce(sim, labels, batch_size)
+    return loss0, loss1, att_maps, acc
+
+
+# --------------------------------------------------------------------------------------
 # optimiser (trainer.py:197-224, 461-462)
 # --------------------------------------------------------------------------------------
 def adam_step(p, g, m, v, step, lr=2e-4, b1=0.5, b2=0.999, eps=1e-8):

@@ -604,3 +604,40 @@ def test_obj_d_loss_parity(cls, n_layer, large, monkeypatch):
         close_grad(params[k].grad, gr, what=k)
         checked += 1
     assert checked >= 10
+
+
+def test_damsm_losses_parity():
+    """DAMSM words_loss / sent_loss (ref: miscc/losses.py:22-159) around the fused func_attention: loss values,
+    attention maps, accuracy and the gradient reaching the image features / image code against the oracle."""
+    from objgan_b200 import losses
+    g = torch.Generator().manual_seed(19)
+    B, nef, T = 6, 256, 18
+    img = torch.randn(B, nef, 17, 17, generator=g)
+    words = torch.randn(B, nef, T, generator=g)
+    cnn = torch.randn(B, nef, generator=g)
+    rnn = torch.randn(B, nef, generator=g)
+    cap_lens = torch.tensor([18, 12, 9, 18, 5, 14])
+    labels = torch.arange(B)
+    class_ids = np.array([3, 7, 3, 1, 7, 9])
+    ir = img.clone().requires_grad_(True)
+    o0, o1, omaps, oacc = O.words_loss(ir, words, labels, cap_lens.tolist(), class_ids, B)
+    go = torch.autograd.grad(o0 + 2.0 * o1, ir)[0]
+    ig = img.to(DEV).requires_grad_(True)
+    w0, w1, maps, acc = losses.words_loss(ig, words.to(DEV), labels.to(DEV), cap_lens, class_ids, B)
+    close(w0, o0.detach(), what="w_loss0")
+    close(w1, o1.detach(), what="w_loss1")
+    assert abs(float(acc) - oacc) < 1e-4
+    for a, b in zip(maps, omaps):
+        close(a, b.detach(), what="att_map")
+    (w0 + 2.0 * w1).backward()
+    close_grad(ig.grad, go, what="g_img_features")
+    cr = cnn.clone().requires_grad_(True)
+    p0, p1, pacc = O.sent_loss(cr, rnn, labels, class_ids, B)
+    gp = torch.autograd.grad(p0 + 0.5 * p1, cr)[0]
+    cg = cnn.to(DEV).requires_grad_(True)
+    s0, s1, sacc = losses.sent_loss(cg, rnn.to(DEV), labels.to(DEV), class_ids, B)
+    close(s0, p0.detach(), what="s_loss0")
+    close(s1, p1.detach(), what="s_loss1")
+    assert abs(float(sacc) - pacc) < 1e-4
+    (s0 + 0.5 * s1).backward()
+    close_grad(cg.grad, gp, what="g_cnn_code")
