@@ -179,6 +179,8 @@ int og_copy_channels(const float* src, int sstride, int soff, float* dst, int ds
                      int accumulate, cudaStream_t stream);
 int og_broadcast_channels(const float* c, int B, int Cc, float* dst, int dstride, int doff, long long pix_per_img,
                           cudaStream_t stream);
+int og_broadcast_channels_bwd(const float* g, int B, int Cc, int gstride, int goff, long long pix_per_img, float* gc,
+                              cudaStream_t stream);   /* gc[b][k] = sum_pixels g[pixel][goff + k] */
 /* Row gather out[i,:] = x[idx[i],:] (idx: int64 device array) and its adjoint (gx zero-filled, then += g rows):
  * the roi compaction of feat_select (ref: miscc/utils.py:465-499) and the raw_conditions[classes] lookup of
  * objD_loss (ref: miscc/losses.py:280-281) without per-roi host loops. */

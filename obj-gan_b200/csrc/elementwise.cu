@@ -250,6 +250,28 @@ OG_API int og_copy_channels(const float* src, int sstride, int soff, float* dst,
   OG_RETURN_LAST_ERROR();
 }
 
+// adjoint of broadcast_channels w.r.t. the code: gc[b][k] = sum over the image's pixels of g[pixel][goff + k]
+// (needed when the conditioning code carries a gradient: the object-discriminator terms of G_loss, losses.py:436-452)
+__global__ void broadcast_channels_bwd_kernel(const float* __restrict__ g, int Cc, int gstride, int goff,
+                                              long long pix_per_img, long long total, float* __restrict__ gc) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / Cc;
+    const int k = (int)(i - b * Cc);
+    const float* src = g + b * pix_per_img * gstride + goff + k;
+    float acc = 0.f;
+    for (long long p = 0; p < pix_per_img; ++p) acc += src[p * gstride];
+    gc[i] = acc;
+  }
+}
+OG_API int og_broadcast_channels_bwd(const float* g, int B, int Cc, int gstride, int goff, long long pix_per_img,
+                                     float* gc, cudaStream_t stream) {
+  long long total = (long long)B * Cc;
+  if (total == 0) return 0;
+  broadcast_channels_bwd_kernel<<<eblocks(total), 256, 0, stream>>>(g, Cc, gstride, goff, pix_per_img, total, gc);
+  OG_RETURN_LAST_ERROR();
+}
+
 // row gather out[i, :] = x[idx[i], :] and its adjoint gx[idx[i], :] += g[i, :]  (feat_select's roi compaction,
 // ref: miscc/utils.py:465-499, and the raw_conditions[classes] lookup, miscc/losses.py:280-281, without host loops)
 __global__ void gather_rows_kernel(const float* __restrict__ x, const long long* __restrict__ idx, long long n_out,

@@ -240,3 +240,68 @@ def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size,
     loss0, loss1, correct = ops.ce_pair(sim, mask, labels, cfg.TRAIN.SMOOTH.GAMMA3)
     accuracy = correct * (100.0 / (batch_size * 2.0)) if top1 else None
     return loss0, loss1, att_maps, accuracy
+
+
+def _obj_g_term(netObjD, fake_img, seg, slabels_emb, raw_bt_c_codes, rois, num_rois, is_large_scale):
+    """One object-discriminator term of G_loss (ref: miscc/losses.py:436-478 / 481-523); None when no roi of that
+    scale class exists.  The generator's bt_c_code rows keep their gradient through the conditioning code."""
+    net = netObjD.module if hasattr(netObjD, "module") else netObjD
+    pooled = netObjD(fake_img, seg, rois, num_rois)
+    feats, classes, codes = feat_select(pooled, raw_bt_c_codes, rois, num_rois, is_large_scale)
+    if len(classes) == 0:
+        return None
+    idx = torch.as_tensor(classes, dtype=torch.int64, device=fake_img.device)
+    conditions = ops.cat_rows(ops.gather_rows(slabels_emb.detach(), idx), codes)
+    err = ops.bce(net.COND_DNET(feats, conditions), 1.0, 1.0)
+    if net.UNCOND_DNET is not None:
+        err = err + ops.bce(net.UNCOND_DNET(feats), 1.0, 1.0)
+    return err * cfg.TRAIN.SMOOTH.OBJ_LAMBDA
+
+
+def G_loss(netsPatD, netsShpD, netObjSSD, netObjLSD, image_encoder, fake_imgs, seg_conditions, words_embs, sent_emb,
+           slabels_emb, raw_bt_c_codes, match_labels, cap_lens, class_ids, rois, fm_rois, num_rois):
+    """ref: miscc/losses.py:364-531 -- the generator's full adversarial + matching loss: per scale the patch-D terms
+    (COND * TXT_LAMBDA + UNCOND * UNCOND_LAMBDA) and the shape-D term (SHP_LAMBDA); at the last scale the DAMSM
+    word / sentence matching terms through ``image_encoder`` (the pretrained Inception CNN_ENCODER: a stock PyTorch
+    module returning (region_features (B, nef, 17, 17), cnn_code (B, nef)); None skips the two terms); the small- and
+    large-scale object-D terms (OBJ_LAMBDA).  Returns (errG_total, logs) with ``logs`` a dict of device scalars instead
+    of the reference's formatted string (no per-step host synchronisation)."""
+    batch_size = fake_imgs[0].size(0)
+    ul, tl = cfg.TRAIN.SMOOTH.UNCOND_LAMBDA, cfg.TRAIN.SMOOTH.TXT_LAMBDA
+    logs = {}
+    total = None
+
+    def add(x):
+        nonlocal total
+        total = x if total is None else total + x
+
+    n_d = len(netsPatD)
+    for i in range(n_d):
+        features = netsPatD[i](fake_imgs[i])
+        cond, uncond = _heads(netsPatD[i])
+        pat = ops.bce(cond(features, sent_emb), 1.0, tl if uncond is not None else 1.0)
+        if uncond is not None:
+            pat = pat + ops.bce(uncond(features), 1.0, ul)
+        add(pat)
+        logs[f"pat_g_loss{i}"] = pat.detach()
+        shp_net = netsShpD[i].module if hasattr(netsShpD[i], "module") else netsShpD[i]
+        shp = ops.bce(shp_net.UNCOND_DNET(netsShpD[i](fake_imgs[i], seg_conditions[i])), 1.0, cfg.TRAIN.SMOOTH.SHP_LAMBDA)
+        add(shp)
+        logs[f"shp_g_loss{i}"] = shp.detach()
+        if i == n_d - 1 and image_encoder is not None:
+            region_features, cnn_code = image_encoder(fake_imgs[i])
+            w0, w1, _, _ = words_loss(region_features, words_embs, match_labels, cap_lens, class_ids, batch_size)
+            s0, s1, _ = sent_loss(cnn_code, sent_emb, match_labels, class_ids, batch_size)
+            w_loss = (w0 + w1) * cfg.TRAIN.SMOOTH.DAMSM_LAMBDA
+            s_loss = (s0 + s1) * cfg.TRAIN.SMOOTH.DAMSM_LAMBDA
+            add(w_loss + s_loss)
+            logs["w_loss"], logs["s_loss"] = w_loss.detach(), s_loss.detach()
+    ss = _obj_g_term(netObjSSD, fake_imgs[-1], seg_conditions[-1], slabels_emb, raw_bt_c_codes, rois, num_rois, False)
+    if ss is not None:
+        add(ss)
+        logs["objss_g_loss"] = ss.detach()
+    ls = _obj_g_term(netObjLSD, fake_imgs[-1], seg_conditions[-1], slabels_emb, raw_bt_c_codes, fm_rois, num_rois, True)
+    if ls is not None:
+        add(ls)
+        logs["objls_g_loss"] = ls.detach()
+    return total, logs

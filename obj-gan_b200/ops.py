@@ -731,8 +731,9 @@ def cat_rows_const(a, b):
 
 
 class _BroadcastCat(torch.autograd.Function):
-    """D_GET_LOGITS conditioning: cat(h, c_code broadcast over the grid) along channels (no grad to c_code,
-    which is the detached sentence embedding in every caller: miscc/losses.py:169-190, 375-377)."""
+    """D_GET_LOGITS conditioning: cat(h, c_code broadcast over the grid) along channels.  c_code is the detached
+    sentence embedding in the patch-D callers (miscc/losses.py:169-190, 375-377); in the object-discriminator terms of
+    G_loss it carries the generator's bt_c_code (losses.py:436-452), so its gradient is produced when asked for."""
 
     @staticmethod
     def forward(ctx, h, c_code):
@@ -747,7 +748,7 @@ class _BroadcastCat(torch.autograd.Function):
         P = n * hh * ww
         _call("og_copy_channels", _p(h), ch, 0, _p(out), cp, 0, ch, P, 0)
         _call("og_broadcast_channels", _p(c_code), n, cc, _p(out), cp, ch, hh * ww)
-        ctx.ch = ch
+        ctx.ch, ctx.cc = ch, cc
         return out
 
     @staticmethod
@@ -756,7 +757,33 @@ class _BroadcastCat(torch.autograd.Function):
         n, hh, ww, cp = g.shape
         gh = torch.empty((n, hh, ww, ctx.ch), device=g.device, dtype=torch.float32)
         _call("og_copy_channels", _p(g), cp, 0, _p(gh), ctx.ch, 0, ctx.ch, n * hh * ww, 0)
-        return gh, None
+        gc = None
+        if ctx.needs_input_grad[1]:
+            gc = torch.empty((n, ctx.cc), device=g.device, dtype=torch.float32)
+            _call("og_broadcast_channels_bwd", _p(g), n, ctx.cc, cp, ctx.ch, hh * ww, _p(gc))
+        return gh, gc
+
+
+class _CatRows(torch.autograd.Function):
+    """torch.cat((a, b), dim=1) of two 2-D tensors where only ``b`` carries a gradient."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.ca = a.shape[1]
+        return cat_rows_const(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        r, c = g.shape
+        cb = c - ctx.ca
+        gb = torch.empty((r, cb), device=g.device, dtype=torch.float32)
+        _call("og_copy_channels", _p(g), c, ctx.ca, _p(gb), cb, 0, cb, r, 0)
+        return None, gb
+
+
+def cat_rows(a_const, b):
+    return _CatRows.apply(a_const, b)
 
 
 def broadcast_cat(h, c_code):

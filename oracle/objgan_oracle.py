@@ -591,6 +591,60 @@ def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size,
     return loss0, loss1, att_maps, acc
 
 
+def _obj_g_term(sd, fake, seg, slabels_emb, raw_bt_c_codes, rois, num_rois, n_layer, is_large_scale, obj_lambda,
+                size_thrs, update):
+    """ref: miscc/losses.py:436-478 / 481-523."""
+    pooled = obj_d_net_forward(sd, fake, seg, np.asarray(rois), n_layer, update=update)
+    feats, classes, codes = feat_select(pooled, raw_bt_c_codes, rois, num_rois, is_large_scale, size_thrs)
+    if len(classes) == 0:
+        return None
+    cond = torch.cat((slabels_emb[torch.as_tensor(classes)], codes), 1)
+    err = bce(d_get_logits(feats, sd, "COND_DNET", cond, update), 1)
+    if "UNCOND_DNET.outlogits.0.weight" in sd:
+        err = err + bce(d_get_logits(feats, sd, "UNCOND_DNET", None, update), 1)
+    return err * obj_lambda
+
+
+def g_loss(sds_pat, sds_shp, sd_ss, sd_ls, image_encoder, fake_imgs, seg_conditions, words_embs, sent_emb, slabels_emb,
+           raw_bt_c_codes, match_labels, cap_lens, class_ids, rois, fm_rois, num_rois, *, uncond_lambda=1.0,
+           txt_lambda=0.1, shp_lambda=1.0, obj_lambda=0.1, damsm_lambda=100.0, size_thrs=16.0, update=True):
+    """G_loss (ref: miscc/losses.py:364-531) over state_dicts; ``image_encoder`` is any callable returning
+    (region_features, cnn_code) or None (no DAMSM terms).  Returns the total and a dict of the terms."""
+    B = fake_imgs[0].shape[0]
+    nums = [int(v) for v in num_rois]
+    terms = {}
+    total = 0
+    n_d = len(sds_pat)
+    for i in range(n_d):
+        f = pat_d_net(fake_imgs[i], sds_pat[i], update)
+        pat = bce(d_get_logits(f, sds_pat[i], "COND_DNET", sent_emb, update), 1)
+        if "UNCOND_DNET.outlogits.0.weight" in sds_pat[i]:
+            pat = bce(d_get_logits(f, sds_pat[i], "UNCOND_DNET", None, update), 1) * uncond_lambda + pat * txt_lambda
+        terms[f"pat_g_loss{i}"] = pat
+        total = total + pat
+        fs = shp_d_net(fake_imgs[i], seg_conditions[i], sds_shp[i], update)
+        shp = bce(d_get_logits(fs, sds_shp[i], "UNCOND_DNET", None, update), 1) * shp_lambda
+        terms[f"shp_g_loss{i}"] = shp
+        total = total + shp
+        if i == n_d - 1 and image_encoder is not None:
+            region, code = image_encoder(fake_imgs[i])
+            w0, w1, _, _ = words_loss(region, words_embs, match_labels, cap_lens, class_ids, B)
+            s0, s1, _ = sent_loss(code, sent_emb, match_labels, class_ids, B)
+            terms["w_loss"], terms["s_loss"] = (w0 + w1) * damsm_lambda, (s0 + s1) * damsm_lambda
+            total = total + terms["w_loss"] + terms["s_loss"]
+    ss = _obj_g_term(sd_ss, fake_imgs[-1], seg_conditions[-1], slabels_emb, raw_bt_c_codes, np.asarray(rois), nums, 3,
+                     False, obj_lambda, size_thrs, update)
+    if ss is not None:
+        terms["objss_g_loss"] = ss
+        total = total + ss
+    ls = _obj_g_term(sd_ls, fake_imgs[-1], seg_conditions[-1], slabels_emb, raw_bt_c_codes, np.asarray(fm_rois), nums,
+                     4, True, obj_lambda, size_thrs, update)
+    if ls is not None:
+        terms["objls_g_loss"] = ls
+        total = total + ls
+    return total, terms
+
+
 # --------------------------------------------------------------------------------------
 # optimiser (trainer.py:197-224, 461-462)
 # --------------------------------------------------------------------------------------

@@ -38,6 +38,39 @@ def sub(t, s):
     return t[..., ::s, ::s].contiguous().numpy()
 
 
+class StubEncoder(torch.nn.Module):
+    """Differentiable stand-in for the pretrained Inception CNN_ENCODER: (regions (B,256,17,17), code (B,256))."""
+
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(77)
+        self.weight = torch.nn.Parameter(torch.randn(256, 3, 1, 1, generator=g) * 0.5)
+        self.bias = torch.nn.Parameter(torch.randn(256, generator=g) * 0.1)
+
+    def forward(self, x):
+        r = torch.nn.functional.conv2d(torch.nn.functional.adaptive_avg_pool2d(x, 17), self.weight, self.bias)
+        return r, r.mean((2, 3))
+
+
+def g_loss_case(seed=404):
+    """Seeded full-G_loss case: the eight discriminators (objgan_b200 constructors on the CPU) and the inputs."""
+    torch.manual_seed(seed)
+    nets = dict(pat=[model.PAT_D_NET64(), model.PAT_D_NET128(), model.PAT_D_NET256()],
+                shp=[model.SHP_D_NET64(80), model.SHP_D_NET128(80), model.SHP_D_NET256(80)],
+                ss=model.OBJ_SS_D_NET(80), ls=model.OBJ_LS_D_NET(80))
+    for n in nets["pat"] + nets["shp"] + [nets["ss"], nets["ls"]]:
+        for p_ in n.parameters():          # cheap, seeded, well-scaled init (weights_init's QR is slow at this size)
+            if p_.dim() > 1:
+                p_.data.normal_(0.0, 1.0 / np.sqrt(p_[0].numel()))
+    inp = synth.make_inputs(2, seed=seed + 1, parity=True)
+    g = torch.Generator().manual_seed(seed + 2)
+    fakes = [torch.tanh(torch.randn(im.shape, generator=g)) for im in inp["imgs"]]
+    raw_bt = torch.randn(2, 10, 48, generator=g)
+    fm = inp["fm_rois"].clone()
+    fm[..., 2:4] *= torch.tensor([3.0, 0.6]).view(2, 1, 1)
+    return nets, inp, fakes, raw_bt, inp["rois"][0].clone(), fm, np.array([4, 9])
+
+
 def obj_d_case(ref, cls, seed=303):
     """Seeded object-discriminator case shared by the fixture generator (ref given: returns the reference net with the
     weights loaded) and the golden test (ref None: returns the state_dict)."""
@@ -152,6 +185,38 @@ def main():
             err = ref.losses.objD_loss(Net(), real, fake, seg, raw_cond, raw_bt, fm, nr, is_large_scale=large)
         res[cls] = float(err)
     np.savez_compressed(os.path.join(HERE, "obj_d_loss.npz"), err_ss=res["OBJ_SS_D_NET"], err_ls=res["OBJ_LS_D_NET"])
+    # ---- full G_loss (miscc/losses.py:364-531): the reference's function, patch / shape discriminators and logit heads;
+    # the object discriminators' bodies go through the (pinned, differentiable) oracle.obj_d_net_forward ------------
+    from oracle import objgan_oracle as O
+    torch.ByteTensor = lambda a: torch.from_numpy(np.asarray(a)).bool()      # torch 2: masked_fill_ wants bool masks
+    nets, inp, fakes, raw_bt, rois0, fm, class_ids = g_loss_case()
+    rnets = dict(pat=[ref.model.PAT_D_NET64(), ref.model.PAT_D_NET128(), ref.model.PAT_D_NET256()],
+                 shp=[ref.model.SHP_D_NET64(80), ref.model.SHP_D_NET128(80), ref.model.SHP_D_NET256(80)],
+                 ss=ref.model.OBJ_SS_D_NET(80), ls=ref.model.OBJ_LS_D_NET(80))
+    for k in ("pat", "shp"):
+        for a_, b_ in zip(rnets[k], nets[k]):
+            a_.load_state_dict(b_.state_dict(), strict=True)
+    rnets["ss"].load_state_dict(nets["ss"].state_dict(), strict=True)
+    rnets["ls"].load_state_dict(nets["ls"].state_dict(), strict=True)
+
+    def stand_in(net, n_layer):
+        sdict = {k: v.clone() for k, v in net.state_dict().items()}
+
+        class Net:
+            COND_DNET, UNCOND_DNET = net.COND_DNET, net.UNCOND_DNET
+
+            def __call__(self, x, s, f, n):
+                return O.obj_d_net_forward(sdict, x, s, f.numpy(), n_layer, update=False)
+        return Net()
+
+    fk = [f.clone().requires_grad_(True) for f in fakes]
+    bt = raw_bt.clone().requires_grad_(True)
+    total, _ = ref.losses.G_loss(rnets["pat"], rnets["shp"], stand_in(rnets["ss"], 3), stand_in(rnets["ls"], 4),
+                                 StubEncoder(), fk, inp["hmaps"], inp["words_embs"], inp["sent_emb"], inp["clabels_emb"],
+                                 bt, torch.arange(2), inp["cap_lens"], class_ids, rois0, fm, inp["num_rois"])
+    grads = torch.autograd.grad(total, fk + [bt])
+    np.savez_compressed(os.path.join(HERE, "g_loss.npz"), total=float(total), g64=grads[0].numpy(),
+                        g128=sub(grads[1], 2), g256=sub(grads[2], 4), gbt=grads[3].numpy())
     print("golden fixtures written to", HERE)
 
 

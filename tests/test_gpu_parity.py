@@ -641,3 +641,35 @@ def test_damsm_losses_parity():
     assert abs(float(sacc) - pacc) < 1e-4
     (s0 + 0.5 * s1).backward()
     close_grad(cg.grad, gp, what="g_cnn_code")
+
+
+def test_g_loss_full_parity(monkeypatch):
+    """The generator's full loss (ref: miscc/losses.py:364-531: patch-D, shape-D, object-D small / large scale and the
+    DAMSM word / sentence terms) -- value and the gradients reaching the three fake images and the generator's
+    bt_c_code -- against the fixture the reference's own G_loss produced (tests/golden/g_loss.npz).  The image
+    encoder is the stock-PyTorch stub of the fixture (the pretrained Inception encoder stays a stock module)."""
+    import os
+    import sys
+    from objgan_b200 import losses
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    monkeypatch.setattr(ops, "CONV_ENGINE", "simt")
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g_loss.npz"))
+    nets, inp, fakes, raw_bt, rois0, fm, class_ids = make_golden.g_loss_case()
+    for n in nets["pat"] + nets["shp"] + [nets["ss"], nets["ls"]]:
+        n.to(DEV)
+    enc = make_golden.StubEncoder().to(DEV)
+    fk = [f.to(DEV).requires_grad_(True) for f in fakes]
+    bt = raw_bt.to(DEV).requires_grad_(True)
+    total, logs = losses.G_loss(nets["pat"], nets["shp"], nets["ss"], nets["ls"], enc, fk,
+                                [h.to(DEV) for h in inp["hmaps"]], inp["words_embs"].to(DEV), inp["sent_emb"].to(DEV),
+                                inp["clabels_emb"].to(DEV), bt, torch.arange(2, device=DEV), inp["cap_lens"], class_ids,
+                                rois0, fm, inp["num_rois"])
+    assert {"objss_g_loss", "objls_g_loss", "w_loss", "s_loss"} <= set(logs)
+    want = float(gold["total"])
+    assert abs(float(total) - want) <= 1e-4 * max(1.0, abs(want)), (float(total), want)
+    total.backward()
+    close_grad(fk[0].grad, torch.from_numpy(gold["g64"]), what="g_fake64")
+    close_grad(fk[1].grad[..., ::2, ::2], torch.from_numpy(gold["g128"]), what="g_fake128")
+    close_grad(fk[2].grad[..., ::4, ::4], torch.from_numpy(gold["g256"]), what="g_fake256")
+    close_grad(bt.grad, torch.from_numpy(gold["gbt"]), what="g_bt_c_code")

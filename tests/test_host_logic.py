@@ -108,3 +108,30 @@ def test_obj_and_damsm_loss_wiring(dry):
     s0, s1, sacc = losses.sent_loss(cnn, torch.randn(B, nef), labels, None, B)
     (s0 + s1).backward()
     assert cnn.grad.shape == cnn.shape
+
+
+def test_g_loss_wiring(dry):
+    """The full G_loss runs through every discriminator family and the DAMSM terms and back-propagates to the fake images
+    and the generator's bt_c_code (DRY_RUN: argument counts and autograd wiring only)."""
+    import numpy as np
+    from objgan_b200 import losses
+    inp = synth.make_inputs(2, seed=5, parity=True)
+    pat = [model.PAT_D_NET64(), model.PAT_D_NET128(), model.PAT_D_NET256()]
+    shp = [model.SHP_D_NET64(80), model.SHP_D_NET128(80), model.SHP_D_NET256(80)]
+    fk = [torch.tanh(torch.randn_like(im)).requires_grad_(True) for im in inp["imgs"]]
+    bt = torch.randn(2, 10, cfg.GAN.GF_DIM, requires_grad=True)
+
+    class Enc(torch.nn.Module):
+        def forward(self, x):
+            r = torch.nn.functional.adaptive_avg_pool2d(x, 17).repeat(1, 86, 1, 1)[:, :256]
+            return r, r.mean((2, 3))
+
+    fm = inp["fm_rois"].clone()
+    fm[..., 2:4] *= torch.tensor([3.0, 0.6]).view(2, 1, 1)
+    total, logs = losses.G_loss(pat, shp, model.OBJ_SS_D_NET(80), model.OBJ_LS_D_NET(80), Enc(), fk, inp["hmaps"],
+                                inp["words_embs"], inp["sent_emb"], inp["clabels_emb"], bt, torch.arange(2),
+                                inp["cap_lens"], np.array([4, 9]), inp["rois"][0], fm, inp["num_rois"])
+    assert "pat_g_loss2" in logs and "shp_g_loss0" in logs and "w_loss" in logs
+    total.backward()
+    assert all(f.grad is not None and f.grad.shape == f.shape for f in fk)
+    assert ("objss_g_loss" not in logs and "objls_g_loss" not in logs) or bt.grad is not None

@@ -79,6 +79,28 @@ def test_obj_d_loss_golden(cls, n_layer, large, key):
     assert abs(float(got) - want) <= 2e-5 * max(1.0, abs(want)), (float(got), want)
 
 
+def test_g_loss_golden():
+    """oracle.g_loss (all patch / shape / object discriminator terms + DAMSM terms) against the total and the
+    gradients the reference's own G_loss produced (fixture made by make_golden.py)."""
+    gold = np.load(os.path.join(GOLD, "g_loss.npz"))
+    nets, inp, fakes, raw_bt, rois0, fm, class_ids = make_golden.g_loss_case()
+    sd = lambda n: {k: v.clone() for k, v in n.state_dict().items()}
+    fk = [f.clone().requires_grad_(True) for f in fakes]
+    bt = raw_bt.clone().requires_grad_(True)
+    total, terms = O.g_loss([sd(n) for n in nets["pat"]], [sd(n) for n in nets["shp"]], sd(nets["ss"]), sd(nets["ls"]),
+                            make_golden.StubEncoder(), fk, inp["hmaps"], inp["words_embs"], inp["sent_emb"],
+                            inp["clabels_emb"], bt, torch.arange(2), inp["cap_lens"].tolist(), class_ids, rois0.numpy(),
+                            fm.numpy(), inp["num_rois"].tolist(), update=False)
+    assert {"objss_g_loss", "objls_g_loss", "w_loss", "s_loss"} <= set(terms)        # every branch is exercised
+    want = float(gold["total"])
+    assert abs(float(total) - want) <= 1e-5 * max(1.0, abs(want)), (float(total), want)
+    grads = torch.autograd.grad(total, fk + [bt])
+    _close(grads[0].numpy(), gold["g64"], 1e-4)
+    _close(grads[1][..., ::2, ::2].numpy(), gold["g128"], 1e-4)
+    _close(grads[2][..., ::4, ::4].numpy(), gold["g256"], 1e-4)
+    _close(grads[3].numpy(), gold["gbt"], 1e-4)
+
+
 def test_attention_golden():
     gold = np.load(os.path.join(GOLD, "attention.npz"))
     W = torch.randn(48, 256, 1, 1, generator=torch.Generator().manual_seed(1)) * 0.1
