@@ -121,8 +121,8 @@ def feat_select(pooled_feat, raw_bt_c_codes, fm_rois, num_rois, is_large_scale=F
     import numpy as np
     fm = fm_rois.detach().cpu().numpy() if torch.is_tensor(fm_rois) else np.asarray(fm_rois)
     nums = num_rois.detach().cpu().numpy().tolist() if torch.is_tensor(num_rois) else list(num_rois)
-    boxes = pooled_feat.shape[1]
-    flat, classes = [], []
+    boxes, code_slots = pooled_feat.shape[1], raw_bt_c_codes.shape[1]
+    flat, flat_c, classes = [], [], []
     for b in range(len(nums)):
         for r in range(int(nums[b])):
             _, _, width, height = fm[b, r, :4]
@@ -132,12 +132,14 @@ def feat_select(pooled_feat, raw_bt_c_codes, fm_rois, num_rois, is_large_scale=F
             if big != bool(is_large_scale):
                 continue
             flat.append(b * boxes + r)
+            flat_c.append(b * code_slots + r)      # the generator's bt_c_code has max(num_rois) slots, not BOXES_NUM
             classes.append(int(fm[b, r, 4]))
     if not flat:
         return [], [], []
     idx = torch.as_tensor(flat, dtype=torch.int64, device=pooled_feat.device)
+    idx_c = torch.as_tensor(flat_c, dtype=torch.int64, device=pooled_feat.device)
     feats = ops.gather_rows(pooled_feat.reshape((-1,) + tuple(pooled_feat.shape[2:])), idx)
-    codes = ops.gather_rows(raw_bt_c_codes.reshape(-1, raw_bt_c_codes.shape[-1]), idx)
+    codes = ops.gather_rows(raw_bt_c_codes.reshape(-1, raw_bt_c_codes.shape[-1]), idx_c)
     return feats, np.asarray(classes, dtype=np.int64), codes
 
 

@@ -320,3 +320,84 @@ def pin(inp: dict) -> dict:
         else:
             out[k] = v
     return out
+
+
+class StepBTrainer(StepATrainer):
+    """The reference's complete training step (ref: trainer.py:385-462): generator forward, then the updates of the three
+    patch discriminators, the three shape discriminators, the small- and large-scale object discriminators, and the
+    generator update through all eight of them (+ the DAMSM terms when an ``image_encoder`` is given + KL) with the
+    fused Adam + EMA.  The box filter of ``feat_select`` and the shuffles of ``permute_seg`` are host decisions (as in
+    the reference), so this step runs eagerly; Step-A (the data-parallel hot path of the bench) is the captured one."""
+
+    def __init__(self, num_classes=80, device="cuda", process_group=None, seed=None, image_encoder=None):
+        super().__init__(num_classes, device, process_group, seed)
+        n = cfg.TREE.BRANCH_NUM
+        self.netsShpD = [model.SHP_D_NET64(num_classes), model.SHP_D_NET128(num_classes),
+                         model.SHP_D_NET256(num_classes)][:n]
+        self.netObjSSD, self.netObjLSD = model.OBJ_SS_D_NET(num_classes), model.OBJ_LS_D_NET(num_classes)
+        for d in [*self.netsShpD, self.netObjSSD, self.netObjLSD]:
+            d.apply(model.weights_init)
+            d.to(self.device)
+        self.bShp = [FlatBucket(d) for d in self.netsShpD]
+        self.bObj = [FlatBucket(self.netObjSSD), FlatBucket(self.netObjLSD)]
+        self.image_encoder = image_encoder        # pretrained CNN_ENCODER (stock PyTorch, frozen); None: no DAMSM terms
+        if image_encoder is not None:
+            for p in image_encoder.parameters():
+                p.requires_grad_(False)
+
+    def _d_buckets(self):
+        return [*self.bD, *self.bShp, *self.bObj]
+
+    def _update(self, bucket, err, lr, gs):
+        """backward + (all-reduce) + Adam for one discriminator; ``err`` may be the int 0 of an empty roi set."""
+        if not torch.is_tensor(err):
+            return None
+        err.backward()
+        w = self._allreduce(bucket)
+        if w is not None:
+            w.wait()
+        bucket.adam(lr, gs)
+        return err.detach()
+
+    def step(self, inp: dict, class_ids=None) -> dict:
+        lr_d, lr_g = cfg.TRAIN.DISCRIMINATOR_LR, cfg.TRAIN.GENERATOR_LR
+        gs = 1.0 / self.world
+        sent, imgs, hmaps, rois = inp["sent_emb"], inp["imgs"], inp["hmaps"], inp["rois"]
+        fm_rois, num_rois = inp["fm_rois"], inp["num_rois"]
+        host = lambda t: t.detach().cpu() if torch.is_tensor(t) else t      # box tables are read on the host
+        rois_h, fm_h, nr_h = [host(r) for r in rois], host(fm_rois), host(num_rois)
+        self.bG.requires_grad_(True)
+        fake_imgs, bt_c_codes, _att, _bt_att, mu, logvar = self.generate(inp)
+        out = {}
+        for b in self._d_buckets():
+            b.requires_grad_(True)
+            b.zero_grad()
+        # (3-1) patch discriminators, (3-2) shape discriminators
+        for i, (d, b) in enumerate(zip(self.netsPatD, self.bD)):
+            out[f"errPatD{i}"] = self._update(b, losses.patD_loss(d, imgs[i], fake_imgs[i], sent), lr_d, gs)
+        for i, (d, b) in enumerate(zip(self.netsShpD, self.bShp)):
+            out[f"errShpD{i}"] = self._update(b, losses.shpD_loss(d, imgs[i], fake_imgs[i], hmaps[i], rois_h[i], nr_h),
+                                              lr_d, gs)
+        # (3-3) / (3-4) object discriminators (small scale on the 64-scale boxes, large scale on the feature-map boxes)
+        codes = bt_c_codes[-1].detach()
+        out["errObjSSD"] = self._update(self.bObj[0], losses.objD_loss(
+            self.netObjSSD, imgs[-1], fake_imgs[-1], hmaps[-1], inp["clabels_emb"], codes, rois_h[0], nr_h), lr_d, gs)
+        out["errObjLSD"] = self._update(self.bObj[1], losses.objD_loss(
+            self.netObjLSD, imgs[-1], fake_imgs[-1], hmaps[-1], inp["clabels_emb"], codes, fm_h, nr_h,
+            is_large_scale=True), lr_d, gs)
+        # (4) generator
+        for b in self._d_buckets():
+            b.requires_grad_(False)
+        self.bG.zero_grad()
+        labels = torch.arange(fake_imgs[0].size(0), device=fake_imgs[0].device)
+        err_g, logs = losses.G_loss(self.netsPatD, self.netsShpD, self.netObjSSD, self.netObjLSD, self.image_encoder,
+                                    fake_imgs, hmaps, inp["words_embs"], sent, inp["clabels_emb"], bt_c_codes[-1], labels,
+                                    inp["cap_lens"], class_ids, rois_h[0], fm_h, nr_h)
+        kl = losses.KL_loss(mu, logvar)
+        (err_g + kl).backward()
+        w = self._allreduce(self.bG)
+        if w is not None:
+            w.wait()
+        self.bG.adam(lr_g, gs)
+        out.update(errG=err_g.detach(), kl=kl.detach(), logs=logs, fake_imgs=[f.detach() for f in fake_imgs])
+        return out

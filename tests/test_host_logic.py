@@ -135,3 +135,19 @@ def test_g_loss_wiring(dry):
     total.backward()
     assert all(f.grad is not None and f.grad.shape == f.shape for f in fk)
     assert ("objss_g_loss" not in logs and "objls_g_loss" not in logs) or bt.grad is not None
+
+
+def test_step_b_wiring(dry):
+    """The complete step (all nine optimisers) on the CPU in DRY_RUN: every bucket steps once, every parameter of every
+    network is a view of its bucket with a gradient view, and the library call arities hold on every path."""
+    t = trainer.StepBTrainer(device="cpu", seed=0)
+    inp = synth.make_inputs(2, parity=True)
+    import random
+    random.seed(1)
+    out = t.step(inp)
+    assert out["errG"].dim() == 0 and "pat_g_loss0" in out["logs"] and "shp_g_loss2" in out["logs"]
+    assert t.bG.step == 1 and all(b.step == 1 for b in [*t.bD, *t.bShp])
+    assert all(b.step in (0, 1) for b in t.bObj)       # an object discriminator only steps when it saw rois of its scale
+    for b in [t.bG, *t._d_buckets()]:
+        for p, o in zip(b.params, b.offsets):
+            assert p.data.data_ptr() == b.flat[o:].data_ptr() and p.grad.data_ptr() == b.grad[o:].data_ptr()
