@@ -26,6 +26,18 @@ from .ops import cpad
 # --------------------------------------------------------------------------------------------------
 # parameter holders (leaf modules).  Their attribute names give the reference's state_dict keys.
 # --------------------------------------------------------------------------------------------------
+# Host-logic tests build dozens of networks on the CPU and never look at the values: they may swap the reference's
+# orthogonal initialisation (a QR per weight, seconds for the large layers) for a plain normal draw.
+FAST_INIT = False
+
+
+def _init_weight(w):
+    if FAST_INIT:
+        w.normal_(0.0, 0.02)
+    else:
+        nn.init.orthogonal_(w, 1.0)
+
+
 class Conv2dP(nn.Module):
     """Holds an OIHW ``weight`` (+ optional ``bias``) like nn.Conv2d; forward is an NHWC kernel call."""
 
@@ -35,7 +47,7 @@ class Conv2dP(nn.Module):
         self.bias = nn.Parameter(torch.empty(cout)) if bias else None
         self.stride, self.pad, self.mode, self.act, self.split = stride, pad, mode, act, split
         self._cache = ops.PackedWeights()
-        nn.init.orthogonal_(self.weight.data, 1.0)
+        _init_weight(self.weight.data)
         if bias:
             bound = 1.0 / np.sqrt(cin * k * k)
             nn.init.uniform_(self.bias.data, -bound, bound)
@@ -54,7 +66,7 @@ class LinearP(nn.Module):
         self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
         self.split = split
         self._cache = ops.PackedWeights()
-        nn.init.orthogonal_(self.weight.data, 1.0)
+        _init_weight(self.weight.data)
 
     def forward(self, x2d):
         b = x2d.shape[0]
@@ -97,7 +109,7 @@ class _Slots(nn.Module):
 def weights_init(m):
     """Mirror of miscc/utils.py:309-319 for this package's parameter holders."""
     if isinstance(m, (Conv2dP, LinearP)):
-        nn.init.orthogonal_(m.weight.data, 1.0)
+        _init_weight(m.weight.data)
         if isinstance(m, LinearP) and m.bias is not None:
             m.bias.data.fill_(0.0)
     elif isinstance(m, BatchNormP):

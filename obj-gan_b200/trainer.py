@@ -348,16 +348,36 @@ class StepBTrainer(StepATrainer):
     def _d_buckets(self):
         return [*self.bD, *self.bShp, *self.bObj]
 
+    def broadcast_parameters(self):
+        super().broadcast_parameters()
+        if self.world > 1:
+            for b in [*self.bShp, *self.bObj]:
+                dist.broadcast(b.flat, src=0, group=self.pg)
+            for m in [*self.netsShpD, self.netObjSSD, self.netObjLSD]:
+                for buf in m.buffers():
+                    dist.broadcast(buf, src=0, group=self.pg)
+            ops.bump_param_epoch()
+
     def _update(self, bucket, err, lr, gs):
-        """backward + (all-reduce) + Adam for one discriminator; ``err`` may be the int 0 of an empty roi set."""
-        if not torch.is_tensor(err):
+        """backward + all-reduce + Adam for one discriminator.  ``err`` may be the int 0 of an empty roi set (the
+        reference then skips the optimiser step, trainer.py:428-431); with several ranks the exchange must stay
+        collective, so the ranks first agree whether ANY of them has a loss, and a rank without one contributes a
+        zero gradient."""
+        mine = torch.is_tensor(err)
+        anyone = mine
+        if self.world > 1:
+            flag = torch.tensor([1.0 if mine else 0.0], device=bucket.flat.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.SUM, group=self.pg)
+            anyone = bool(flag.item() > 0)
+        if mine:
+            err.backward()
+        if not anyone:
             return None
-        err.backward()
         w = self._allreduce(bucket)
         if w is not None:
             w.wait()
         bucket.adam(lr, gs)
-        return err.detach()
+        return err.detach() if mine else None
 
     def step(self, inp: dict, class_ids=None) -> dict:
         lr_d, lr_g = cfg.TRAIN.DISCRIMINATOR_LR, cfg.TRAIN.GENERATOR_LR

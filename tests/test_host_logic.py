@@ -11,8 +11,10 @@ from objgan_b200.config import cfg
 @pytest.fixture()
 def dry():
     lib.DRY_RUN = True
+    model.FAST_INIT = True        # DRY_RUN never looks at values: skip the QR-based orthogonal initialisation
     yield
     lib.DRY_RUN = False
+    model.FAST_INIT = False
 
 
 def test_step_a_wiring(dry):
