@@ -739,3 +739,92 @@ def step_a(state: StepAState, inp: dict, *, lr=2e-4, keep=None):
         keep["g_grads"] = dict(zip(state.g_keys, ggrads))
         keep["d_grads"] = d_grads
     return losses
+
+
+# --------------------------------------------------------------------------------------
+# Step-B: the reference's complete step (trainer.py:385-462) -- SURVEY.md section 8, row a21 in full
+# --------------------------------------------------------------------------------------
+def shp_d_loss(sd, real, fake, seg, rois, num_rois, update=True):
+    """ref: miscc/losses.py:213-251 (shpD_loss): real / fake / permuted-shape terms on the UNCOND head."""
+    rf = shp_d_net(real, seg, sd, update)
+    ff = shp_d_net(fake.detach(), seg, sd, update)
+    fake_seg, valid = permute_seg(seg, rois, [int(v) for v in num_rois])
+    err = bce(d_get_logits(rf, sd, "UNCOND_DNET", None, update), 1)
+    fake_err = bce(d_get_logits(ff, sd, "UNCOND_DNET", None, update), 0)
+    if len(valid) > 0:
+        wrong = shp_d_net(real[valid], fake_seg[valid], sd, update)
+        return err + (fake_err + bce(d_get_logits(wrong, sd, "UNCOND_DNET", None, update), 0)) / 2.0
+    return err + fake_err
+
+
+class StepBState(StepAState):
+    """StepAState + the three shape discriminators and the two object discriminators with their Adam moments."""
+
+    def __init__(self, g_sd, d_sds, shp_sds, ss_sd, ls_sd):
+        super().__init__(g_sd, d_sds)
+        self.extra = [{k: v.clone() for k, v in sd.items()} for sd in [*shp_sds, ss_sd, ls_sd]]
+        self.x_keys = [trainable_keys(sd) for sd in self.extra]
+        z = lambda sd, keys: {k: torch.zeros_like(sd[k]) for k in keys}
+        self.x_m = [z(sd, k) for sd, k in zip(self.extra, self.x_keys)]
+        self.x_v = [z(sd, k) for sd, k in zip(self.extra, self.x_keys)]
+        self.x_step = [0] * len(self.extra)          # an object discriminator only steps when it has a loss
+
+
+def step_b(state: StepBState, inp: dict, *, image_encoder=None, class_ids=None, lr=2e-4):
+    """One complete step on the CPU: G forward; PatD x3, ShpD x3, ObjSS, ObjLS updates; G update through all of them
+    (+ DAMSM terms when ``image_encoder`` is given) + KL; EMA.  Host randomness (permute_seg) is drawn from Python's
+    ``random`` in exactly this order, which is also the product's order."""
+    state.step += 1
+    t = state.step
+    g_live, g_leaves = _with_grad(state.g, state.g_keys)
+    fake, btc, _att, _btatt, mu, logvar = g_net_forward(g_live, inp)
+    for k, v in g_live.items():
+        if k not in g_leaves:
+            state.g[k] = v
+    losses = {}
+    sent, imgs, hmaps = inp["sent_emb"], inp["imgs"], inp["hmaps"]
+    rois = [np.asarray(r) for r in inp["rois"]]
+    fm, nums = np.asarray(inp["fm_rois"]), [int(v) for v in inp["num_rois"]]
+
+    def d_update(sd, keys, m, v, loss_fn, step):
+        live, leaves = _with_grad(sd, keys)
+        err = loss_fn(live)
+        if not torch.is_tensor(err):
+            return None
+        grads = torch.autograd.grad(err, [leaves[k] for k in keys], allow_unused=True)
+        for k, val in live.items():
+            if k not in leaves:
+                sd[k] = val
+        for k, gk in zip(keys, grads):
+            adam_step(sd[k], gk if gk is not None else torch.zeros_like(sd[k]), m[k], v[k], step, lr)
+        return float(err.detach())
+
+    for i, d in enumerate(state.ds):
+        losses[f"errPatD{i}"] = d_update(d, state.d_keys[i], state.d_m[i], state.d_v[i],
+                                         lambda live, i=i: pat_d_loss(live, imgs[i], fake[i], sent), t)
+    for i in range(3):
+        losses[f"errShpD{i}"] = d_update(state.extra[i], state.x_keys[i], state.x_m[i], state.x_v[i],
+                                         lambda live, i=i: shp_d_loss(live, imgs[i], fake[i], hmaps[i], rois[i], nums), t)
+        state.x_step[i] += 1
+    codes = btc[-1].detach()
+    for j, (name, boxes, n_layer, large) in enumerate((("errObjSSD", rois[0], 3, False), ("errObjLSD", fm, 4, True))):
+        idx = 3 + j
+        nxt = state.x_step[idx] + 1
+        res = d_update(state.extra[idx], state.x_keys[idx], state.x_m[idx], state.x_v[idx],
+                       lambda live: obj_d_loss(live, imgs[-1], fake[-1], hmaps[-1], inp["clabels_emb"], codes, boxes, nums,
+                                               n_layer, is_large_scale=large), nxt)
+        if res is not None:
+            state.x_step[idx] = nxt
+        losses[name] = res
+    labels = torch.arange(fake[0].shape[0])
+    errg, terms = g_loss(state.ds, state.extra[:3], state.extra[3], state.extra[4], image_encoder, fake, hmaps,
+                         inp["words_embs"], sent, inp["clabels_emb"], btc[-1], labels,
+                         [int(v) for v in inp["cap_lens"]], class_ids, rois[0], fm, nums)
+    kl = kl_loss(mu, logvar)
+    ggrads = torch.autograd.grad(errg + kl, [g_leaves[k] for k in state.g_keys])
+    for k, gk in zip(state.g_keys, ggrads):
+        adam_step(state.g[k], gk, state.g_m[k], state.g_v[k], t, lr)
+        ema_update(state.g_avg[k], state.g[k])
+    losses["errG"], losses["kl"] = float(errg), float(kl)
+    losses["terms"] = {k: float(v) for k, v in terms.items()}
+    return losses

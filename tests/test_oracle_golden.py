@@ -202,3 +202,38 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def test_step_b_oracle_composition():
+    """oracle.step_b is the composition of the individually pinned pieces: its first discriminator losses equal
+    pat_d_loss / shp_d_loss / obj_d_loss evaluated directly on the initial weights with the same shuffles, and its
+    generator loss equals g_loss on the updated discriminators."""
+    import random
+    from objgan_b200 import model
+    model.FAST_INIT = True
+    try:
+        torch.manual_seed(0)
+        nets = [model.G_NET(80), model.PAT_D_NET64(), model.PAT_D_NET128(), model.PAT_D_NET256(), model.SHP_D_NET64(80),
+                model.SHP_D_NET128(80), model.SHP_D_NET256(80), model.OBJ_SS_D_NET(80), model.OBJ_LS_D_NET(80)]
+    finally:
+        model.FAST_INIT = False
+    for n in nets:
+        for p in n.parameters():
+            if p.dim() > 1:
+                p.data.normal_(0.0, 1.0 / np.sqrt(p[0].numel()))
+    sd = lambda n: {k: v.clone() for k, v in n.state_dict().items()}
+    st = O.StepBState(sd(nets[0]), [sd(n) for n in nets[1:4]], [sd(n) for n in nets[4:7]], sd(nets[7]), sd(nets[8]))
+    inp = make_golden.synth.make_inputs(2, seed=4, parity=True)
+    with torch.no_grad():
+        fake = O.g_net_forward(sd(nets[0]), inp)[0]
+        random.seed(5)
+        want_pat = float(O.pat_d_loss(sd(nets[1]), inp["imgs"][0], fake[0], inp["sent_emb"]))
+        want_shp = float(O.shp_d_loss(sd(nets[4]), inp["imgs"][0], fake[0], inp["hmaps"][0], inp["rois"][0].numpy(),
+                                      inp["num_rois"].tolist()))
+    random.seed(5)
+    out = O.step_b(st, inp)
+    assert abs(out["errPatD0"] - want_pat) < 1e-5 and abs(out["errShpD0"] - want_shp) < 1e-5
+    assert st.step == 1 and st.x_step[:3] == [1, 1, 1]
+    assert all(np.isfinite(v) for k, v in out.items() if isinstance(v, float))
+    total = sum(out["terms"].values())
+    assert abs(total - out["errG"]) < 1e-4 * max(1.0, abs(out["errG"]))
