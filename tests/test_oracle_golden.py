@@ -237,3 +237,41 @@ def test_step_b_oracle_composition():
     assert all(np.isfinite(v) for k, v in out.items() if isinstance(v, float))
     total = sum(out["terms"].values())
     assert abs(total - out["errG"]) < 1e-4 * max(1.0, abs(out["errG"]))
+
+
+def test_roi_align_edge_cases_bit_exact():
+    """Edge cases against the reference's roi_align.c compiled verbatim (oracle/_ref, build container): boxes partly or
+    entirely outside the map, inverted and zero-area boxes, sub-pixel boxes, a box covering the whole map, an empty roi
+    list -- numpy and C restatements must agree with it bit for bit (ref: roi_align.c:80-150)."""
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libroi_align_ref_cpu.so")
+    if not os.path.exists(ref_so):
+        pytest.skip("oracle/_ref not built (the reference sources are absent)")
+    r, c = ctypes.CDLL(ref_so), _c_oracle()
+    fp = ctypes.POINTER(ctypes.c_float)
+    rng = np.random.default_rng(5)
+    C, H, W = 3, 12, 20
+    feat = rng.standard_normal((2, C, H, W)).astype(np.float32)
+    s = 16.0
+    boxes = [
+        [0, -40.0, -40.0, 60.0, 70.0],                 # hangs over the top-left corner
+        [1, 250.0, 150.0, 400.0, 300.0],               # hangs over the bottom-right corner
+        [0, 500.0, 500.0, 600.0, 600.0],               # entirely outside
+        [1, -300.0, -300.0, -100.0, -100.0],           # entirely outside (negative)
+        [0, 100.0, 80.0, 40.0, 20.0],                  # inverted (x2 < x1, y2 < y1)
+        [1, 64.0, 64.0, 64.0, 64.0],                   # zero area
+        [0, 33.3, 17.7, 33.9, 18.1],                   # sub-pixel
+        [1, 0.0, 0.0, (W - 1) * s, (H - 1) * s],       # the whole map, corners exactly on the last samples
+        [0, 0.0, 0.0, W * s, H * s],                   # one cell past the map
+    ]
+    rois = np.asarray(boxes, dtype=np.float32)
+    for ah, aw in ((6, 6), (3, 5), (2, 2)):
+        want = np.zeros((len(boxes), C, ah, aw), dtype=np.float32)
+        r.ROIAlignForwardCpu(feat.ctypes.data_as(fp), ctypes.c_float(1.0 / s), len(boxes), H, W, C, ah, aw,
+                             rois.ctypes.data_as(fp), want.ctypes.data_as(fp))
+        assert np.array_equal(O.roi_align_forward_np(feat, rois, ah, aw, 1.0 / s), want), (ah, aw)
+        out = np.zeros_like(want)
+        c.og_oracle_roi_align_forward(feat.ctypes.data_as(fp), ctypes.c_float(1.0 / s), len(boxes), H, W, C, ah, aw,
+                                      rois.ctypes.data_as(fp), out.ctypes.data_as(fp))
+        assert np.array_equal(out, want), (ah, aw)
+    empty = np.zeros((0, 5), dtype=np.float32)
+    assert O.roi_align_forward_np(feat, empty, 6, 6, 1.0 / s).shape == (0, C, 6, 6)
