@@ -485,6 +485,11 @@ __global__ void __launch_bounds__(256) paint_max_fwd_kernel(const float* __restr
 OG_API int og_paint_max_fwd(const float* f, const float* m, int B, int num, int R, int Rtot, long long P, float* out,
                             int dstride, int doff, cudaStream_t stream) {
   if (B == 0 || P == 0) return 0;
+  if (R == 0) {   // no boxes in the whole batch: the painted maps are zero (ref: model.py:571-576, 689-694)
+    OG_CHECK(cudaMemset2DAsync(out + doff, sizeof(float) * (size_t)dstride, 0, sizeof(float) * (size_t)num,
+                               (size_t)B * (size_t)P, stream));
+    return 0;
+  }
   size_t sm = sizeof(float) * (num * R + R * PAINT_PIX);
   dim3 grid(og_cdiv(P, PAINT_PIX), B);
   paint_max_fwd_kernel<<<grid, 256, sm, stream>>>(f, m, num, R, Rtot, P, out, dstride, doff);
@@ -533,7 +538,7 @@ __global__ void __launch_bounds__(256) paint_max_bwd_kernel(const float* __restr
 OG_API int og_paint_max_bwd(const float* f, const float* m, const float* g, int gstride, int goff, int B, int num,
                             int R, int Rtot, long long P, float* g_f, cudaStream_t stream) {
   OG_CHECK(cudaMemsetAsync(g_f, 0, sizeof(float) * (size_t)B * num * R, stream));
-  if (B == 0 || P == 0) return 0;
+  if (B == 0 || P == 0 || R == 0) return 0;
   size_t sm = sizeof(float) * (2 * num * R + R * PAINT_PIX);
   dim3 grid(og_cdiv(P, PAINT_PIX), B);
   paint_max_bwd_kernel<<<grid, 256, sm, stream>>>(f, m, g, gstride, goff, num, R, Rtot, P, g_f);

@@ -306,6 +306,13 @@ def pprocess_bt_attns(fmaps, ih, iw, bt_mask):
 def _bt_branch(bt_att, slabels_feat, glove_word_embs, word_embs, mask, bt_mask, ef_dim2):
     """Shared by the INIT / NEXT stage mains (ref: model.py:552-569, 668-687)."""
     rmax = slabels_feat.shape[2]
+    if rmax == 0:
+        # ref: model.py:571-576 / 689-694 -- a batch without boxes contributes all-zero code / attention / label maps
+        # (the reference's INIT-stage `else` reads an undefined `att`; its intent, zeros, is what the NEXT stage does)
+        b, (ih, iw) = slabels_feat.shape[0], bt_mask.shape[2:]
+        z = lambda c: torch.zeros((b, ih, iw, ops.cpad(c)), device=bt_mask.device, dtype=torch.float32)
+        raw = torch.zeros((b, bt_att.idf, 0, 1), device=bt_mask.device, dtype=torch.float32)
+        return raw, z(bt_att.idf), z(mask.shape[1]), z(ef_dim2)
     bt_att.applyMask(mask)
     bt_c_code, bt_att_map = bt_att(slabels_feat, glove_word_embs, word_embs)          # (B,idf,R,1), (B,L,R,1)
     b = bt_c_code.shape[0]

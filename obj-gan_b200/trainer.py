@@ -388,6 +388,7 @@ class StepBTrainer(StepATrainer):
         rois_h, fm_h, nr_h = [host(r) for r in rois], host(fm_rois), host(num_rois)
         self.bG.requires_grad_(True)
         fake_imgs, bt_c_codes, _att, _bt_att, mu, logvar = self.generate(inp)
+        bt_c_codes = [c.detach() for c in bt_c_codes]       # ref: trainer.py:393 -- constants for every loss below
         out = {}
         for b in self._d_buckets():
             b.requires_grad_(True)
@@ -399,7 +400,7 @@ class StepBTrainer(StepATrainer):
             out[f"errShpD{i}"] = self._update(b, losses.shpD_loss(d, imgs[i], fake_imgs[i], hmaps[i], rois_h[i], nr_h),
                                               lr_d, gs)
         # (3-3) / (3-4) object discriminators (small scale on the 64-scale boxes, large scale on the feature-map boxes)
-        codes = bt_c_codes[-1].detach()
+        codes = bt_c_codes[-1]
         out["errObjSSD"] = self._update(self.bObj[0], losses.objD_loss(
             self.netObjSSD, imgs[-1], fake_imgs[-1], hmaps[-1], inp["clabels_emb"], codes, rois_h[0], nr_h), lr_d, gs)
         out["errObjLSD"] = self._update(self.bObj[1], losses.objD_loss(
@@ -411,7 +412,7 @@ class StepBTrainer(StepATrainer):
         self.bG.zero_grad()
         labels = torch.arange(fake_imgs[0].size(0), device=fake_imgs[0].device)
         err_g, logs = losses.G_loss(self.netsPatD, self.netsShpD, self.netObjSSD, self.netObjLSD, self.image_encoder,
-                                    fake_imgs, hmaps, inp["words_embs"], sent, inp["clabels_emb"], bt_c_codes[-1], labels,
+                                    fake_imgs, hmaps, inp["words_embs"], sent, inp["clabels_emb"], codes, labels,
                                     inp["cap_lens"], class_ids, rois_h[0], fm_h, nr_h)
         kl = losses.KL_loss(mu, logvar)
         (err_g + kl).backward()

@@ -178,6 +178,13 @@ def g_hmap(hmap, sd, p):
 
 def _bt_branch(sd, p, words, glove, slabels_feat, mask, bt_mask, rmax, buattn_norm):
     slabels = slabels_feat[:, :, :rmax]
+    if rmax == 0:
+        # ref: model.py:689-694 (NEXT stage `else`): zero code / attention / label maps and an empty raw code; the INIT
+        # stage's `else` (571-576) reads an undefined `att` and crashes -- the same zeros are its evident intent
+        b, (ih, iw) = slabels_feat.shape[0], bt_mask.shape[2:]
+        z = lambda c: torch.zeros(b, c, ih, iw, dtype=words.dtype)
+        idf = sd[p + ".bt_att.conv_context.weight"].shape[0]
+        return torch.zeros(b, idf, 0, 1, dtype=words.dtype), z(idf), z(words.shape[2]), z(slabels_feat.shape[1])
     bt_c, bt_att = global_bu_attention(slabels, glove, words, sd[p + ".bt_att.conv_context.weight"], mask,
                                        buattn_norm)
     m = bt_mask[:, :rmax]
@@ -806,7 +813,7 @@ def step_b(state: StepBState, inp: dict, *, image_encoder=None, class_ids=None, 
         losses[f"errShpD{i}"] = d_update(state.extra[i], state.x_keys[i], state.x_m[i], state.x_v[i],
                                          lambda live, i=i: shp_d_loss(live, imgs[i], fake[i], hmaps[i], rois[i], nums), t)
         state.x_step[i] += 1
-    codes = btc[-1].detach()
+    codes = btc[-1].detach()      # ref: trainer.py:393 detaches every bt_c_code right after the G forward
     for j, (name, boxes, n_layer, large) in enumerate((("errObjSSD", rois[0], 3, False), ("errObjLSD", fm, 4, True))):
         idx = 3 + j
         nxt = state.x_step[idx] + 1
@@ -818,7 +825,7 @@ def step_b(state: StepBState, inp: dict, *, image_encoder=None, class_ids=None, 
         losses[name] = res
     labels = torch.arange(fake[0].shape[0])
     errg, terms = g_loss(state.ds, state.extra[:3], state.extra[3], state.extra[4], image_encoder, fake, hmaps,
-                         inp["words_embs"], sent, inp["clabels_emb"], btc[-1], labels,
+                         inp["words_embs"], sent, inp["clabels_emb"], codes, labels,
                          [int(v) for v in inp["cap_lens"]], class_ids, rois[0], fm, nums)
     kl = kl_loss(mu, logvar)
     ggrads = torch.autograd.grad(errg + kl, [g_leaves[k] for k in state.g_keys])
@@ -827,4 +834,5 @@ def step_b(state: StepBState, inp: dict, *, image_encoder=None, class_ids=None, 
         ema_update(state.g_avg[k], state.g[k])
     losses["errG"], losses["kl"] = float(errg), float(kl)
     losses["terms"] = {k: float(v) for k, v in terms.items()}
+    losses["fake"] = [f.detach() for f in fake]
     return losses
