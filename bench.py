@@ -27,6 +27,23 @@ import torch  # noqa: E402
 METRIC = "G+D training-step images/sec @256x256 (Step-A: G fwd+bwd, 3 PatD updates, G update through 3 PatD + KL)"
 UNIT = "images/s"
 GMAC_PER_IMG_STEP_A = 330.0  # SURVEY.md 8d / BASELINE.md section 2
+GMAC_PER_IMG_STEP_B = 765.0  # same table; includes DAMSM + per-step Inception (48 GMAC) which this step does not run
+DTYPE = "f32 (contractions: 3xFP16 error-compensated tcgen05 MMA, 22-bit mantissa operands, fp32 accumulate)"
+
+
+def ncu_traffic(kernel_key):
+    """DRAM read+write bytes per launch of a kernel, from the committed ncu --set full capture summary
+    (profiles/ncu_traffic.json, written by profiles/summarise_ncu.py from the .ncu-rep of this bench command).
+    Returns (bytes or None, provenance string)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, "no ncu capture summary committed"
+    d = json.load(open(p))
+    e = d.get(kernel_key)
+    if not e:
+        return None, f"{kernel_key} not in profiles/ncu_traffic.json"
+    return e["dram_bytes"], f"dram__bytes_read.sum + dram__bytes_write.sum per launch, {e['source']}"
+
 
 
 def peaks():
@@ -143,18 +160,19 @@ def conv_roofline(hbm, bf16_tf, src):
     peak = bf16_tf                                         # kind::f16 runs at the bf16 rate
     from objgan_b200 import ops as _ops
     eng = _ops.CONV_ENGINE
+    traffic, tsrc = ncu_traffic("conv_tc2_res3_conv1") if eng == "f16x3" else (None, "")
     kname = {"simt": "conv_gemm_kernel<8> (fp32 FMA)", "f16": "conv_tc2_kernel<208> (tcgen05 kind::f16, 1 product)",
              "f16x3": "conv_tc2_kernel<208> (tcgen05 kind::f16, 3xFP16 error-compensated hi/lo operands)"}[eng]
     note = {"simt": "CUDA-core fp32 path", "f16": "single fp16 product (not the parity mode)",
             "f16x3": "3 MMAs per algorithmic product, so frac <= 1/3 by construction; amax + prep_split passes included"}[eng]
     return {"bound": "tensor", "kernel": kname + " + prep_split: res-block conv1 194->388 3x3 @128x128, B=16",
             "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-            "traffic": 816.9e6 if eng == "f16x3" else None, "ms_per_launch": round(ms, 3),
+            "traffic": traffic, "ms_per_launch": round(ms, 3),
             "algorithmic_flops_per_launch": flops,
             "issued_mma_tflops": round(achieved * (3 if eng == "f16x3" else 1), 1) if eng != "simt" else None,
             "frac_of_peak_counting_issued_mmas": round(achieved * (3 if eng == "f16x3" else 1) / peak, 4) if eng != "simt" else None,
-            "peak_source": f"{src} bf16 cuBLAS burst (kind::f16 = bf16 rate); {note}; traffic = dram read+write of "
-                           "conv_tc2_kernel<208,1> in profiles/r01_final_kernels.ncu-rep (algorithmic: 635 MB)"}
+            "peak_source": f"{src} bf16 cuBLAS burst (kind::f16 = bf16 rate); {note}; traffic = {tsrc} "
+                           "(algorithmic: 635 MB)"}
 
 
 def attn_roofline(hbm, src):
@@ -180,15 +198,17 @@ def attn_roofline(hbm, src):
     ms = sum(times) / len(times)
     byts = 4.0 * Q * (2 * C + L) * B
     ach = byts / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "att_general_fwd_kernel<20,2> (Q=16384, L=18, C=48, B=16)", "achieved": round(ach, 1),
-            "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": 62.96e6, "ms_per_launch": round(ms, 4),
-            "peak_source": f"{src} copy bandwidth; traffic = dram read+write in profiles/r01_final_attention.ncu-rep (50.4 MB read; "
-                           "most of the 69 MB written is still dirty in the 126 MB L2 when the kernel ends)"}
+    traffic, tsrc = ncu_traffic("att_general_fwd")
+    return {"bound": "hbm", "kernel": "att_general_fwd_kernel (Q=16384, L=18, C=48, B=16)", "achieved": round(ach, 1),
+            "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": traffic, "ms_per_launch": round(ms, 4),
+            "algorithmic_bytes_per_launch": byts,
+            "peak_source": f"{src} copy bandwidth; traffic = {tsrc} (written lines may still be dirty in the 126 MB L2 "
+                           "when the kernel ends)"}
 
 
 def _best_cpu_threads():
-    """The reference's CPU path is torch CPU ops; on a many-core host more threads is not always faster at batch 2,
-    so give it the best of a few thread counts (measured on one G forward each) -- the fairest CPU arm we can build."""
+    """The reference's CPU path is torch CPU ops; on a many-core host more threads is not always faster, so give it
+    the best of a few thread counts (measured on one G forward at batch 2 each) -- the fairest CPU arm we can build."""
     from objgan_b200 import model, synth
     from oracle import objgan_oracle as O
     cores = os.cpu_count() or 1
@@ -209,44 +229,126 @@ def _best_cpu_threads():
     return best
 
 
+CPU_BATCH = 16     # the CPU arm runs the SAME configuration as the GPU arm (BASELINE configs[1]: batch 16)
+
+
+def _reference_modules():
+    """The reference's own image_generation modules, importable only where /root/reference is mounted (never on the
+    GPU box).  Returns the namespace of tests/refimport.py or None."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import refimport
+        return refimport.load() if refimport.available() else None
+    except Exception:
+        return None
+
+
 def cpu_step_a(batch, steps, warmup, seed=1234):
-    """Reference algorithm (oracle port) on the host cores: Step-A at batch `batch`.  Returns img/s, s/step, threads."""
+    """The reference's algorithm for Step-A on the host cores at batch `batch`.  kind "reference": the reference's own
+    model.py / losses.py modules + torch.optim.Adam (only where /root/reference is importable); kind "port": the
+    oracle restatement (oracle/objgan_oracle.py), which is what can travel to the GPU box.
+    Returns (img/s, s/step, threads, kind)."""
     from objgan_b200 import model, synth
     from oracle import objgan_oracle as O
     threads = _best_cpu_threads()
     torch.set_num_threads(threads)
     torch.manual_seed(seed)
-    g = model.G_NET(80)
-    ds = [model.PAT_D_NET64(), model.PAT_D_NET128(), model.PAT_D_NET256()]
-    state = O.StepAState(g.state_dict(), [d.state_dict() for d in ds])
     inp = synth.make_inputs(batch, seed=seed, parity=False)
+    ref = _reference_modules()
+    if ref is not None:
+        g = ref.model.G_NET(80)
+        ds = [ref.model.PAT_D_NET64(), ref.model.PAT_D_NET128(), ref.model.PAT_D_NET256()]
+        for m in [g, *ds]:
+            m.apply(ref.utils.weights_init)
+        opt_g = torch.optim.Adam(g.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        opt_d = [torch.optim.Adam(d.parameters(), lr=2e-4, betas=(0.5, 0.999)) for d in ds]
+        avg = [p.data.clone() for p in g.parameters()]
+        bce = torch.nn.BCELoss()
+
+        def one():  # ref: trainer.py:388-406, 444-462 restricted to G + PatD + KL (Step-A, SURVEY.md 8d)
+            out = g(inp["z"], inp["sent_emb"], inp["words_embs"], inp["glove_words_embs"], inp["slabels_feat"],
+                    inp["mask"], inp["hmaps"], inp["rois"], inp["fm_rois"], inp["num_rois"], inp["bt_masks"],
+                    inp["fm_bt_masks"], inp["glb_max_num_roi"])
+            fake, mu, logvar = out[0], out[4], out[5]
+            for i, d in enumerate(ds):
+                d.zero_grad()
+                ref.losses.patD_loss(d, inp["imgs"][i], fake[i], inp["sent_emb"]).backward()
+                opt_d[i].step()
+            g.zero_grad()
+            total = ref.losses.KL_loss(mu, logvar)
+            for i, d in enumerate(ds):
+                f = d(fake[i])
+                c, u = d.COND_DNET(f, inp["sent_emb"]), d.UNCOND_DNET(f)
+                total = total + bce(u, torch.ones_like(u)) * 1.0 + bce(c, torch.ones_like(c)) * 0.1
+            total.backward()
+            opt_g.step()
+            for p, a in zip(g.parameters(), avg):
+                a.mul_(0.999).add_(p.data, alpha=0.001)
+        kind = "reference"
+    else:
+        g = model.G_NET(80)
+        ds = [model.PAT_D_NET64(), model.PAT_D_NET128(), model.PAT_D_NET256()]
+        state = O.StepAState(g.state_dict(), [d.state_dict() for d in ds])
+        one = lambda: O.step_a(state, inp)
+        kind = "port"
     for _ in range(warmup):
-        O.step_a(state, inp)
+        one()
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.step_a(state, inp)
+        one()
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, threads
+    return batch * steps / dt, dt / steps, threads, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = 2
-    ips, spstep, cores = cpu_step_a(B, args.steps, args.warmup)
+    B = CPU_BATCH
+    ips, spstep, cores, kind = cpu_step_a(B, args.steps, args.warmup)
+    what = ("the reference's own model.py / losses.py modules" if kind == "reference"
+            else "oracle/objgan_oracle.py, the CPU restatement of the reference (the Python reference itself cannot "
+                 "travel to the GPU box)")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(ips, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(spstep * 1e3, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "step_a_b16_256 (BASELINE configs[1]); CPU arm runs a bounded sample of it: batch 2 per step",
-                   "global_batch": B, "words": 18, "rois": 10},
-        "cpu_baseline": {"value": round(ips, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} Step-A steps at batch {B} (oracle/objgan_oracle.py, torch CPU fp32, "
+        "config": {"workload": "step_a_b16_256 (BASELINE configs[1]: full G_NET 64/128/256 + 3 patch Ds, batch 16)",
+                   "global_batch": B, "words": 18, "rois": 10, "same_config_as_gpu_arm": True},
+        "cpu_baseline": {"value": round(ips, 4), "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} Step-A steps at batch {B} ({what}; torch CPU fp32, "
                                    f"{cores} threads = best of 8/16/32/64/all {os.cpu_count()} host cores)"},
         "e2e": {"value": round(ips, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def step_b_section(args, local, hbm):
+    """The reference's COMPLETE step (trainer.py:385-462: + 3 shape Ds, 2 object Ds at 512^2 and their G-loss terms)
+    on the same batch-16 inputs; eager launches (the kept-roi count and permute_seg's shuffles change the tensor
+    shapes every step, so it is not replayed from a graph), no host synchronisation inside the step."""
+    from objgan_b200 import synth, trainer
+    import random
+    random.seed(1234)
+    B = args.batch_per_gpu
+    tr = trainer.StepBTrainer(device=f"cuda:{local}", seed=1234)
+    host = trainer.pin(synth.make_inputs(B, seed=1234, parity=False))
+    host.pop("eps")
+    dev = tr.to_device(host)
+    for _ in range(2):
+        tr.step(dev)
+    torch.cuda.synchronize()
+    n = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    ms = timed(lambda: tr.step(dev), n, 1)
+    wall = time.perf_counter() - t0
+    ips = B * n / (ms * 1e-3)
+    return {"workload": "step_b_b16_256: G fwd, 3 PatD + 3 ShpD + ObjSS + ObjLS updates, G update through all eight "
+                        "+ KL, Adam x9, EMA (no DAMSM image encoder, no per-step Inception score)",
+            "value": round(ips, 3), "unit": UNIT, "ms_per_step": round(ms / n, 2), "steps": n, "cuda_graph": False,
+            "host_wall_ms_per_step": round(wall * 1e3 / n, 2),
+            "algorithmic_gmac_per_image": GMAC_PER_IMG_STEP_B - 48.0,
+            "algorithmic_tflops": round(2 * (GMAC_PER_IMG_STEP_B - 48.0) * 1e9 * ips / 1e12, 2)}
 
 
 def run_b200(args):
@@ -293,15 +395,23 @@ def run_b200(args):
     roof_att = attn_roofline(hbm, src)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ips, sps, thr = cpu_step_a(2, 1, 0)
-        cpu = {"value": round(ips, 4), "unit": UNIT, "cores": thr, "kind": "port",
-               "sample": f"1 Step-A step at batch 2 ({sps:.1f} s) of oracle/objgan_oracle.py, torch CPU fp32, {thr} threads "
-                         f"(best of 8/16/32/64/all {os.cpu_count()} host cores)"}
+        ips, sps, thr, kind = cpu_step_a(CPU_BATCH, 1, 0)
+        cpu = {"value": round(ips, 4), "unit": UNIT, "cores": thr, "kind": kind,
+               "sample": f"1 Step-A step at batch {CPU_BATCH} (the GPU arm's configuration; {sps:.1f} s) of "
+                         f"{'the reference modules' if kind == 'reference' else 'oracle/objgan_oracle.py'}, torch CPU "
+                         f"fp32, {thr} threads (best of 8/16/32/64/all {os.cpu_count()} host cores)"}
+    ops_lines = step_b = None
+    if world == 1 and not args.no_extras:
+        import bench_ops
+        ops_lines = bench_ops.collect()          # BASELINE configs[2] / configs[3] operator lines
+        del tr
+        torch.cuda.empty_cache()
+        step_b = step_b_section(args, local, hbm)
     step_tflops = 2 * GMAC_PER_IMG_STEP_A * 1e9 * value / 1e12
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": {"workload": "step_a_b16_256 (BASELINE configs[1]: full G_NET 64/128/256 + 3 patch Ds, batch 16/GPU)",
                    "global_batch": world * B, "words": 18, "rois": 10, "parallelism": f"dp{world}",
                    "l2": "inputs (0.47 GB/step) and activations (>10 GB) exceed the 126 MB L2; no explicit flush",
@@ -313,6 +423,10 @@ def run_b200(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if ops_lines is not None:
+        line["ops"] = ops_lines
+    if step_b is not None:
+        line["step_b"] = step_b
     print(json.dumps(line), flush=True)
 
 
@@ -325,6 +439,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-extras", action="store_true", help="skip the operator lines (configs 3/4) and the Step-B section")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

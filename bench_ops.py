@@ -1,9 +1,14 @@
 #!/usr/bin/env python
 """Operator-level measurements for BASELINE.json configs[2] (attention isolation) and configs[3] (object path):
 achieved HBM GB/s of the bandwidth kernels against the measured copy peak, and ROIAlign against the reference's own
-roi_align_kernel.cu compiled for sm_100a (oracle/_ref) on the same GPU.  Prints one JSON object per line.
+roi_align_kernel.cu compiled for sm_100a (oracle/_ref) on the same GPU.
 
-    python bench_ops.py > profiles/r01_ops_bench.jsonl
+    python bench_ops.py > profiles/r02_ops_bench.jsonl      # one JSON object per line
+    bench.py imports collect() and folds the same records into its JSON line ("ops").
+
+Timing: every operator is launched over K independent input sets whose combined footprint exceeds the 126 MB L2
+(so each launch reads HBM-cold data), the K launches are captured once in a CUDA graph (no host launch overhead
+between them) and the graph is replayed between two CUDA events; the reported time is the median over replays / K.
 """
 import ctypes
 import json
@@ -17,75 +22,102 @@ import torch  # noqa: E402
 from objgan_b200 import model, ops  # noqa: E402
 
 DEV = "cuda"
-peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-HBM = peaks.get("hbm_gbs", 6650.0)
-FLUSH = torch.empty(256 * 1024 * 1024 // 4, device=DEV)
+_pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+HBM = (json.load(open(_pk)) if os.path.exists(_pk) else {}).get("hbm_gbs", 6650.0)
+L2_BYTES = 126e6
 
 
-def timeit(fn, iters=10, warm=3):
+def nsets(bytes_per_set):
+    return int(min(64, max(4, 2.5 * L2_BYTES // max(bytes_per_set, 1) + 1)))
+
+
+def time_graph(fns, replays=7):
+    """fns: list of zero-argument callables (one per input set).  Returns ms per call."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for f in fns:                      # warm-up (allocator, kernel attributes)
+            f()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        for f in fns:
+            f()
     ts = []
-    for i in range(warm + iters):
-        FLUSH.zero_()                                  # evict the 126 MB L2
+    for _ in range(replays):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        g.replay()
         e1.record()
         torch.cuda.synchronize()
-        if i >= warm:
-            ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / len(fns))
     ts.sort()
     return ts[len(ts) // 2]
 
 
-def emit(**kw):
-    print(json.dumps(kw), flush=True)
-
-
-def attention_sweep():
+def attention_sweep(out, quick):
     C, L = 48, 18
-    for B in (16, 32, 64):
-        for Q in (1024, 4096, 16384):
-            ih = int(Q ** 0.5)
-            h = torch.randn(B, ih, ih, C, device=DEV, requires_grad=True)
-            src = torch.randn(B, C, L, device=DEV, requires_grad=True)
-            ms = timeit(lambda: ops.att_general(h.detach(), src.detach(), None, C))
-            byts = 4.0 * Q * (2 * C + L) * B
-            wc, _ = ops.att_general(h, src, None, C)
-            g = torch.randn_like(wc)
+    cases = [(16, 16384), (16, 4096)] if quick else [(b, q) for b in (16, 32, 64) for q in (1024, 4096, 16384)]
+    for B, Q in cases:
+        ih = int(Q ** 0.5)
+        byts = 4.0 * Q * (2 * C + L) * B
+        bytb = 4.0 * Q * (3 * C + L) * B
+        K = nsets(byts)
+        hs = [torch.randn(B, ih, ih, C, device=DEV) for _ in range(K)]
+        srcs = [torch.randn(B, C, L, device=DEV) for _ in range(K)]
+        ms = time_graph([lambda h=h, s=s: ops.att_general(h, s, None, C) for h, s in zip(hs, srcs)])
+        outs = []
+        for h, s in zip(hs, srcs):
+            h.requires_grad_(True)
+            s.requires_grad_(True)
+            outs.append(ops.att_general(h, s, None, C)[0])
+        gs = [torch.randn_like(o) for o in outs]
+        msb = time_graph([lambda o=o, h=h, s=s, g=g: torch.autograd.grad(o, (h, s), g, retain_graph=True)
+                          for o, h, s, g in zip(outs, hs, srcs, gs)])
+        out.append(dict(config=3, op="GlobalAttentionGeneral", B=B, Q=Q, L=L, C=C, fwd_ms=round(ms, 4),
+                        fwd_gbs=round(byts / ms / 1e6, 1), fwd_frac_of_hbm_peak=round(byts / ms / 1e6 / HBM, 3),
+                        bwd_ms=round(msb, 4), bwd_gbs=round(bytb / msb / 1e6, 1),
+                        bwd_frac_of_hbm_peak=round(bytb / msb / 1e6 / HBM, 3), hbm_peak_gbs=HBM, input_sets=K))
+        del hs, srcs, outs, gs
+    for Bn in ((16,) if quick else (16, 32)):            # all B x B (image, caption) pairs of words_loss, one launch
+        feat = torch.randn(Bn, 256, 17, 17, device=DEV, requires_grad=True)
+        words = torch.randn(Bn, 256, 18, device=DEV)
+        lens = torch.full((Bn,), 18, dtype=torch.int64, device=DEV)
+        ms = time_graph([lambda: ops.words_pairs(feat.detach(), words, lens, 4.0, 5.0)] * 4)
+        sim, _ = ops.words_pairs(feat, words, lens, 4.0, 5.0)
+        g = torch.randn_like(sim)
+        msb = time_graph([lambda: torch.autograd.grad(sim, feat, g, retain_graph=True)] * 4)
+        P = Bn * Bn
+        flops = 2.0 * P * 2 * 289 * 256 * 18
+        byts = 4.0 * (Bn * 256 * 289 + Bn * 256 * 18 + P * (256 * 18 + 18 * 289 + 1))
+        out.append(dict(config=3, op="func_attention over all BxB pairs (words_pairs)", B=Bn, pairs=P, regions=289, Lq=18,
+                        ndf=256, fwd_ms=round(ms, 4), bwd_ms=round(msb, 4), fwd_gflops=round(flops / ms / 1e6, 1),
+                        fwd_gbs=round(byts / ms / 1e6, 1), fwd_frac_of_hbm_peak=round(byts / ms / 1e6 / HBM, 3),
+                        note="L2-resident working set (4.7 MB of image features at B=16): bound by fp32 FMA issue, "
+                             "not HBM; reference = B launches of func_attention + B cosine / pooling launches"))
 
-            def bwd():
-                torch.autograd.grad(wc, (h, src), g, retain_graph=True)
-            msb = timeit(bwd)
-            bytb = 4.0 * Q * (3 * C + L) * B
-            emit(config=3, op="GlobalAttentionGeneral", B=B, Q=Q, L=L, C=C, fwd_ms=round(ms, 4),
-                 fwd_gbs=round(byts / ms / 1e6, 1), fwd_frac_of_hbm_peak=round(byts / ms / 1e6 / HBM, 3),
-                 bwd_ms=round(msb, 4), bwd_gbs=round(bytb / msb / 1e6, 1), hbm_peak_gbs=HBM)
-    for P in (256, 1024):                              # B^2 (image, caption) pairs of words_loss
-        q = torch.randn(P, 256, 18, device=DEV)
-        ctx = torch.randn(P, 256, 17, 17, device=DEV)
-        ms = timeit(lambda: ops.func_attention(q, ctx, 4.0))
-        byts = 4.0 * P * (256 * 289 + 256 * 18 * 2 + 18 * 289)
-        emit(config=3, op="func_attention", pairs=P, regions=289, Lq=18, ndf=256, fwd_ms=round(ms, 4),
-             fwd_gbs=round(byts / ms / 1e6, 1), fwd_frac_of_hbm_peak=round(byts / ms / 1e6 / HBM, 3))
 
-
-def object_path():
+def object_path(out, quick):
     B, R, L = 32, 10, 18
-    for ih in (64, 128):
+    for ih in ((64,) if quick else (64, 128)):
         bu = model.BT_ATT_NET(48, 256).to(DEV)
-        lab, glove, words = torch.randn(B, 50, R, 1, device=DEV), torch.randn(B, 50, L, device=DEV), torch.randn(B, 256, L, device=DEV)
-        m = torch.rand(B, R, ih, ih, device=DEV)
+        byts = 3 * 4.0 * B * R * ih * ih + 4.0 * B * ih * ih * (48 + 24 + 56)
+        K = nsets(byts)
+        lab, glove, words = (torch.randn(B, 50, R, 1, device=DEV), torch.randn(B, 50, L, device=DEV),
+                             torch.randn(B, 256, L, device=DEV))
+        ms_ = [torch.rand(B, R, ih, ih, device=DEV) for _ in range(K)]
 
-        def run():
+        def run(m):
             wc, att = bu(lab, glove, words)
             ops.paint_max(wc.reshape(B, 48, R), m)
             ops.paint_max(att.reshape(B, L, R), m)
             ops.paint_max(lab.reshape(B, 50, R), m)
         with torch.no_grad():
-            ms = timeit(run)
-        byts = 3 * 4.0 * B * R * ih * ih + 4.0 * B * ih * ih * (48 + 24 + 56)
-        emit(config=4, op="BT_ATT_NET + 3x pprocess_bt_attns", B=B, R=R, size=ih, ms=round(ms, 4), gbs=round(byts / ms / 1e6, 1),
-             frac_of_hbm_peak=round(byts / ms / 1e6 / HBM, 3))
+            ms = time_graph([lambda m=m: run(m) for m in ms_])
+        out.append(dict(config=4, op="BT_ATT_NET + 3x pprocess_bt_attns", B=B, R=R, size=ih, ms=round(ms, 4),
+                        gbs=round(byts / ms / 1e6, 1), frac_of_hbm_peak=round(byts / ms / 1e6 / HBM, 3), input_sets=K))
+        del ms_
     so = os.path.join(ROOT, "oracle", "_ref", "libroi_align_ref_cuda.so")
     ref = ctypes.CDLL(so) if os.path.exists(so) else None
     if ref:
@@ -93,39 +125,52 @@ def object_path():
         ref.ROIAlignForwardLaucher.argtypes = [vp, cf, ci, ci, ci, ci, ci, ci, vp, vp, vp]
         ref.ROIAlignBackwardLaucher.argtypes = [vp, cf, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp]
     for (C, H) in ((384, 64), (768, 32)):
-        feat = torch.randn(B, C, H, H, device=DEV)
-        xy = torch.rand(B * R, 2) * 40
-        wh = 6 + torch.rand(B * R, 2) * 18
-        rois = torch.cat([torch.arange(B).repeat_interleave(R).float().unsqueeze(1), xy, xy + wh], 1).to(DEV)
         nr = B * R
-        st = torch.cuda.current_stream().cuda_stream
-        ms_f = timeit(lambda: ops.roi_align_avg(feat, rois, 5, 5, 1 / 16))
+        K = nsets(4.0 * B * C * H * H)
+        feats = [torch.randn(B, C, H, H, device=DEV) for _ in range(K)]
+        xy = torch.rand(nr, 2) * 40 * 16 * H / 64
+        wh = (6 + torch.rand(nr, 2) * 18) * 16 * H / 64
+        rois = torch.cat([torch.arange(B).repeat_interleave(R).float().unsqueeze(1), xy, xy + wh], 1).to(DEV)
+        outs = [torch.empty(nr, C, 5, 5, device=DEV) for _ in range(K)]
+        ms_f = time_graph([lambda f=f, o=o: ops._call("og_roi_align_avg_fwd", f.data_ptr(), H, H, C, rois.data_ptr(), nr,
+                                                      5, 5, 1 / 16, o.data_ptr()) for f, o in zip(feats, outs)])
         g = torch.randn(nr, C, 5, 5, device=DEV)
-        gin = torch.zeros_like(feat)
-
-        def bwd():
-            gin.zero_()
-            ops._call("og_roi_align_avg_bwd", g.data_ptr(), H, H, C, rois.data_ptr(), nr, 5, 5, 1 / 16, gin.data_ptr())
-        ms_b = timeit(bwd)
+        gins = [torch.zeros_like(f) for f in feats]
+        ms_b = time_graph([lambda gi=gi: ops._call("og_roi_align_avg_bwd", g.data_ptr(), H, H, C, rois.data_ptr(), nr, 5,
+                                                   5, 1 / 16, gi.data_ptr()) for gi in gins])
+        wbytes = 4.0 * nr * C * 25
         rec = dict(config=4, op="RoIAlignAvg(5,5,1/16)", B=B, rois=nr, C=C, H=H, fused_fwd_ms=round(ms_f, 4),
-                   fused_bwd_ms=round(ms_b, 4), fwd_out_gbs=round(4.0 * nr * C * 25 / ms_f / 1e6, 1))
+                   fused_bwd_ms=round(ms_b, 4), fwd_out_gbs=round(wbytes / ms_f / 1e6, 1),
+                   fwd_frac_of_hbm_peak=round(wbytes / ms_f / 1e6 / HBM, 3), input_sets=K)
         if ref:
             o6 = torch.zeros(nr, C, 6, 6, device=DEV)
-
-            def ref_f():
-                ref.ROIAlignForwardLaucher(feat.data_ptr(), 1 / 16, nr, H, H, C, 6, 6, rois.data_ptr(), o6.data_ptr(), st)
-                torch.nn.functional.avg_pool2d(o6, 2, 1)
             g6 = torch.randn_like(o6)
 
-            def ref_b():
-                gin.zero_()
-                ref.ROIAlignBackwardLaucher(g6.data_ptr(), 1 / 16, B, nr, H, H, C, 6, 6, rois.data_ptr(), gin.data_ptr(), st)
-            rec["reference_cu_fwd_ms"] = round(timeit(ref_f), 4)
-            rec["reference_cu_bwd_ms"] = round(timeit(ref_b), 4)
-            rec["note"] = "reference = roi_align_kernel.cu compiled verbatim for sm_100a + torch avg_pool2d (fwd); its bwd excludes the pool adjoint"
-        emit(**rec)
+            def ref_f(f):
+                ref.ROIAlignForwardLaucher(f.data_ptr(), 1 / 16, nr, H, H, C, 6, 6, rois.data_ptr(), o6.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream)
+                torch.nn.functional.avg_pool2d(o6, 2, 1)
+
+            def ref_b(gi):
+                ref.ROIAlignBackwardLaucher(g6.data_ptr(), 1 / 16, B, nr, H, H, C, 6, 6, rois.data_ptr(), gi.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream)
+            rec["reference_cu_fwd_ms"] = round(time_graph([lambda f=f: ref_f(f) for f in feats]), 4)
+            rec["reference_cu_bwd_ms"] = round(time_graph([lambda gi=gi: ref_b(gi) for gi in gins]), 4)
+            rec["note"] = ("reference = roi_align_kernel.cu compiled verbatim for sm_100a + torch avg_pool2d (fwd); its "
+                           "bwd excludes the pool adjoint")
+        out.append(rec)
+        del feats, outs, gins
+
+
+def collect(quick=True):
+    out = []
+    with torch.no_grad():
+        pass
+    attention_sweep(out, quick)
+    object_path(out, quick)
+    return out
 
 
 if __name__ == "__main__":
-    attention_sweep()
-    object_path()
+    for rec in collect(quick="--full" not in sys.argv):
+        print(json.dumps(rec), flush=True)

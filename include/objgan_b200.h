@@ -232,6 +232,21 @@ int og_ce_pair(const float* sim, const unsigned char* mask, const long long* lab
 int og_ce_pair_bwd(const float* G0, const float* G1, const float* g0, const float* g1, int n, float* gsim,
                    cudaStream_t stream);
 
+/* All (image, caption) pairs of words_loss in ONE launch (ref: miscc/losses.py:87-127 -- the reference calls
+ * func_attention once per caption in a Python loop).  words [NC][ndf][T] (caption i uses its first lens[i] words),
+ * ctx [B][ndf][S] image region features (NCHW flattened), lens [NC] int64 on the device.  pair p = b * NC + i.
+ *  fwd: wc [B*NC][ndf][T] (weighted contexts), attn [B*NC][T][S], sim [B][NC] = log sum_l exp(gamma2 * cos_l)
+ *       (rows / columns beyond a caption's length are not written)
+ *  bwd: g_ctx [B][ndf][S] = d (sum_p g_sim[p] * sim[p]) / d ctx  (zero-filled by the call, fp32 atomics) */
+int og_words_pairs_fwd(const float* words, const float* ctx, const long long* lens, int B, int NC, int ndf, int T, int S,
+                       float gamma1, float gamma2, float eps, float* wc, float* attn, float* sim, cudaStream_t stream);
+int og_words_pairs_bwd(const float* words, const float* ctx, const long long* lens, const float* wc, const float* attn,
+                       const float* g_sim, int B, int NC, int ndf, int T, int S, float gamma1, float gamma2, float eps,
+                       float* g_ctx, cudaStream_t stream);
+
+/* zero-fill (a memset node when captured in a CUDA graph; no kernel launch) */
+int og_zero_bytes(float* p, long long bytes, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -221,24 +221,29 @@ def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8, top1=
     return loss0, loss1, accuracy
 
 
-def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size, top1=True, is_training=True):
+def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size, top1=True, is_training=True,
+               need_att_maps=True):
     """ref: miscc/losses.py:74-159 (DAMSM word-region matching).  img_features (B, nef, 17, 17) carries the gradient;
-    words_emb (B, nef, T) is a constant.  Per caption i: fused func_attention of its words against every image,
-    cosine similarity word / attended context, Eq. (10) pooling; then the two cross-entropy directions over the
-    B x B similarity matrix.  Returns (loss0, loss1, att_maps, accuracy)."""
-    lens = cap_lens.detach().cpu().tolist() if torch.is_tensor(cap_lens) else list(cap_lens)
-    words_emb = words_emb.detach()
-    sims, att_maps = [], []
-    for i in range(batch_size):
-        n = int(lens[i])
-        word = words_emb[i, :, :n].contiguous()                                  # (nef, n)
-        query = word.unsqueeze(0).expand(batch_size, -1, -1).contiguous()         # the caption against every image
-        wei, attn = ops.func_attention(query, img_features, cfg.TRAIN.SMOOTH.GAMMA1)
-        att_maps.append(attn[i].unsqueeze(0).contiguous())
-        row = ops.cosine_cl(word, wei)                                            # (B, n)
-        sims.append(ops.expsumlog(row, cfg.TRAIN.SMOOTH.GAMMA2).view(batch_size, 1))
-    sim = torch.cat(sims, 1)                                                      # (image, caption)
-    mask = _class_masks(class_ids, batch_size, img_features.device)
+    words_emb (B, nef, T) is a constant.  All B x B (image, caption) pairs run in ONE launch (``ops.words_pairs``:
+    func_attention of caption i's words against image b, cosine similarity word / attended context, Eq. (10) pooling)
+    instead of the reference's per-caption Python loop; then the two cross-entropy directions over the B x B
+    similarity matrix.  ``cap_lens``: int64 tensor on the device (no host synchronisation), or a host list / tensor.
+    Returns (loss0, loss1, att_maps, accuracy); att_maps[i] = (1, n_i, 17, 17) like the reference when
+    ``need_att_maps`` (slicing by n_i needs the lengths on the host), else the padded (B, T, 17, 17) tensor."""
+    dev = img_features.device
+    if torch.is_tensor(cap_lens) and cap_lens.device == dev:
+        lens_dev = cap_lens.to(torch.int64).contiguous()
+    else:
+        lens_dev = torch.as_tensor([int(v) for v in cap_lens], dtype=torch.int64).to(dev, non_blocking=True)
+    sim, attn = ops.words_pairs(img_features, words_emb.detach(), lens_dev[:batch_size], cfg.TRAIN.SMOOTH.GAMMA1,
+                                cfg.TRAIN.SMOOTH.GAMMA2)                     # sim[image, caption]
+    diag = attn[torch.arange(batch_size, device=dev), torch.arange(batch_size, device=dev)] if need_att_maps else None
+    if need_att_maps:
+        lens = cap_lens.detach().cpu().tolist() if torch.is_tensor(cap_lens) else list(cap_lens)
+        att_maps = [diag[i:i + 1, :int(lens[i])].contiguous() for i in range(batch_size)]
+    else:
+        att_maps = None
+    mask = _class_masks(class_ids, batch_size, dev)
     loss0, loss1, correct = ops.ce_pair(sim, mask, labels, cfg.TRAIN.SMOOTH.GAMMA3)
     accuracy = correct * (100.0 / (batch_size * 2.0)) if top1 else None
     return loss0, loss1, att_maps, accuracy
@@ -292,7 +297,8 @@ def G_loss(netsPatD, netsShpD, netObjSSD, netObjLSD, image_encoder, fake_imgs, s
         logs[f"shp_g_loss{i}"] = shp.detach()
         if i == n_d - 1 and image_encoder is not None:
             region_features, cnn_code = image_encoder(fake_imgs[i])
-            w0, w1, _, _ = words_loss(region_features, words_embs, match_labels, cap_lens, class_ids, batch_size)
+            w0, w1, _, _ = words_loss(region_features, words_embs, match_labels, cap_lens, class_ids, batch_size,
+                                      need_att_maps=False)
             s0, s1, _ = sent_loss(cnn_code, sent_emb, match_labels, class_ids, batch_size)
             w_loss = (w0 + w1) * cfg.TRAIN.SMOOTH.DAMSM_LAMBDA
             s_loss = (s0 + s1) * cfg.TRAIN.SMOOTH.DAMSM_LAMBDA

@@ -1109,6 +1109,52 @@ def expsumlog(s, gamma):
     return _ExpSumLog.apply(s, gamma)
 
 
+def zeros(shape, device):
+    """Zero-filled fp32 tensor through cudaMemsetAsync (a memset node inside a captured graph, no library kernel)."""
+    t = torch.empty(shape, device=device, dtype=torch.float32)
+    _chk(t)
+    _call("og_zero_bytes", _p(t), t.numel() * 4)
+    return t
+
+
+class _WordsPairs(torch.autograd.Function):
+    """All B x NC (image, caption) pairs of words_loss in one launch (ref: miscc/losses.py:87-127): func_attention,
+    word / attended-context cosine and the Eq. (10) pooling.  ctx_feat (B, ndf, ih, iw) carries the gradient;
+    words (NC, ndf, T) and lens (NC,) int64 on the device are constants.  Returns sim (B, NC), attn (B, NC, T, ih, iw)
+    (rows beyond a caption's length are zero)."""
+
+    @staticmethod
+    def forward(ctx, feat, words, lens, gamma1, gamma2, eps):
+        _chk(feat, words, lens)
+        feat, words = feat.contiguous(), words.detach().contiguous()
+        assert lens.dtype == torch.int64 and lens.is_contiguous()
+        b, ndf, ih, iw = feat.shape
+        nc, _, t = words.shape
+        s = ih * iw
+        wc = zeros((b * nc, ndf, t), feat.device)
+        attn = zeros((b, nc, t, ih, iw), feat.device)
+        sim = torch.empty((b, nc), device=feat.device, dtype=torch.float32)
+        _call("og_words_pairs_fwd", _p(words), _p(feat), _p(lens), b, nc, ndf, t, s, float(gamma1), float(gamma2),
+              float(eps), _p(wc), _p(attn), _p(sim))
+        ctx.cfg = (b, nc, ndf, t, s, float(gamma1), float(gamma2), float(eps))
+        ctx.save_for_backward(feat, words, lens, wc, attn)
+        ctx.mark_non_differentiable(attn)
+        return sim, attn
+
+    @staticmethod
+    def backward(ctx, g_sim, _g_attn):
+        feat, words, lens, wc, attn = ctx.saved_tensors
+        b, nc, ndf, t, s, g1, g2, eps = ctx.cfg
+        g_feat = torch.empty_like(feat)
+        _call("og_words_pairs_bwd", _p(words), _p(feat), _p(lens), _p(wc), _p(attn), _p(g_sim.contiguous()), b, nc, ndf,
+              t, s, g1, g2, eps, _p(g_feat))
+        return g_feat, None, None, None, None, None
+
+
+def words_pairs(feat, words, lens, gamma1, gamma2, eps=1e-8):
+    return _WordsPairs.apply(feat, words, lens, gamma1, gamma2, eps)
+
+
 class _CosineMatrix(torch.autograd.Function):
     """out[i, j] = <a_i, b_j> / max(|a_i| |b_j|, eps) (ref: miscc/losses.py:43-50); ``b`` is a constant."""
 

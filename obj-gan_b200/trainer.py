@@ -139,8 +139,11 @@ class StepATrainer:
                 out[k] = [t.to(self.device, non_blocking=True) for t in v]
             else:
                 out[k] = v
-        for k in ("rois", "fm_rois"):  # float64 host arrays in the reference; the hot path never reads them on device
-            pass
+        # box tables stay readable on the host as well: the roi filter of feat_select and the class shuffles of
+        # permute_seg are host decisions (like the reference), and reading them back from the device would stall the
+        # step (the reference does exactly that: .cpu() in utils.py:447, 467)
+        out["host_boxes"] = {"rois": [r.detach().cpu() for r in inp["rois"]], "fm_rois": inp["fm_rois"].detach().cpu(),
+                             "num_rois": inp["num_rois"].detach().cpu()}
         return out
 
     def generate(self, inp):
@@ -358,6 +361,46 @@ class StepBTrainer(StepATrainer):
                     dist.broadcast(buf, src=0, group=self.pg)
             ops.bump_param_epoch()
 
+    # ------------------------------------------------------------------ reference-format snapshots
+    def save_model(self, model_dir: str, epoch: int) -> list:
+        """The reference's snapshot file set (ref: trainer.py:251-273): ``netG_epoch_%d.pth`` holds the EMA weights
+        (the reference swaps avg_param_G in before saving), ``netPatD%d.pth`` / ``netShpD%d.pth`` / ``netObjSSD.pth``
+        / ``netObjLSD.pth`` the live discriminators; plain ``state_dict`` pickles with the reference's keys, on
+        the CPU so either side can load them."""
+        os.makedirs(model_dir, exist_ok=True)
+        cpu = lambda sd: {k: v.detach().cpu().clone() for k, v in sd.items()}
+        files = {f"netG_epoch_{epoch}.pth": cpu(self.bG.ema_state_dict())}
+        for i, d in enumerate(self.netsPatD):
+            files[f"netPatD{i}.pth"] = cpu(d.state_dict())
+        for i, d in enumerate(self.netsShpD):
+            files[f"netShpD{i}.pth"] = cpu(d.state_dict())
+        files["netObjSSD.pth"] = cpu(self.netObjSSD.state_dict())
+        files["netObjLSD.pth"] = cpu(self.netObjLSD.state_dict())
+        for name, sd in files.items():
+            torch.save(sd, os.path.join(model_dir, name))
+        return sorted(files)
+
+    def load_model(self, net_g_path: str) -> int:
+        """Resume like the reference's ``build_models`` (ref: trainer.py:152-194): ``cfg.TRAIN.NET_G`` names the
+        generator snapshot, the discriminators are read from the same directory; returns the epoch to continue
+        from (snapshot epoch + 1).  Rebuilds the flat buckets (fresh Adam moments, like the reference; EMA restarts
+        from the loaded weights, ref: trainer.py:303)."""
+        load = lambda f: torch.load(f, map_location="cpu")
+        to = lambda sd: {k: v.to(self.device) for k, v in sd.items()}
+        self.netG.load_state_dict(to(load(net_g_path)), strict=True)
+        d = os.path.dirname(net_g_path)
+        for i, net in enumerate(self.netsPatD):
+            net.load_state_dict(to(load(os.path.join(d, f"netPatD{i}.pth"))), strict=True)
+        for i, net in enumerate(self.netsShpD):
+            net.load_state_dict(to(load(os.path.join(d, f"netShpD{i}.pth"))), strict=True)
+        self.netObjSSD.load_state_dict(to(load(os.path.join(d, "netObjSSD.pth"))), strict=True)
+        self.netObjLSD.load_state_dict(to(load(os.path.join(d, "netObjLSD.pth"))), strict=True)
+        self._flatten()
+        self.bShp = [FlatBucket(n) for n in self.netsShpD]
+        self.bObj = [FlatBucket(self.netObjSSD), FlatBucket(self.netObjLSD)]
+        name = os.path.basename(net_g_path)
+        return int(name[name.rfind("_") + 1:name.rfind(".")]) + 1
+
     def _update(self, bucket, err, lr, gs):
         """backward + all-reduce + Adam for one discriminator.  ``err`` may be the int 0 of an empty roi set (the
         reference then skips the optimiser step, trainer.py:428-431); with several ranks the exchange must stay
@@ -384,8 +427,11 @@ class StepBTrainer(StepATrainer):
         gs = 1.0 / self.world
         sent, imgs, hmaps, rois = inp["sent_emb"], inp["imgs"], inp["hmaps"], inp["rois"]
         fm_rois, num_rois = inp["fm_rois"], inp["num_rois"]
-        host = lambda t: t.detach().cpu() if torch.is_tensor(t) else t      # box tables are read on the host
-        rois_h, fm_h, nr_h = [host(r) for r in rois], host(fm_rois), host(num_rois)
+        hb = inp.get("host_boxes")
+        if hb is None:                               # device-only batch: one synchronising read of the box tables
+            host = lambda t: t.detach().cpu() if torch.is_tensor(t) else t
+            hb = {"rois": [host(r) for r in rois], "fm_rois": host(fm_rois), "num_rois": host(num_rois)}
+        rois_h, fm_h, nr_h = hb["rois"], hb["fm_rois"], hb["num_rois"]
         self.bG.requires_grad_(True)
         fake_imgs, bt_c_codes, _att, _bt_att, mu, logvar = self.generate(inp)
         bt_c_codes = [c.detach() for c in bt_c_codes]       # ref: trainer.py:393 -- constants for every loss below

@@ -153,3 +153,41 @@ def test_step_b_wiring(dry):
     for b in [t.bG, *t._d_buckets()]:
         for p, o in zip(b.params, b.offsets):
             assert p.data.data_ptr() == b.flat[o:].data_ptr() and p.grad.data_ptr() == b.grad[o:].data_ptr()
+
+
+def test_checkpoint_files_round_trip(dry, tmp_path):
+    """f4: the reference's snapshot file set (ref: trainer.py:251-273) written by StepBTrainer.save_model loads back
+    (strict) into a fresh trainer with identical tensors, and -- where /root/reference is mounted -- into the
+    reference's own modules with load_state_dict(strict=True), which is what its build_models does (152-194)."""
+    t = trainer.StepBTrainer(device="cpu", seed=0)
+    with torch.no_grad():
+        for b in [t.bG, *t._d_buckets()]:
+            b.flat.copy_(torch.randn(b.flat.shape))
+        t.bG.avg.copy_(t.bG.flat * 0.5)
+    files = t.save_model(str(tmp_path), 7)
+    assert files == sorted(["netG_epoch_7.pth", "netPatD0.pth", "netPatD1.pth", "netPatD2.pth", "netShpD0.pth",
+                            "netShpD1.pth", "netShpD2.pth", "netObjSSD.pth", "netObjLSD.pth"])
+    u = trainer.StepBTrainer(device="cpu", seed=1)
+    assert u.load_model(str(tmp_path / "netG_epoch_7.pth")) == 8
+    for (ka, a), (kb, b) in zip(u.netG.state_dict().items(), t.bG.ema_state_dict().items()):
+        assert ka == kb and torch.equal(a, b), ka                         # the generator file holds the EMA weights
+    assert torch.equal(u.bG.avg, u.bG.flat)
+    for na, nb in zip([*u.netsPatD, *u.netsShpD, u.netObjSSD, u.netObjLSD],
+                      [*t.netsPatD, *t.netsShpD, t.netObjSSD, t.netObjLSD]):
+        for (ka, a), (kb, b) in zip(na.state_dict().items(), nb.state_dict().items()):
+            assert ka == kb and torch.equal(a, b), ka
+    for b in [u.bG, *u._d_buckets()]:                                      # parameters are bucket views again
+        for p, o in zip(b.params, b.offsets):
+            assert p.data.data_ptr() == b.flat[o:].data_ptr()
+    if refimport.available():
+        ref = refimport.load()
+        pairs = [("netG_epoch_7.pth", ref.model.G_NET(80)), ("netPatD0.pth", ref.model.PAT_D_NET64()),
+                 ("netPatD1.pth", ref.model.PAT_D_NET128()), ("netPatD2.pth", ref.model.PAT_D_NET256()),
+                 ("netShpD0.pth", ref.model.SHP_D_NET64(80)), ("netShpD1.pth", ref.model.SHP_D_NET128(80)),
+                 ("netShpD2.pth", ref.model.SHP_D_NET256(80)), ("netObjSSD.pth", ref.model.OBJ_SS_D_NET(80)),
+                 ("netObjLSD.pth", ref.model.OBJ_LS_D_NET(80))]
+        for name, net in pairs:
+            sd = torch.load(str(tmp_path / name), map_location=lambda storage, loc: storage)
+            net.load_state_dict(sd)                                         # strict, like trainer.py:155-191
+            back = net.state_dict()
+            assert all(torch.equal(back[k], sd[k]) for k in sd), name
