@@ -31,17 +31,17 @@ def nsets(bytes_per_set):
     return int(min(64, max(4, 2.5 * L2_BYTES // max(bytes_per_set, 1) + 1)))
 
 
+SIDE = None   # every launch of this file (forward, autograd backward, capture, events) goes to this one stream
+
+
 def time_graph(fns, replays=7):
-    """fns: list of zero-argument callables (one per input set).  Returns ms per call."""
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for f in fns:                      # warm-up (allocator, kernel attributes)
-            f()
-    torch.cuda.current_stream().wait_stream(side)
+    """fns: list of zero-argument callables (one per input set), called with SIDE as the current stream.
+    Returns ms per call."""
+    for f in fns:                          # warm-up (allocator, kernel attributes)
+        f()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g, stream=side):
+    with torch.cuda.graph(g, stream=SIDE):
         for f in fns:
             f()
     ts = []
@@ -163,11 +163,15 @@ def object_path(out, quick):
 
 
 def collect(quick=True):
+    global SIDE
     out = []
-    with torch.no_grad():
-        pass
-    attention_sweep(out, quick)
-    object_path(out, quick)
+    SIDE = torch.cuda.Stream()
+    SIDE.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(SIDE):
+        attention_sweep(out, quick)
+        object_path(out, quick)
+    torch.cuda.current_stream().wait_stream(SIDE)
+    torch.cuda.synchronize()
     return out
 
 

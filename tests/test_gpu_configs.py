@@ -110,6 +110,33 @@ def test_config3_func_attention_pairs(B):
     close(cg.grad, ctx.grad, what="g_context")
 
 
+@pytest.mark.parametrize("B", [16, 32])
+def test_config3_words_loss_all_pairs(B):
+    """BASELINE configs[2], the B^2 = 256 / 1024 (image, caption) pairs of words_loss in ONE launch (the reference
+    loops over the captions): both loss directions, the caption-wise attention maps and the gradient reaching the image
+    features, ragged caption lengths passed as a DEVICE tensor (no host read), class-id mask on."""
+    from objgan_b200 import losses
+    g = torch.Generator().manual_seed(85 + B)
+    img = torch.randn(B, 256, 17, 17, generator=g)
+    words = torch.randn(B, 256, 18, generator=g)
+    lens = torch.randint(4, 19, (B,), generator=g)
+    lens[0] = 18
+    class_ids = np.arange(B) // 2                         # pairs of captions share a class -> masked entries
+    labels = torch.arange(B)
+    ir = img.clone().requires_grad_(True)
+    o0, o1, omaps, oacc = O.words_loss(ir, words, labels, lens.tolist(), class_ids, B)
+    go = torch.autograd.grad(o0 + 2.0 * o1, ir)[0]
+    ig = img.to(DEV).requires_grad_(True)
+    w0, w1, maps, acc = losses.words_loss(ig, words.to(DEV), labels.to(DEV), lens.to(DEV), class_ids, B)
+    close(w0, o0.detach(), what="w_loss0")
+    close(w1, o1.detach(), what="w_loss1")
+    assert abs(float(acc) - oacc) < 1e-4
+    for a, b in zip(maps, omaps):
+        close(a, b.detach(), what="att_map")
+    (w0 + 2.0 * w1).backward()
+    close(ig.grad, go, 2e-3, what="g_img_features")
+
+
 @pytest.mark.parametrize("ih", [64, 128])
 def test_config4_bu_attention_and_paint_b32(ih):
     """BASELINE configs[3]: batch 32, 10 boxes per image: bottom-up attention, then the three mask paints of a stage
