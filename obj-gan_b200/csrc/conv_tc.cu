@@ -84,6 +84,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// bounded wait (CTA-pair kernel): a broken cross-CTA barrier protocol traps after ~2 s instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t done = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((++spins & 255) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -144,6 +163,62 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- CTA-pair (cta_group::2) forms: two CTAs of a (2,1,1) cluster issue ONE M = 256 MMA; PTX forms as in the
+// vendored CUTLASS headers (cute/arch/copy_sm100_tma.hpp SM100_TMA_2SM_LOAD_*, mma_sm100_umma.hpp
+// SM100_MMA_F16BF16_2x1SM_SS, cutlass/arch/barrier.h umma_arrive_multicast_2x1SM, tmem_allocator_sm100.hpp) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: "the leader's"
+// both CTAs of the pair load into their OWN shared memory; the transaction bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs: 128 rows each] (+)= A[each CTA's own smem] * B[N/2 rows from each CTA's smem]; leader only
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs once all MMAs issued so far have completed
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
 }
 
 __device__ __forceinline__ float tc_act(float v, int act, float slope) {
@@ -558,6 +633,224 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant of the two-tile kernel (cta_group::2): the two CTAs of a (2,1,1) cluster each own TWO 128-pixel
+// tiles (4 tiles per pair) and HALF of every weight stage.  One tcgen05.mma.cta_group::2 (M = 256 = 128 pixels of
+// each CTA, N = BN) is issued by the leader per (tile half, product term, k-step); the tensor cores of both SMs read
+// their own A rows and BN/2 weight rows from each CTA, so per SM the shared-memory read per MMA drops from
+// 16*2*(128 + BN) bytes to 16*2*(128 + BN/2) and a weight stage from 2*BN*128 to BN*128 bytes (4 stages fit).
+//   barriers: fullA / fullB live in the LEADER (both CTAs' TMA loads credit their bytes there: PEER_BIT_MASK);
+//             emptyA / emptyB / tmem_full exist in both CTAs, released by the leader's multicast tcgen05.commit.
+//   TMEM: allocated with cta_group::2 by warp 1 of each CTA; each CTA's epilogue reads its own 128 lanes.
+// ------------------------------------------------------------------------------------------------
+template <int BN, bool TALL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2x_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                 const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                 const TcParams p) {
+  constexpr int AS = 3, BS = 4;
+  constexpr int BNH = BN / 2;                                 // weight rows held by each CTA
+  constexpr uint32_t A_BYTES = (TALL ? 160 : TC_BM) * 128;
+  constexpr uint32_t B_BYTES = BNH * 128;
+  constexpr uint32_t A_SLOT = 2 * A_BYTES, B_SLOT = 2 * B_BYTES;
+  constexpr uint32_t ACC_STRIDE = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + AS * A_SLOT;
+  __shared__ __align__(8) uint64_t fullA[AS], emptyA[AS], fullB[BS], emptyB[BS], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int col0 = blockIdx.y * BN;
+  const int nk = p.taps.n * p.cchunks;
+  const bool split3 = p.nsplit == 3;
+  int tn0[2], th0[2], tw0[2];
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    int t = blockIdx.x * 2 + hf;      // blockIdx.x = 2 * pair + rank: tiles 4*pair + 2*rank + hf
+    const int tw_i = t % p.tiles_w;
+    t /= p.tiles_w;
+    const int th_i = t % p.tiles_h;
+    const int tn_i = t / p.tiles_h;   // past the last image for a padded tile count: TMA zero-fills, rows masked
+    tn0[hf] = tn_i * p.TN; th0[hf] = th_i * p.TH; tw0[hf] = tw_i * p.TW;
+  }
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_ah);
+    prefetch_tmap(&map_bh);
+    for (int s = 0; s < AS; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // the peer's barriers are initialised before anything may arrive on them
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      auto load_b = [&](int tap, int c0) {
+        mbar_wait_bounded(&emptyB[bs], bph ^ 1);
+        uint8_t* sb = smem_b + (size_t)bs * B_SLOT;
+        if (leader) mbar_expect_tx(&fullB[bs], 2 * (split3 ? B_SLOT : B_BYTES));     // both CTAs' halves
+        tma2_load_3d(sb, &map_bh, &fullB[bs], c0, col0 + (int)rank * BNH, p.taps.widx[tap]);
+        if (split3) tma2_load_3d(sb + B_BYTES, &map_bl, &fullB[bs], c0, col0 + (int)rank * BNH, p.taps.widx[tap]);
+        if (++bs == BS) { bs = 0; bph ^= 1; }
+      };
+      auto load_a = [&](int hf, int tap, int c0) {
+        mbar_wait_bounded(&emptyA[as], aph ^ 1);
+        uint8_t* sa = smem_a + (size_t)as * A_SLOT;
+        if (leader) mbar_expect_tx(&fullA[as], 2 * (split3 ? A_SLOT : A_BYTES));
+        const int ws = tw0[hf] + p.taps.dw[tap], hs = th0[hf] + p.taps.dh[tap], ns = tn0[hf] + p.taps.dn[tap];
+        tma2_load_4d(sa, &map_ah, &fullA[as], c0, ws, hs, ns);
+        if (split3) tma2_load_4d(sa + A_BYTES, &map_al, &fullA[as], c0, ws, hs, ns);
+        if (++as == AS) { as = 0; aph ^= 1; }
+      };
+      if (TALL) {
+        const int groups = (p.taps.n / 3) * p.cchunks;
+        for (int g = 0; g < groups; ++g) {
+          const int kwi = g / p.cchunks, cc = g - kwi * p.cchunks;
+          const int c0 = cc * TC_BK, t0 = kwi * 3;
+          load_a(0, t0, c0);
+          load_b(t0, c0);
+          load_a(1, t0, c0);
+          load_b(t0 + 1, c0);
+          load_b(t0 + 2, c0);
+        }
+      } else {
+        for (int it = 0; it < nk; ++it) {
+          const int tap = it / p.cchunks, cc = it - tap * p.cchunks;
+          const int c0 = cc * TC_BK;
+          load_b(tap, c0);
+          load_a(0, tap, c0);
+          load_a(1, tap, c0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_f16(2 * TC_BM, BN);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      auto mma_half = [&](uint32_t sa, uint32_t rowoff, uint32_t sb, int hf, bool first, int ks) {
+        const uint64_t ah = make_desc_sw128(sa + rowoff), al = make_desc_sw128(sa + A_BYTES + rowoff);
+        const uint64_t bh = make_desc_sw128(sb), bl = make_desc_sw128(sb + B_BYTES);
+        const uint32_t d = tmem_base + hf * ACC_STRIDE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k >= ks) break;
+          const uint64_t koff = (uint64_t)((k * 32) >> 4);
+          const uint32_t acc = (!first || k > 0) ? 1u : 0u;
+          if (split3) {
+            umma2_f16(d, al + koff, bh + koff, idesc, acc);
+            umma2_f16(d, ah + koff, bl + koff, idesc, 1u);
+            umma2_f16(d, ah + koff, bh + koff, idesc, 1u);
+          } else {
+            umma2_f16(d, ah + koff, bh + koff, idesc, acc);
+          }
+        }
+      };
+      if (TALL) {
+        const int groups = (p.taps.n / 3) * p.cchunks;
+        for (int g = 0; g < groups; ++g) {
+          const int a0 = as, a1 = (as + 1) % AS;
+          const uint32_t aph0 = aph, aph1 = (as + 1 == AS) ? (aph ^ 1) : aph;
+          const int ks = ((g + 1) % p.cchunks == 0) ? p.klast : 4;
+          for (int j = 0; j < 3; ++j) {
+            mbar_wait_bounded(&fullB[bs], bph);
+            const uint32_t sb = smem_u32(smem_b + (size_t)bs * B_SLOT);
+            if (j == 0) mbar_wait_bounded(&fullA[a0], aph0);
+            tc_fence_after();
+            mma_half(smem_u32(smem_a + (size_t)a0 * A_SLOT), j * 16 * 128, sb, 0, g == 0 && j == 0, ks);
+            if (j == 0) {
+              mbar_wait_bounded(&fullA[a1], aph1);
+              tc_fence_after();
+            }
+            mma_half(smem_u32(smem_a + (size_t)a1 * A_SLOT), j * 16 * 128, sb, 1, g == 0 && j == 0, ks);
+            umma2_commit(&emptyB[bs]);
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+          umma2_commit(&emptyA[a0]);
+          umma2_commit(&emptyA[a1]);
+          for (int k = 0; k < 2; ++k)
+            if (++as == AS) { as = 0; aph ^= 1; }
+        }
+      } else {
+        for (int it = 0; it < nk; ++it) {
+          mbar_wait_bounded(&fullB[bs], bph);
+          const uint32_t sb = smem_u32(smem_b + (size_t)bs * B_SLOT);
+          const int ks = ((it + 1) % p.cchunks == 0) ? p.klast : 4;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            mbar_wait_bounded(&fullA[as], aph);
+            tc_fence_after();
+            mma_half(smem_u32(smem_a + (size_t)as * A_SLOT), 0, sb, hf, it == 0, ks);
+            umma2_commit(&emptyA[as]);
+            if (++as == AS) { as = 0; aph ^= 1; }
+          }
+          umma2_commit(&emptyB[bs]);
+          if (++bs == BS) { bs = 0; bph ^= 1; }
+        }
+      }
+      umma2_commit(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tw = row % p.TW;
+    const int th = (row / p.TW) % p.TH;
+    const int tn = row / (p.TW * p.TH);
+    const TcScale sc = tc_scale(p.amax_a, p.amax_b);
+    mbar_wait_bounded(&tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {
+      const int n = tn0[hf] + tn, h = th0[hf] + th, w = tw0[hf] + tw;
+      const int oy = p.osy * h + p.opy, ox = p.osx * w + p.opx;
+      const bool row_ok = (n < p.N) && (h < p.OH) && (w < p.OW) && (oy < p.OHfull) && (ox < p.OWfull);
+      float* yrow = p.y + (long long)n * p.ysn + (long long)oy * p.ysh + (long long)ox * p.ysw + col0;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * ACC_STRIDE + c), r);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c + j < BN && col0 + c + j < p.K) {
+              float4 v = make_float4(__uint_as_float(r[j]) * sc.fa * sc.fb, __uint_as_float(r[j + 1]) * sc.fa * sc.fb,
+                                     __uint_as_float(r[j + 2]) * sc.fa * sc.fb, __uint_as_float(r[j + 3]) * sc.fa * sc.fb);
+              if (p.bias) {
+                float4 b = ldg4(p.bias + col0 + c + j);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if (p.act != OG_ACT_NONE) {
+                v.x = tc_act(v.x, p.act, p.slope); v.y = tc_act(v.y, p.act, p.slope);
+                v.z = tc_act(v.z, p.act, p.slope); v.w = tc_act(v.w, p.act, p.slope);
+              }
+              *reinterpret_cast<float4*>(yrow + c + j) = v;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();                 // neither CTA frees TMEM / leaves while the pair's MMAs or arrivals are in flight
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -967,6 +1260,32 @@ int launch_tc2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
   return (int)cudaGetLastError();
 }
 
+// CTA-pair launch: grid.x = tile pairs rounded up to an even count, clusters of two consecutive CTAs along x
+template <int BN, bool TALL>
+int launch_tc2x(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                const TcParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)3 * (2 * (TALL ? 160 : TC_BM) * 128) + (size_t)4 * (2 * (BN / 2) * 128) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2x_kernel<BN, TALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((grid.x + 1) / 2 * 2, grid.y, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, conv_tc2x_kernel<BN, TALL>, ah, al, bh, bl, p);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -1069,6 +1388,18 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
   if (!no_tc2 && p.ksplit == 1 && (BNsel == 208 || BNsel == 256) && (long long)grid.x * grid.y >= tc2_min) {
     dim3 grid2((grid.x + 1) / 2, grid.y, 1);
     static const bool no_tall = getenv("OG_NO_TALL") != nullptr;
+    // CTA pairs (cta_group::2): each CTA loads half of every weight stage (box of BNsel / 2 rows)
+    static const bool pair = getenv("OG_TC2X") != nullptr && atoi(getenv("OG_TC2X")) != 0;
+    CUtensorMap pbh = mbh, pbl = mbl;
+    if (pair) {
+      unsigned hbox[3] = {(unsigned)TC_BK, (unsigned)(BNsel / 2), 1u};
+      if ((rc = make_map(&pbh, wh, 3, bdims, bstr, hbox))) return rc;
+      if (nsplit == 3) {
+        if ((rc = make_map(&pbl, wl, 3, bdims, bstr, hbox))) return rc;
+      } else {
+        pbl = pbh;
+      }
+    }
     if (!no_tall && tap_layout == 1 && ntaps % 3 == 0 && BNsel == 208 && TN == 1 && TH == 8 && TW == 16) {
       // taps are ordered (column-major) in groups of three consecutive source rows: one tall A patch per group
       unsigned tbox[4] = {(unsigned)TC_BK, 16u, 10u, 1u};
@@ -1080,8 +1411,12 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
         tal = tah;
       }
       p.tall = 1;
+      if (pair) return launch_tc2x<208, true>(tah, tal, pbh, pbl, p, grid2, stream);
       return launch_tc2<208, true>(tah, tal, mbh, mbl, p, grid2, stream);
     }
+    if (pair)
+      return BNsel == 208 ? launch_tc2x<208, false>(mah, mal, pbh, pbl, p, grid2, stream)
+                          : launch_tc2x<256, false>(mah, mal, pbh, pbl, p, grid2, stream);
     return BNsel == 208 ? launch_tc2<208, false>(mah, mal, mbh, mbl, p, grid2, stream)
                         : launch_tc2<256, false>(mah, mal, mbh, mbl, p, grid2, stream);
   }

@@ -165,9 +165,11 @@ def objD_loss(netObjD, real_imgs, fake_imgs, seg_conditions, raw_conditions, raw
         vi = torch.as_tensor(valid, device=dev)
         fm_t = fm_rois if torch.is_tensor(fm_rois) else torch.as_tensor(fm_rois)
         nr_t = num_rois if torch.is_tensor(num_rois) else torch.as_tensor(num_rois)
-        pooled2 = netObjD(real_imgs[vi], fake_seg[vi], fm_t[vi.to(fm_t.device)], nr_t[vi.to(nr_t.device)])
-        fake_features2, classes2, bt_c_codes2 = feat_select(pooled2, raw_bt_c_codes, fm_t[vi.to(fm_t.device)],
-                                                            nr_t[vi.to(nr_t.device)], is_large_scale)
+        # index the (host or device) box tables with an index on THEIR device: no device -> host read of `valid`
+        sel = lambda t: t[torch.as_tensor(valid, device=t.device)]
+        pooled2 = netObjD(real_imgs[vi], fake_seg[vi], sel(fm_t), sel(nr_t))
+        fake_features2, classes2, bt_c_codes2 = feat_select(pooled2, raw_bt_c_codes, sel(fm_t), sel(nr_t),
+                                                            is_large_scale)
     n = len(classes)
     if n == 0:
         return 0

@@ -133,3 +133,19 @@ def test_two_tile_kernels_on_small_cases():
                         "test_tc_conv_fwd_dgrad and f16x3 and (case0 or case1 or case3 or case6)"],
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_cta_pair_kernels_on_small_cases():
+    """The cta_group::2 variant of the two-tile kernel (conv_tc2x: clusters of two CTAs issue one M = 256 MMA, each
+    CTA holding half of every weight stage) on the parity cases that reach the two-tile path, forced through
+    OG_TC2X=1 / OG_TC2_MIN in a fresh process (the library reads the variables once).  Odd tile-pair counts and
+    ragged tiles included (case 4 has 5 x 5 tiles per image)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, OG_TC2_MIN="4", OG_TC2X="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k",
+                        "test_tc_conv_fwd_dgrad and (case0 or case1 or case3 or case6)"],
+                       env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
