@@ -139,9 +139,20 @@ def object_path(out, quick):
         ms_b = time_graph([lambda gi=gi: ops._call("og_roi_align_avg_bwd", g.data_ptr(), H, H, C, rois.data_ptr(), nr, 5,
                                                    5, 1 / 16, gi.data_ptr()) for gi in gins])
         wbytes = 4.0 * nr * C * 25
-        rec = dict(config=4, op="RoIAlignAvg(5,5,1/16)", B=B, rois=nr, C=C, H=H, fused_fwd_ms=round(ms_f, 4),
-                   fused_bwd_ms=round(ms_b, 4), fwd_out_gbs=round(wbytes / ms_f / 1e6, 1),
-                   fwd_frac_of_hbm_peak=round(wbytes / ms_f / 1e6 / HBM, 3), input_sets=K)
+        # channels-last kernels (what the object discriminators run): same values, coalesced 16-byte accesses
+        nfeats = [f.permute(0, 2, 3, 1).contiguous() for f in feats]
+        nouts = [torch.empty(nr, 5, 5, C, device=DEV) for _ in range(K)]
+        ms_nf = time_graph([lambda f=f, o=o: ops._call("og_roi_align_avg_nhwc_fwd", f.data_ptr(), H, H, C, rois.data_ptr(),
+                                                       nr, 5, 5, 1 / 16, o.data_ptr()) for f, o in zip(nfeats, nouts)])
+        ms_nb = time_graph([lambda gi=gi: ops._call("og_roi_align_avg_nhwc_bwd", g.data_ptr(), H, H, C, rois.data_ptr(), nr,
+                                                    5, 5, 1 / 16, gi.data_ptr()) for gi in gins])
+        rec = dict(config=4, op="RoIAlignAvg(5,5,1/16)", B=B, rois=nr, C=C, H=H, nhwc_fwd_ms=round(ms_nf, 4),
+                   nhwc_bwd_ms=round(ms_nb, 4), nhwc_fwd_out_gbs=round(wbytes / ms_nf / 1e6, 1),
+                   nhwc_fwd_frac_of_hbm_peak=round(wbytes / ms_nf / 1e6 / HBM, 3),
+                   nchw_fused_fwd_ms=round(ms_f, 4), nchw_fused_bwd_ms=round(ms_b, 4), input_sets=K,
+                   note2="algorithmic bytes = the pooled output only (4*C*25 per roi, SURVEY 8d); the gather also reads "
+                         "up to (6x6 samples x 4 neighbours) x 4C bytes per roi from L2/HBM")
+        del nfeats, nouts
         if ref:
             o6 = torch.zeros(nr, C, 6, 6, device=DEV)
             g6 = torch.randn_like(o6)

@@ -44,6 +44,15 @@ int og_roi_align_avg_fwd(const float* features, int height, int width, int chann
 int og_roi_align_avg_bwd(const float* grad_out, int height, int width, int channels, const float* rois, int num_rois,
                          int AH, int AW, float spatial_scale, float* grad_features, cudaStream_t stream);
 
+/* channels-last variant (features NHWC [B][H][W][C], out NHWC [R][AH][AW][C], C % 4 == 0): identical values, coalesced
+ * 16-byte loads / stores / vector atomics; what the object discriminators use internally (their feature maps are
+ * produced channels-last), the NCHW entry points above stay the drop-in for the reference's callers. */
+int og_roi_align_avg_nhwc_fwd(const float* features, int height, int width, int channels, const float* rois,
+                              int num_rois, int AH, int AW, float spatial_scale, float* out, cudaStream_t stream);
+int og_roi_align_avg_nhwc_bwd(const float* grad_out, int height, int width, int channels, const float* rois,
+                              int num_rois, int AH, int AW, float spatial_scale, float* grad_features,
+                              cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Convolutions / linear layers as implicit GEMM -- replaces the cuDNN/cuBLAS calls behind nn.Conv2d /
  * nn.Linear in ref: model.py:36-39 (conv3x3), 43-49 (upBlock), 52-60 (downBlock_G), 63-81 (HmapResBlock),

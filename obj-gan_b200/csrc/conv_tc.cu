@@ -851,6 +851,229 @@ conv_tc2x_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent CTA-pair kernel (cta_group::2 + static tile scheduler + double-buffered TMEM accumulators).
+// grid = 2 x (number of SM pairs); cluster c processes work units c, c + nclusters, ...; a unit = (pair of adjacent
+// 128-pixel tiles: one per CTA, N tile).  Per unit the leader issues M = 256 MMAs into accumulator stage (k & 1)
+// (TMEM columns [0, BN) / [256, 256 + BN)); the epilogue warps of both CTAs drain stage k & 1 while the MMAs of unit
+// k + 1 already run into the other stage, so TMEM allocation, barrier setup and the epilogue are off the critical
+// path.  Weight stages are shared by the pair (each CTA loads BN/2 rows), which gives the same L2 -> SM weight
+// traffic per pixel tile as two tiles per CTA, with one tile per CTA.
+//   barriers: fullA/fullB (leader; both CTAs' TMA bytes), emptyA/emptyB/tmem_full[2] (both CTAs; multicast commit),
+//             tmem_empty[2] (leader; 8 arrivals = 4 epilogue warps of each CTA).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+
+template <int BN, bool TALL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tcp_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                const TcParams p, const int nunits, const int ntn) {
+  constexpr int AS = 3, BS = 4;
+  constexpr int BNH = BN / 2;
+  constexpr uint32_t A_BYTES = (TALL ? 160 : TC_BM) * 128;
+  constexpr uint32_t B_BYTES = BNH * 128;
+  constexpr uint32_t A_SLOT = 2 * A_BYTES, B_SLOT = 2 * B_BYTES;
+  constexpr uint32_t ACC_STRIDE = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + AS * A_SLOT;
+  __shared__ __align__(8) uint64_t fullA[AS], emptyA[AS], fullB[BS], emptyB[BS], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int nk = p.taps.n * p.cchunks;
+  const bool split3 = p.nsplit == 3;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_ah);
+    prefetch_tmap(&map_bh);
+    for (int s = 0; s < AS; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // this CTA's tile of unit u
+  auto tile_of = [&](int u, int& n0, int& h0, int& w0, int& col0) {
+    const int pp = u / ntn;
+    col0 = (u - pp * ntn) * BN;
+    int t = pp * 2 + (int)rank;
+    const int tw_i = t % p.tiles_w;
+    t /= p.tiles_w;
+    const int th_i = t % p.tiles_h;
+    const int tn_i = t / p.tiles_h;   // past the last image for an odd tile count: TMA zero-fills, rows are masked
+    n0 = tn_i * p.TN; h0 = th_i * p.TH; w0 = tw_i * p.TW;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int u = cluster; u < nunits; u += nclusters) {
+        int n0, h0, w0, col0;
+        tile_of(u, n0, h0, w0, col0);
+        auto load_b = [&](int tap, int c0) {
+          mbar_wait_bounded(&emptyB[bs], bph ^ 1);
+          uint8_t* sb = smem_b + (size_t)bs * B_SLOT;
+          if (leader) mbar_expect_tx(&fullB[bs], 2 * (split3 ? B_SLOT : B_BYTES));
+          tma2_load_3d(sb, &map_bh, &fullB[bs], c0, col0 + (int)rank * BNH, p.taps.widx[tap]);
+          if (split3) tma2_load_3d(sb + B_BYTES, &map_bl, &fullB[bs], c0, col0 + (int)rank * BNH, p.taps.widx[tap]);
+          if (++bs == BS) { bs = 0; bph ^= 1; }
+        };
+        auto load_a = [&](int tap, int c0) {
+          mbar_wait_bounded(&emptyA[as], aph ^ 1);
+          uint8_t* sa = smem_a + (size_t)as * A_SLOT;
+          if (leader) mbar_expect_tx(&fullA[as], 2 * (split3 ? A_SLOT : A_BYTES));
+          const int ws = w0 + p.taps.dw[tap], hs = h0 + p.taps.dh[tap], ns = n0 + p.taps.dn[tap];
+          tma2_load_4d(sa, &map_ah, &fullA[as], c0, ws, hs, ns);
+          if (split3) tma2_load_4d(sa + A_BYTES, &map_al, &fullA[as], c0, ws, hs, ns);
+          if (++as == AS) { as = 0; aph ^= 1; }
+        };
+        if (TALL) {
+          const int groups = (p.taps.n / 3) * p.cchunks;
+          for (int g = 0; g < groups; ++g) {
+            const int kwi = g / p.cchunks, cc = g - kwi * p.cchunks;
+            const int c0 = cc * TC_BK, t0 = kwi * 3;
+            load_a(t0, c0);
+            load_b(t0, c0);
+            load_b(t0 + 1, c0);
+            load_b(t0 + 2, c0);
+          }
+        } else {
+          for (int it = 0; it < nk; ++it) {
+            const int tap = it / p.cchunks, cc = it - tap * p.cchunks;
+            load_b(tap, cc * TC_BK);
+            load_a(tap, cc * TC_BK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_f16(2 * TC_BM, BN);
+      int as = 0, bs = 0, k = 0;
+      uint32_t aph = 0, bph = 0;
+      auto mma_step = [&](uint32_t sa, uint32_t rowoff, uint32_t sb, uint32_t d, bool first, int ks) {
+        const uint64_t ah = make_desc_sw128(sa + rowoff), al = make_desc_sw128(sa + A_BYTES + rowoff);
+        const uint64_t bh = make_desc_sw128(sb), bl = make_desc_sw128(sb + B_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (kk >= ks) break;
+          const uint64_t koff = (uint64_t)((kk * 32) >> 4);
+          const uint32_t acc = (!first || kk > 0) ? 1u : 0u;
+          if (split3) {
+            umma2_f16(d, al + koff, bh + koff, idesc, acc);
+            umma2_f16(d, ah + koff, bl + koff, idesc, 1u);
+            umma2_f16(d, ah + koff, bh + koff, idesc, 1u);
+          } else {
+            umma2_f16(d, ah + koff, bh + koff, idesc, acc);
+          }
+        }
+      };
+      for (int u = cluster; u < nunits; u += nclusters, ++k) {
+        const int st = k & 1;
+        mbar_wait_bounded(&tmem_empty[st], ((k >> 1) & 1) ^ 1);       // both CTAs' epilogues drained this stage
+        tc_fence_after();
+        const uint32_t d = tmem_base + st * ACC_STRIDE;
+        if (TALL) {
+          const int groups = (p.taps.n / 3) * p.cchunks;
+          for (int g = 0; g < groups; ++g) {
+            const int ks = ((g + 1) % p.cchunks == 0) ? p.klast : 4;
+            mbar_wait_bounded(&fullA[as], aph);
+            const uint32_t sa = smem_u32(smem_a + (size_t)as * A_SLOT);
+            for (int j = 0; j < 3; ++j) {
+              mbar_wait_bounded(&fullB[bs], bph);
+              tc_fence_after();
+              mma_step(sa, j * 16 * 128, smem_u32(smem_b + (size_t)bs * B_SLOT), d, g == 0 && j == 0, ks);
+              umma2_commit(&emptyB[bs]);
+              if (++bs == BS) { bs = 0; bph ^= 1; }
+            }
+            umma2_commit(&emptyA[as]);
+            if (++as == AS) { as = 0; aph ^= 1; }
+          }
+        } else {
+          for (int it = 0; it < nk; ++it) {
+            const int ks = ((it + 1) % p.cchunks == 0) ? p.klast : 4;
+            mbar_wait_bounded(&fullB[bs], bph);
+            mbar_wait_bounded(&fullA[as], aph);
+            tc_fence_after();
+            mma_step(smem_u32(smem_a + (size_t)as * A_SLOT), 0, smem_u32(smem_b + (size_t)bs * B_SLOT), d, it == 0, ks);
+            umma2_commit(&emptyA[as]);
+            umma2_commit(&emptyB[bs]);
+            if (++as == AS) { as = 0; aph ^= 1; }
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+        }
+        umma2_commit(&tmem_full[st]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tw = row % p.TW;
+    const int th = (row / p.TW) % p.TH;
+    const int tn = row / (p.TW * p.TH);
+    const TcScale sc = tc_scale(p.amax_a, p.amax_b);
+    int k = 0;
+    for (int u = cluster; u < nunits; u += nclusters, ++k) {
+      const int st = k & 1;
+      int n0, h0, w0, col0;
+      tile_of(u, n0, h0, w0, col0);
+      const int n = n0 + tn, h = h0 + th, w = w0 + tw;
+      const int oy = p.osy * h + p.opy, ox = p.osx * w + p.opx;
+      const bool row_ok = (n < p.N) && (h < p.OH) && (w < p.OW) && (oy < p.OHfull) && (ox < p.OWfull);
+      float* yrow = p.y + (long long)n * p.ysn + (long long)oy * p.ysh + (long long)ox * p.ysw + col0;
+      mbar_wait_bounded(&tmem_full[st], (k >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * ACC_STRIDE + c), r);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c + j < BN && col0 + c + j < p.K) {
+              float4 v = make_float4(__uint_as_float(r[j]) * sc.fa * sc.fb, __uint_as_float(r[j + 1]) * sc.fa * sc.fb,
+                                     __uint_as_float(r[j + 2]) * sc.fa * sc.fb, __uint_as_float(r[j + 3]) * sc.fa * sc.fb);
+              if (p.bias) {
+                float4 b = ldg4(p.bias + col0 + c + j);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if (p.act != OG_ACT_NONE) {
+                v.x = tc_act(v.x, p.act, p.slope); v.y = tc_act(v.y, p.act, p.slope);
+                v.z = tc_act(v.z, p.act, p.slope); v.w = tc_act(v.w, p.act, p.slope);
+              }
+              *reinterpret_cast<float4*>(yrow + c + j) = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[st]);       // this warp's quadrant of stage st is drained
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1286,6 +1509,39 @@ int launch_tc2x(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap&
   return (int)cudaLaunchKernelEx(&cfg, conv_tc2x_kernel<BN, TALL>, ah, al, bh, bl, p);
 }
 
+// persistent CTA-pair launch: one cluster of two CTAs per SM pair
+template <int BN, bool TALL>
+int launch_tcp(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+               const TcParams& p, int ntiles, int ntn, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)3 * (2 * (TALL ? 160 : TC_BM) * 128) + (size_t)4 * (2 * (BN / 2) * 128) + 1024;
+  static bool configured = false;
+  static int sm_pairs = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BN, TALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sm_pairs = sms / 2;
+    configured = true;
+  }
+  const int nunits = ((ntiles + 1) / 2) * ntn;
+  const int nclusters = nunits < sm_pairs ? nunits : sm_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * nclusters, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, conv_tcp_kernel<BN, TALL>, ah, al, bh, bl, p, nunits, ntn);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -1381,6 +1637,34 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
   } else {
     mal = mah;
     mbl = mbh;
+  }
+  // persistent CTA pairs (cta_group::2, double-buffered accumulators): every BN = 208 / 256 problem with enough tiles
+  static const int tcp = getenv("OG_TCP") ? atoi(getenv("OG_TCP")) : 0;
+  static const long long tcp_min = getenv("OG_TCP_MIN") ? atoll(getenv("OG_TCP_MIN")) : 64;
+  if (tcp && p.ksplit == 1 && (BNsel == 208 || BNsel == 256) && (long long)grid.x * grid.y >= tcp_min) {
+    CUtensorMap pbh, pbl;
+    unsigned hbox[3] = {(unsigned)TC_BK, (unsigned)(BNsel / 2), 1u};
+    if ((rc = make_map(&pbh, wh, 3, bdims, bstr, hbox))) return rc;
+    if (nsplit == 3) {
+      if ((rc = make_map(&pbl, wl, 3, bdims, bstr, hbox))) return rc;
+    } else {
+      pbl = pbh;
+    }
+    static const bool no_tall = getenv("OG_NO_TALL") != nullptr;
+    if (!no_tall && tap_layout == 1 && ntaps % 3 == 0 && BNsel == 208 && TN == 1 && TH == 8 && TW == 16) {
+      unsigned tbox[4] = {(unsigned)TC_BK, 16u, 10u, 1u};
+      CUtensorMap tah, tal;
+      if ((rc = make_map(&tah, xh, 4, adims, astr, tbox))) return rc;
+      if (nsplit == 3) {
+        if ((rc = make_map(&tal, xl, 4, adims, astr, tbox))) return rc;
+      } else {
+        tal = tah;
+      }
+      p.tall = 1;
+      return launch_tcp<208, true>(tah, tal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream);
+    }
+    return BNsel == 208 ? launch_tcp<208, false>(mah, mal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream)
+                        : launch_tcp<256, false>(mah, mal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream);
   }
   // large problems: two pixel tiles per CTA share every weight stage (see conv_tc2_kernel)
   static const bool no_tc2 = getenv("OG_NO_TC2") != nullptr;

@@ -206,6 +206,116 @@ __global__ void __launch_bounds__(256) roi_align_avg_bwd_kernel(const float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Channels-last fused RoIAlignAvg: features NHWC [B][H][W][C] (C % 4 == 0), out NHWC [R][AH][AW][C].
+// Same sample coordinates / bilinear arithmetic as above (bit-identical values); what changes is the memory side:
+// a thread owns FOUR consecutive channels, so each of the four neighbour reads of a sample is one coalesced 16-byte
+// load per thread (a warp reads 512 contiguous bytes of one pixel) instead of 4-byte gathers from 4 * C planes, and
+// the pooled row is written with coalesced 16-byte stores.  One CTA = (roi, pooled output row): sample rows oh and
+// oh + 1 (2 x (AW+1) samples per channel) are combined in registers; nothing but the result touches HBM.
+// The discriminators' feature maps are produced channels-last by the conv kernels, so this variant also removes the
+// NHWC -> NCHW -> NHWC round trip around the reference-ABI op (model.py:1241, 1307 call sites).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float roi_bilerp(float ul, float ur, float dl, float dr, float h_ratio, float w_ratio) {
+  return ul * (1. - h_ratio) * (1. - w_ratio) + ur * (1. - h_ratio) * w_ratio + dl * h_ratio * (1. - w_ratio) +
+         dr * h_ratio * w_ratio;
+}
+__global__ void __launch_bounds__(256) roi_align_avg_nhwc_fwd_kernel(const float* __restrict__ feat, float spatial_scale,
+                                                                     int height, int width, int C, int AH, int AW,
+                                                                     const float* __restrict__ rois,
+                                                                     float* __restrict__ out) {
+  __shared__ RoiAxis hs[ROI_MAX_S], ws[ROI_MAX_S];
+  __shared__ float s_batch;
+  const int n = blockIdx.x, oh = blockIdx.y, SH = AH + 1, SW = AW + 1;
+  float bi;
+  if (threadIdx.x < SH + SW) {
+    roi_setup(rois + n * 5, spatial_scale, height, width, SH, SW, hs, ws, bi);
+    if (threadIdx.x == 0) s_batch = bi;
+  }
+  __syncthreads();
+  const RoiAxis h0 = hs[oh], h1 = hs[oh + 1];
+  const float* img = feat + (long long)(int)s_batch * height * width * C;
+  float* orow = out + ((long long)n * AH + oh) * AW * C;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    float4 top_prev = make_float4(0.f, 0.f, 0.f, 0.f), bot_prev = top_prev;
+    for (int pw = 0; pw < SW; ++pw) {
+      const RoiAxis w = ws[pw];
+      float4 top = make_float4(0.f, 0.f, 0.f, 0.f), bot = top;
+      if (w.ok && h0.ok) {
+        const float* p = img + ((long long)h0.start * width + w.start) * C + c;
+        const float4 ul = ldg4(p), ur = ldg4(p + C), dl = ldg4(p + (long long)width * C), dr = ldg4(p + (long long)width * C + C);
+        top.x = roi_bilerp(ul.x, ur.x, dl.x, dr.x, h0.ratio, w.ratio);
+        top.y = roi_bilerp(ul.y, ur.y, dl.y, dr.y, h0.ratio, w.ratio);
+        top.z = roi_bilerp(ul.z, ur.z, dl.z, dr.z, h0.ratio, w.ratio);
+        top.w = roi_bilerp(ul.w, ur.w, dl.w, dr.w, h0.ratio, w.ratio);
+      }
+      if (w.ok && h1.ok) {
+        const float* p = img + ((long long)h1.start * width + w.start) * C + c;
+        const float4 ul = ldg4(p), ur = ldg4(p + C), dl = ldg4(p + (long long)width * C), dr = ldg4(p + (long long)width * C + C);
+        bot.x = roi_bilerp(ul.x, ur.x, dl.x, dr.x, h1.ratio, w.ratio);
+        bot.y = roi_bilerp(ul.y, ur.y, dl.y, dr.y, h1.ratio, w.ratio);
+        bot.z = roi_bilerp(ul.z, ur.z, dl.z, dr.z, h1.ratio, w.ratio);
+        bot.w = roi_bilerp(ul.w, ur.w, dl.w, dr.w, h1.ratio, w.ratio);
+      }
+      if (pw > 0) {
+        // avg_pool2d(kernel 2, stride 1): window summed row-major in fp32, divided by 4 (same order as the NCHW kernel)
+        float4 o;
+        o.x = (((top_prev.x + top.x) + bot_prev.x) + bot.x) / 4.f;
+        o.y = (((top_prev.y + top.y) + bot_prev.y) + bot.y) / 4.f;
+        o.z = (((top_prev.z + top.z) + bot_prev.z) + bot.z) / 4.f;
+        o.w = (((top_prev.w + top.w) + bot_prev.w) + bot.w) / 4.f;
+        st4(orow + (long long)(pw - 1) * C + c, o);
+      }
+      top_prev = top;
+      bot_prev = bot;
+    }
+  }
+}
+
+// adjoint: one CTA = (roi, sample row ph); grad_features NHWC, zero-filled by the caller, 16-byte vector atomics
+__global__ void __launch_bounds__(256) roi_align_avg_nhwc_bwd_kernel(const float* __restrict__ gout, float spatial_scale,
+                                                                     int height, int width, int C, int AH, int AW,
+                                                                     const float* __restrict__ rois,
+                                                                     float* __restrict__ gfeat) {
+  __shared__ RoiAxis hs[ROI_MAX_S], ws[ROI_MAX_S];
+  __shared__ float s_batch;
+  const int n = blockIdx.x, ph = blockIdx.y, SH = AH + 1, SW = AW + 1;
+  float bi;
+  if (threadIdx.x < SH + SW) {
+    roi_setup(rois + n * 5, spatial_scale, height, width, SH, SW, hs, ws, bi);
+    if (threadIdx.x == 0) s_batch = bi;
+  }
+  __syncthreads();
+  const RoiAxis h = hs[ph];
+  if (!h.ok) return;
+  float* img = gfeat + (long long)(int)s_batch * height * width * C;
+  const float* g = gout + (long long)n * AH * AW * C;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    for (int pw = 0; pw < SW; ++pw) {
+      const RoiAxis w = ws[pw];
+      if (!w.ok) continue;
+      float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int dh = -1; dh <= 0; ++dh)
+        for (int dw = -1; dw <= 0; ++dw) {
+          const int oh = ph + dh, ow = pw + dw;
+          if (oh >= 0 && oh < AH && ow >= 0 && ow < AW) {
+            const float4 t = ldg4(g + ((long long)oh * AW + ow) * C + c);
+            gv.x += t.x / 4.f; gv.y += t.y / 4.f; gv.z += t.z / 4.f; gv.w += t.w / 4.f;
+          }
+        }
+      const float hr = h.ratio, wr = w.ratio;
+      const float k00 = (1. - hr) * (1 - wr), k01 = (1. - hr) * wr, k10 = hr * (1 - wr), k11 = (double)hr * wr;
+      float* p = img + ((long long)h.start * width + w.start) * C + c;
+      atomicAdd(reinterpret_cast<float4*>(p), make_float4(gv.x * k00, gv.y * k00, gv.z * k00, gv.w * k00));
+      atomicAdd(reinterpret_cast<float4*>(p + C), make_float4(gv.x * k01, gv.y * k01, gv.z * k01, gv.w * k01));
+      atomicAdd(reinterpret_cast<float4*>(p + (long long)width * C),
+                make_float4(gv.x * k10, gv.y * k10, gv.z * k10, gv.w * k10));
+      atomicAdd(reinterpret_cast<float4*>(p + (long long)width * C + C),
+                make_float4(gv.x * k11, gv.y * k11, gv.z * k11, gv.w * k11));
+    }
+  }
+}
+
 static int roi_ch_per_block(int num_rois, int channels, int S) {
   // enough CTAs to fill 148 SMs a few times over, at least ~2 passes of 256 threads per CTA
   int cpb = channels;
@@ -261,5 +371,29 @@ OG_API int og_roi_align_avg_bwd(const float* grad_out, int height, int width, in
   size_t sm = sizeof(float) * CH_AVG * AH * AW;
   roi_align_avg_bwd_kernel<<<grid, 256, sm, stream>>>(grad_out, spatial_scale, height, width, channels, AH, AW, rois,
                                                       grad_features);
+  OG_RETURN_LAST_ERROR();
+}
+
+// ---- channels-last fused RoIAlignAvg (features / out NHWC; C % 4 == 0) ----
+OG_API int og_roi_align_avg_nhwc_fwd(const float* features, int height, int width, int channels, const float* rois,
+                                     int num_rois, int AH, int AW, float spatial_scale, float* out, cudaStream_t stream) {
+  if (AH + 1 > ROI_MAX_S || AW + 1 > ROI_MAX_S || AH + AW + 2 > 64 || channels % 4) return (int)cudaErrorInvalidValue;
+  if (num_rois == 0 || channels == 0) return 0;
+  int threads = (channels / 4 + 31) / 32 * 32;
+  threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
+  roi_align_avg_nhwc_fwd_kernel<<<dim3(num_rois, AH), threads, 0, stream>>>(features, spatial_scale, height, width,
+                                                                           channels, AH, AW, rois, out);
+  OG_RETURN_LAST_ERROR();
+}
+// grad_features must be zero-filled by the caller
+OG_API int og_roi_align_avg_nhwc_bwd(const float* grad_out, int height, int width, int channels, const float* rois,
+                                     int num_rois, int AH, int AW, float spatial_scale, float* grad_features,
+                                     cudaStream_t stream) {
+  if (AH + 1 > ROI_MAX_S || AW + 1 > ROI_MAX_S || AH + AW + 2 > 64 || channels % 4) return (int)cudaErrorInvalidValue;
+  if (num_rois == 0 || channels == 0) return 0;
+  int threads = (channels / 4 + 31) / 32 * 32;
+  threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
+  roi_align_avg_nhwc_bwd_kernel<<<dim3(num_rois, AH + 1), threads, 0, stream>>>(grad_out, spatial_scale, height, width,
+                                                                               channels, AH, AW, rois, grad_features);
   OG_RETURN_LAST_ERROR();
 }

@@ -630,8 +630,11 @@ class _ObjD(_Base):
         code = self.img_code(x_s)                                           # NHWC (B, S/2^n, S/2^n, feat_dim)
         rois = _get_rois_blob(fm.reshape(b * fm.shape[1], fm.shape[2])[:, :4], np.array([1] * b * cfg.ROI.BOXES_NUM))
         rois_t = torch.from_numpy(rois).to(x_var.device)
-        pooled = self.RoIAlignAvg(ops.to_nchw(code, self.feat_dim), rois_t)  # (B*10, C, 5, 5)
-        pooled = self.roi_code[0](ops.to_nhwc(pooled))                       # conv k4 s1 p1 + bias + LReLU
+        # the feature map is channels-last already: the channels-last RoIAlignAvg kernel (same values as the
+        # reference-ABI NCHW op behind self.RoIAlignAvg) feeds roi_code without any layout round trip
+        pooled = ops.roi_align_avg_nhwc(code, rois_t, self.RoIAlignAvg.aligned_height, self.RoIAlignAvg.aligned_width,
+                                        self.RoIAlignAvg.spatial_scale)     # (B*10, 5, 5, C)
+        pooled = self.roi_code[0](pooled)                                    # conv k4 s1 p1 + bias + LReLU
         out = ops.to_nchw(pooled, pooled.shape[3])
         return out.view(b, cfg.ROI.BOXES_NUM, out.shape[1], out.shape[2], out.shape[3])
 

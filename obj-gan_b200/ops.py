@@ -1302,6 +1302,36 @@ def roi_align_avg(features, rois, ah, aw, scale):
     return _RoIAlignAvg.apply(features, rois, ah, aw, scale)
 
 
+class _RoIAlignAvgNHWC(torch.autograd.Function):
+    """Channels-last fused RoIAlignAvg: features (B, H, W, C) -> (R, ah, aw, C); same values as ``roi_align_avg``."""
+
+    @staticmethod
+    def forward(ctx, features, rois, ah, aw, scale):
+        _chk(features, rois)
+        features, rois = features.contiguous(), rois.contiguous()
+        assert rois.shape[1] == 5 and features.shape[3] % 4 == 0
+        b, h, w, c = features.shape
+        r = rois.shape[0]
+        out = torch.empty((r, ah, aw, c), device=features.device, dtype=torch.float32)
+        _call("og_roi_align_avg_nhwc_fwd", _p(features), h, w, c, _p(rois), r, ah, aw, float(scale), _p(out))
+        ctx.cfg = (b, h, w, c, ah, aw, scale)
+        ctx.save_for_backward(rois)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (rois,) = ctx.saved_tensors
+        b, h, w, c, ah, aw, scale = ctx.cfg
+        gin = zeros((b, h, w, c), g.device)
+        _call("og_roi_align_avg_nhwc_bwd", _p(g.contiguous()), h, w, c, _p(rois), rois.shape[0], ah, aw, float(scale),
+              _p(gin))
+        return gin, None, None, None, None
+
+
+def roi_align_avg_nhwc(features, rois, ah, aw, scale):
+    return _RoIAlignAvgNHWC.apply(features, rois, ah, aw, scale)
+
+
 # --------------------------------------------------------------------------------------------------
 def adam_ema_(p, g, m, v, avg, step, *, lr=2e-4, b1=0.5, b2=0.999, eps=1e-8, gscale=1.0, decay=0.999, step_dev=None):
     """Fused Adam (+EMA) over flat fp32 buffers, in place.  ``step_dev`` (int64 device scalar) replaces the host

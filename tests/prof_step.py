@@ -42,7 +42,7 @@ tot = collections.defaultdict(lambda: [0, 0.0])
 busy = 0.0
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
-        k = ev.name.split("(")[0][:90]
+        k = ev.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:90]
         tot[k][0] += 1
         tot[k][1] += ev.device_time
         busy += ev.device_time

@@ -348,6 +348,28 @@ def test_roi_align_avg_and_backward():
     close(fg2.grad, torch.from_numpy(want_g), 1e-5, what="bwd")
 
 
+@pytest.mark.parametrize("B,C,H", [(3, 8, 32), (32, 384, 64), (4, 768, 32)])
+def test_roi_align_avg_channels_last_is_bit_identical(B, C, H):
+    """The channels-last fused RoIAlignAvg (what the object discriminators run) returns exactly the bits of the NCHW
+    reference-ABI path (itself bit-identical to the reference .cu, tests above); its adjoint matches the float64 oracle."""
+    torch.manual_seed(31 + C)
+    feat = torch.randn(B, C, H, H)
+    rois = _rois(B, 10, H, 5 + C)
+    rd = torch.from_numpy(rois).to(DEV)
+    want = model.RoIAlignAvg(5, 5, 1.0 / 16)(feat.to(DEV), rd)
+    fg = feat.to(DEV).permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+    got = ops.roi_align_avg_nhwc(fg, rd, 5, 5, 1.0 / 16)
+    assert torch.equal(got.permute(0, 3, 1, 2), want)
+    g = torch.randn(want.shape)
+    got.backward(g.to(DEV).permute(0, 2, 3, 1).contiguous())
+    g6 = torch.zeros(rois.shape[0], C, 6, 6)
+    for dh in (0, 1):
+        for dw in (0, 1):
+            g6[:, :, dh:dh + 5, dw:dw + 5] += g / 4
+    want_g = O.roi_align_backward_np(g6.numpy(), rois, feat.shape, 6, 6, 1.0 / 16)
+    close(fg.grad.permute(0, 3, 1, 2), torch.from_numpy(want_g), 2e-5, what="nhwc avg bwd")
+
+
 # ---------------------------------------------------------------------------------------------------
 # whole networks and the training step
 # ---------------------------------------------------------------------------------------------------
@@ -440,6 +462,32 @@ def test_pat_d_loss_parity(engine, l2, mx, monkeypatch):
     params = dict(d.named_parameters())
     for k, g in zip(keys, grads):
         close_grad(params[k].grad, g, what=k, l2=l2, mx=mx)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_cond_head_small_batches(n):
+    """D_GET_LOGITS (jointConv + BatchNorm + LeakyReLU + logits conv) on n = 1, 2, 3 samples: patD_loss runs the COND
+    head on B - 1 "wrong pair" samples, which is a single sample at per-GPU batch 2."""
+    torch.manual_seed(40 + n)
+    d = model.PAT_D_NET128()
+    d.apply(model.weights_init)
+    d.to(DEV)
+    sd = _cpu_sd(d)
+    h = torch.randn(n, 768, 8, 8) * 0.5
+    c = torch.rand(n, 256)
+    keys = [k for k in O.trainable_keys(sd) if k.startswith("COND_DNET")]
+    live, leaves = O._with_grad(sd, keys)
+    hr = h.clone().requires_grad_(True)
+    loss_r = O.bce(O.d_get_logits(hr, live, "COND_DNET", c), 0)
+    grads = torch.autograd.grad(loss_r, [hr] + [leaves[k] for k in keys])
+    hg = h.to(DEV).requires_grad_(True)
+    loss = ops.bce(d.COND_DNET(hg, c.to(DEV)), 0.0, 1.0)
+    close(loss, loss_r.detach(), 1e-5, what="loss")
+    loss.backward()
+    close_grad(hg.grad, grads[0], what="g_h")
+    params = dict(d.named_parameters())
+    for k, g in zip(keys, grads[1:]):
+        close_grad(params[k].grad, g, what=k)
 
 
 def test_adam_ema_kernel():

@@ -149,3 +149,18 @@ def test_cta_pair_kernels_on_small_cases():
                        env=env, capture_output=True, text=True, timeout=600,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_persistent_cta_pair_kernel_on_small_cases():
+    """conv_tcp (persistent clusters of two CTAs, cta_group::2 MMAs, double-buffered TMEM accumulators) on the parity
+    cases with 208- / 256-wide output tiles, forced through OG_TCP=1 / OG_TCP_MIN=1 in a fresh process; includes an
+    odd tile count, more work units than clusters (several rounds through both accumulator stages) and fewer."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, OG_TCP="1", OG_TCP_MIN="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k",
+                        "test_tc_conv_fwd_dgrad and (case0 or case1 or case3 or case6 or case13)"],
+                       env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
