@@ -253,6 +253,15 @@ int og_words_pairs_bwd(const float* words, const float* ctx, const long long* le
                        const float* g_sim, int B, int NC, int ndf, int T, int S, float gamma1, float gamma2, float eps,
                        float* g_ctx, cudaStream_t stream);
 
+/* Device-side input preparation (ref: trainDataset.py:79-128, miscc/load.py:160-176, miscc/utils.py:502-522):
+ *  og_form_hmaps        : out[b][cls[b][r]][p] += masks[b][r][p] for r < num_rois[b], in roi order (the loader's loop);
+ *                         clamp_max > 0 additionally clamps the touched channels (synthetic inputs); out NCHW, zeroed here
+ *  og_form_clabels_feat : out[b][e][r] = emb[cls[b][r]][e] for r < num_rois[b], else 0   (B, E, Rmax, 1) */
+int og_form_hmaps(const float* masks, const long long* cls, const long long* num_rois, int B, int R, long long P,
+                  int ncls, float clamp_max, float* out, cudaStream_t stream);
+int og_form_clabels_feat(const float* emb, const long long* cls, const long long* num_rois, int B, int R, int Rmax, int E,
+                         int ncls, float* out, cudaStream_t stream);
+
 /* zero-fill (a memset node when captured in a CUDA graph; no kernel launch) */
 int og_zero_bytes(float* p, long long bytes, cudaStream_t stream);
 

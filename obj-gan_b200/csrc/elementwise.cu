@@ -590,3 +590,68 @@ OG_API int og_bilinear_bwd(const float* g, int N, int IH, int IW, int C, int OH,
   bilinear_bwd_kernel<<<eblocks(total), 256, 0, stream>>>(g, IH, IW, OH, OW, C, rh, rw, total, gx);
   OG_RETURN_LAST_ERROR();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-side input preparation (the part of the reference's host data path that only re-arranges what the loader
+// already produced; ref: trainDataset.py:79-128 prepare_data, miscc/load.py:160-176 get_hmaps_rois,
+// miscc/utils.py:502-522 form_clabels_feat).  The 80-channel class heat maps are, by construction, the per-class sums
+// of the 10 per-roi masks (load.py:176: hmaps[cat] += re_mask), so only the masks cross PCIe (7x fewer bytes) and the
+// heat maps are rebuilt here, in roi order like the loader's loop.
+// ---------------------------------------------------------------------------------------------------------------
+// masks [B][R][P], cls [B][R] (int64 class index per roi slot), num_rois [B] (int64) -> out [B][ncls][P] (NCHW)
+__global__ void __launch_bounds__(256) form_hmaps_kernel(const float* __restrict__ masks, const long long* __restrict__ cls,
+                                                         const long long* __restrict__ num_rois, int R, long long P,
+                                                         int ncls, float clamp_max, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int n = min((int)num_rois[b], R);
+  __shared__ int scls[64];
+  for (int r = threadIdx.x; r < n && r < 64; r += blockDim.x) scls[r] = (int)cls[(long long)b * R + r];
+  __syncthreads();
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    float* o = out + (long long)b * ncls * P + p;
+    for (int r = 0; r < n; ++r) {                       // sequential, in roi order: same sums as the host loop
+      const int c = scls[r];
+      if (c < 0 || c >= ncls) continue;
+      float v = o[(long long)c * P] + masks[((long long)b * R + r) * P + p];
+      o[(long long)c * P] = v;
+    }
+    if (clamp_max > 0.f)
+      for (int r = 0; r < n; ++r) {
+        const int c = scls[r];
+        if (c < 0 || c >= ncls) continue;
+        o[(long long)c * P] = fminf(o[(long long)c * P], clamp_max);
+      }
+  }
+}
+OG_API int og_form_hmaps(const float* masks, const long long* cls, const long long* num_rois, int B, int R, long long P,
+                         int ncls, float clamp_max, float* out, cudaStream_t stream) {
+  if (R > 64) return (int)cudaErrorInvalidValue;
+  OG_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * ncls * P, stream));
+  if (B == 0 || P == 0) return 0;
+  dim3 grid(og_cdiv(P, 256) < 148 * 4 ? og_cdiv(P, 256) : 148 * 4, B);
+  form_hmaps_kernel<<<grid, 256, 0, stream>>>(masks, cls, num_rois, R, P, ncls, clamp_max, out);
+  OG_RETURN_LAST_ERROR();
+}
+// emb [ncls][E], cls [B][R], num_rois [B] -> out [B][E][Rmax] (= (B, E, Rmax, 1)); slots r >= num_rois[b] are zero
+__global__ void form_clabels_feat_kernel(const float* __restrict__ emb, const long long* __restrict__ cls,
+                                         const long long* __restrict__ num_rois, int R, int Rmax, int E, int ncls,
+                                         long long total, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int r = (int)(i % Rmax);
+  const int e = (int)((i / Rmax) % E);
+  const int b = (int)(i / ((long long)Rmax * E));
+  float v = 0.f;
+  if (r < (int)num_rois[b] && r < R) {
+    const int c = (int)cls[(long long)b * R + r];
+    if (c >= 0 && c < ncls) v = emb[(long long)c * E + e];
+  }
+  out[i] = v;
+}
+OG_API int og_form_clabels_feat(const float* emb, const long long* cls, const long long* num_rois, int B, int R, int Rmax,
+                                int E, int ncls, float* out, cudaStream_t stream) {
+  const long long total = (long long)B * E * Rmax;
+  if (total == 0) return 0;
+  form_clabels_feat_kernel<<<og_cdiv(total, 256), 256, 0, stream>>>(emb, cls, num_rois, R, Rmax, E, ncls, total, out);
+  OG_RETURN_LAST_ERROR();
+}

@@ -1117,6 +1117,32 @@ def zeros(shape, device):
     return t
 
 
+def form_hmaps(bt_masks, roi_cls, num_rois, num_classes, clamp_max=0.0, out=None):
+    """Class heat maps (B, num_classes, S, S) from the per-roi masks (B, R, S, S) and the roi class ids (B, R) int64:
+    what the reference's loader accumulates on the host (ref: miscc/load.py:160-176), rebuilt on the device."""
+    _chk(bt_masks, roi_cls, num_rois)
+    bt_masks = bt_masks.contiguous()
+    b, r, h, w = bt_masks.shape
+    assert roi_cls.dtype == torch.int64 and num_rois.dtype == torch.int64 and roi_cls.shape == (b, r)
+    if out is None:
+        out = torch.empty((b, num_classes, h, w), device=bt_masks.device, dtype=torch.float32)
+    _call("og_form_hmaps", _p(bt_masks), _p(roi_cls.contiguous()), _p(num_rois.contiguous()), b, r, h * w, num_classes,
+          float(clamp_max), _p(out))
+    return out
+
+
+def form_clabels_feat(clabels_emb, roi_cls, num_rois, rmax, out=None):
+    """ref: miscc/utils.py:502-522 on the device: (B, E, rmax, 1) label embeddings of the first num_rois[b] boxes."""
+    _chk(clabels_emb, roi_cls, num_rois)
+    b, r = roi_cls.shape
+    ncls, e = clabels_emb.shape
+    if out is None:
+        out = torch.empty((b, e, rmax, 1), device=clabels_emb.device, dtype=torch.float32)
+    _call("og_form_clabels_feat", _p(clabels_emb.contiguous()), _p(roi_cls.contiguous()), _p(num_rois.contiguous()), b, r,
+          rmax, e, ncls, _p(out))
+    return out
+
+
 class _WordsPairs(torch.autograd.Function):
     """All B x NC (image, caption) pairs of words_loss in one launch (ref: miscc/losses.py:87-127): func_attention,
     word / attended-context cosine and the Eq. (10) pooling.  ctx_feat (B, ndf, ih, iw) carries the gradient;

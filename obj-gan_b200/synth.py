@@ -118,6 +118,18 @@ def make_inputs(batch: int, seed: int = 1234, *, words: int | None = None, max_r
                 hmaps=hmaps, imgs=imgs, glb_max_num_roi=rmax)
 
 
+HMAP_CLAMP = 1.0     # make_inputs clamps its synthetic class heat maps at 1 (the reference's loader does not clamp)
+
+
+def compact(inp: dict) -> dict:
+    """The batch as it needs to cross PCIe: without the two tensors the device rebuilds from the rest
+    (``hmaps`` = per-class sums of ``bt_masks``, 86 % of the bytes; ``slabels_feat`` = label embeddings of the roi
+    classes), plus the roi class ids as an int64 table (column 4 of ``rois[0]``)."""
+    out = {k: v for k, v in inp.items() if k not in ("hmaps", "slabels_feat")}
+    out["roi_cls"] = inp["rois"][0][..., 4].to(torch.int64).contiguous()
+    return out
+
+
 def input_bytes(inp: dict) -> int:
     """Bytes a step copies host->device (every tensor in the batch)."""
     n = 0

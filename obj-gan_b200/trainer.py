@@ -139,12 +139,35 @@ class StepATrainer:
                 out[k] = [t.to(self.device, non_blocking=True) for t in v]
             else:
                 out[k] = v
+        if "hmaps" not in out and "roi_cls" in out:
+            self.prepare_data(out)       # compact batch: rebuild the class heat maps / label embeddings on the device
         # box tables stay readable on the host as well: the roi filter of feat_select and the class shuffles of
         # permute_seg are host decisions (like the reference), and reading them back from the device would stall the
         # step (the reference does exactly that: .cpu() in utils.py:447, 467)
         out["host_boxes"] = {"rois": [r.detach().cpu() for r in inp["rois"]], "fm_rois": inp["fm_rois"].detach().cpu(),
                              "num_rois": inp["num_rois"].detach().cpu()}
         return out
+
+    def prepare_data(self, dev: dict, into: dict | None = None) -> dict:
+        """Device-side tail of the reference's host data path (ref: trainDataset.py:79-128 ``prepare_data``,
+        miscc/load.py:160-176, miscc/utils.py:502-522 ``form_clabels_feat``): from the per-roi masks, the roi class ids
+        and the class-label embeddings already on the device, build the 80-channel class heat maps of the three
+        scales and the (B, 50, Rmax, 1) label-embedding tensor -- 86 % of the bytes the reference copies host->device
+        every step are these derived tensors.  ``into``: dict holding preallocated ``hmaps`` / ``slabels_feat`` buffers
+        (the static inputs of a captured graph) to fill instead of allocating."""
+        from . import synth
+        dst = into if into is not None else dev
+        ncls = self.netG.num_classes if hasattr(self.netG, "num_classes") else dev["clabels_emb"].shape[0]
+        cls, nr = dev["roi_cls"], dev["num_rois"]
+        clamp = float(dev.get("hmap_clamp", synth.HMAP_CLAMP))
+        have = into is not None and "hmaps" in into
+        hm = [ops.form_hmaps(m, cls, nr, ncls, clamp, out=(into["hmaps"][i] if have else None))
+              for i, m in enumerate(dev["bt_masks"])]
+        rmax = int(dev["glb_max_num_roi"])
+        sl = ops.form_clabels_feat(dev["clabels_emb"], cls, nr, rmax,
+                                   out=(into["slabels_feat"] if into is not None and "slabels_feat" in into else None))
+        dst["hmaps"], dst["slabels_feat"] = hm, sl
+        return dst
 
     def generate(self, inp):
         g = self.netG
@@ -299,7 +322,9 @@ class StepATrainer:
             copied = torch.cuda.Event()
             copied.record(self._copy_stream)
         cur.wait_event(copied)
-        self._load_static(stg)                                      # device->device into the captured buffers
+        if "hmaps" not in host_inp and "roi_cls" in host_inp:       # compact batch: derived tensors built in place
+            self.prepare_data(stg, into=self._static)
+        self._load_static({k: v for k, v in stg.items() if k in host_inp})   # device->device into the captured buffers
         self._stage_free[k].record(cur)
         out = self.step(self._static)
         self._loss_host[k].copy_(out["errG"] + out["kl"], non_blocking=True)

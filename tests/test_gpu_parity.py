@@ -561,6 +561,26 @@ def test_step_a_parity(engine, cos_min, l2_max, monkeypatch):
         assert moved > 1e-5, k   # the optimiser really stepped
 
 
+def test_device_side_prepare_data_is_exact():
+    """f4: the compact batch (no class heat maps, no label-embedding tensor: 14 % of the bytes) + the device-side
+    rebuild (trainer.prepare_data: og_form_hmaps / og_form_clabels_feat) gives bit-identical step inputs to the
+    host-built batch (ref: miscc/load.py:160-176 heat-map accumulation in roi order; miscc/utils.py:502-522)."""
+    inp = synth.make_inputs(5, seed=9, parity=True)
+    small = synth.compact(inp)
+    assert synth.input_bytes(small) < 0.16 * synth.input_bytes(inp)
+    t = trainer.StepATrainer(device=DEV, seed=5)
+    dev = t.to_device(small)
+    for a, b in zip(dev["hmaps"], inp["hmaps"]):
+        assert torch.equal(a.cpu(), b)
+    assert torch.equal(dev["slabels_feat"].cpu(), inp["slabels_feat"])
+    # reference semantics (no clamp): overlapping same-class boxes add up
+    dev2 = dict(t.to_device(small), hmap_clamp=0.0)
+    hm = t.prepare_data(dev2)["hmaps"][0].cpu()
+    want = torch.zeros_like(inp["hmaps"][0])
+    want.scatter_add_(1, small["roi_cls"].view(5, -1, 1, 1).expand_as(inp["bt_masks"][0]), inp["bt_masks"][0])
+    assert torch.equal(hm, want)
+
+
 def test_cuda_graph_replay_matches_eager():
     """A replay of the captured whole-step CUDA graph computes the same step as eager launches from the same state."""
     inp = synth.make_inputs(4, seed=8, parity=True)
