@@ -554,10 +554,11 @@ class _NormAct(torch.autograd.Function):
         bstats = torch.empty(groups * cy * 2, device=g.device, dtype=torch.float64)
         dy = torch.empty_like(y)
         dgamma = dbeta = None
-        direct = gamma is not None and ctx.sinks[0] is not None and ctx.sinks[1] is not None
+        want_pg = gamma is not None and ctx.needs_input_grad[1]     # frozen discriminators (G update): no param grads
+        direct = want_pg and ctx.sinks[0] is not None and ctx.sinks[1] is not None
         if direct:
             dgamma, dbeta = ctx.sinks
-        elif gamma is not None:
+        elif want_pg:
             dgamma = torch.empty_like(gamma)
             dbeta = torch.empty_like(beta)
         _call("og_norm_backward", _p(y), _p(g), groups, P, cy, _p(mean), _p(rstd), _p(gamma), _p(beta), act,

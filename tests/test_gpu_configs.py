@@ -280,6 +280,7 @@ def test_gradient_error_vs_float64_oracle(monkeypatch):
             b.requires_grad_(False)
         fake, _b, _a, _ba, mu, logvar = t.generate(dev)
         (losses.G_loss_pat(t.netsPatD, fake, dev["sent_emb"])[0] + losses.KL_loss(mu, logvar)).backward()
+        t.bD[1].zero_grad()
         t.bD[1].requires_grad_(True)
         losses.patD_loss(t.netsPatD[1], dev["imgs"][1], fake[1].detach(), dev["sent_emb"]).backward()
         for name, got, g32, g64 in (("G", dict(t.netG.named_parameters()), gg32, gg64),
