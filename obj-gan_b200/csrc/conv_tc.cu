@@ -1641,7 +1641,7 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
   // persistent CTA pairs (cta_group::2, double-buffered accumulators): every BN = 208 / 256 problem with enough tiles
   static const int tcp = getenv("OG_TCP") ? atoi(getenv("OG_TCP")) : 1;
   static const long long tcp_min = getenv("OG_TCP_MIN") ? atoll(getenv("OG_TCP_MIN")) : 64;
-  if (tcp && p.ksplit == 1 && (BNsel == 208 || BNsel == 256) && (long long)grid.x * grid.y >= tcp_min) {
+  if (tcp && p.ksplit == 1 && (tcp > 1 || BNsel == 208 || BNsel == 256) && (long long)grid.x * grid.y >= tcp_min) {
     CUtensorMap pbh, pbl;
     unsigned hbox[3] = {(unsigned)TC_BK, (unsigned)(BNsel / 2), 1u};
     if ((rc = make_map(&pbh, wh, 3, bdims, bstr, hbox))) return rc;
@@ -1663,8 +1663,13 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
       p.tall = 1;
       return launch_tcp<208, true>(tah, tal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream);
     }
-    return BNsel == 208 ? launch_tcp<208, false>(mah, mal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream)
-                        : launch_tcp<256, false>(mah, mal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream);
+    switch (BNsel) {
+      case 32:  return launch_tcp<32, false>(mah, mal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream);
+      case 64:  return launch_tcp<64, false>(mah, mal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream);
+      case 112: return launch_tcp<112, false>(mah, mal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream);
+      case 208: return launch_tcp<208, false>(mah, mal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream);
+      default:  return launch_tcp<256, false>(mah, mal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream);
+    }
   }
   // large problems: two pixel tiles per CTA share every weight stage (see conv_tc2_kernel)
   static const bool no_tc2 = getenv("OG_NO_TC2") != nullptr;

@@ -105,11 +105,18 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
   const int Co4 = Co >> 2;
   const long long total = total_pix * Co4;
   float mx = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long p = i / Co4;
-    int c = (int)(i - p * Co4) * 4;
-    long long g = p / P;
+  // (pixel p, channel quad c4, group g, pixel-in-group pg) advance incrementally: no division per element
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long dp = stride / Co4;
+  const int dc = (int)(stride - dp * Co4);
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long p = i / Co4;
+  int c4i = (int)(i - p * Co4);
+  long long g = p / P, pg = p - g * P;
+  for (; i < total; i += stride, p += dp, pg += dp, c4i += dc) {
+    if (c4i >= Co4) { c4i -= Co4; ++p; ++pg; }
+    while (pg >= P) { pg -= P; ++g; }
+    const int c = c4i * 4;
     const float* mrow = mean + g * Cy;
     const float* rrow = rstd + g * Cy;
     float4 v = ldg4(y + p * Cy + c);
@@ -254,41 +261,64 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __rest
   const int Co4 = Co >> 2;
   const long long total = total_pix * Co4;
   float mx = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long p = i / Co4;
-    int c = (int)(i - p * Co4) * 4;
-    long long grp = p / P;
+  (void)inv_count;
+  // coef[(grp * Cy + ch) * 4 + {0, 1}] = (float)(S1 / count), (float)(S2 / count): written over the fp64 sums by
+  // norm_bwd_coef_kernel (same float values the per-element double products gave)
+  const float* coef = reinterpret_cast<const float*>(bstats);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long dp = stride / Co4;
+  const int dc = (int)(stride - dp * Co4);
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long p = i / Co4;
+  int c4i = (int)(i - p * Co4);
+  long long grp = p / P, pg = p - grp * P;
+  for (; i < total; i += stride, p += dp, pg += dp, c4i += dc) {
+    if (c4i >= Co4) { c4i -= Co4; ++p; ++pg; }
+    while (pg >= P) { pg -= P; ++grp; }
+    const int c = c4i * 4;
     const float* mrow = mean + grp * Cy;
     const float* rrow = rstd + grp * Cy;
     float4 xh, dn, xh2, dn2;
     act_grad4<ACT>(y, g, p, Cy, c, mrow, rrow, gamma, beta, slope, xh, dn, xh2, dn2);
     {
-      const double* bs = bstats + (grp * Cy + c) * 2;
+      const float* bs = coef + (grp * Cy + c) * 4;
+      const float2 k0 = *reinterpret_cast<const float2*>(bs), k1 = *reinterpret_cast<const float2*>(bs + 4);
+      const float2 k2 = *reinterpret_cast<const float2*>(bs + 8), k3 = *reinterpret_cast<const float2*>(bs + 12);
       float4 r = ldg4(rrow + c);
       float4 ga = gamma ? ldg4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
       float4 o;
-      o.x = r.x * ga.x * (dn.x - (float)(bs[0] * inv_count) - xh.x * (float)(bs[1] * inv_count));
-      o.y = r.y * ga.y * (dn.y - (float)(bs[2] * inv_count) - xh.y * (float)(bs[3] * inv_count));
-      o.z = r.z * ga.z * (dn.z - (float)(bs[4] * inv_count) - xh.z * (float)(bs[5] * inv_count));
-      o.w = r.w * ga.w * (dn.w - (float)(bs[6] * inv_count) - xh.w * (float)(bs[7] * inv_count));
+      o.x = r.x * ga.x * (dn.x - k0.x - xh.x * k0.y);
+      o.y = r.y * ga.y * (dn.y - k1.x - xh.y * k1.y);
+      o.z = r.z * ga.z * (dn.z - k2.x - xh.z * k2.y);
+      o.w = r.w * ga.w * (dn.w - k3.x - xh.w * k3.y);
       st4(dy + p * Cy + c, o);
       mx = amax4(mx, o);
     }
     if (ACT == OG_NA_GLU) {
-      const double* bs = bstats + (grp * Cy + Co + c) * 2;
+      const float* bs = coef + (grp * Cy + Co + c) * 4;
+      const float2 k0 = *reinterpret_cast<const float2*>(bs), k1 = *reinterpret_cast<const float2*>(bs + 4);
+      const float2 k2 = *reinterpret_cast<const float2*>(bs + 8), k3 = *reinterpret_cast<const float2*>(bs + 12);
       float4 r = ldg4(rrow + Co + c);
       float4 ga = gamma ? ldg4(gamma + Co + c) : make_float4(1.f, 1.f, 1.f, 1.f);
       float4 o;
-      o.x = r.x * ga.x * (dn2.x - (float)(bs[0] * inv_count) - xh2.x * (float)(bs[1] * inv_count));
-      o.y = r.y * ga.y * (dn2.y - (float)(bs[2] * inv_count) - xh2.y * (float)(bs[3] * inv_count));
-      o.z = r.z * ga.z * (dn2.z - (float)(bs[4] * inv_count) - xh2.z * (float)(bs[5] * inv_count));
-      o.w = r.w * ga.w * (dn2.w - (float)(bs[6] * inv_count) - xh2.w * (float)(bs[7] * inv_count));
+      o.x = r.x * ga.x * (dn2.x - k0.x - xh2.x * k0.y);
+      o.y = r.y * ga.y * (dn2.y - k1.x - xh2.y * k1.y);
+      o.z = r.z * ga.z * (dn2.z - k2.x - xh2.z * k2.y);
+      o.w = r.w * ga.w * (dn2.w - k3.x - xh2.w * k3.y);
       st4(dy + p * Cy + Co + c, o);
       mx = amax4(mx, o);
     }
   }
   if (amax) block_amax_256(mx, amax);
+}
+
+// (S1, S2) fp64 -> ((float)(S1 / count), (float)(S2 / count)) stored over the first 8 bytes of the same 16-byte slot
+__global__ void norm_bwd_coef_kernel(double* __restrict__ bstats, long long n, double inv_count) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double s1 = bstats[i * 2], s2 = bstats[i * 2 + 1];
+  float2 k = make_float2((float)(s1 * inv_count), (float)(s2 * inv_count));
+  *reinterpret_cast<float2*>(bstats + i * 2) = k;
 }
 
 // dgamma = S2, dbeta = S1 for batch norm (groups == 1): copy fp64 sums to fp32 parameter-gradient vectors
@@ -366,6 +396,9 @@ OG_API int og_norm_backward(const float* y, const float* g, int groups, long lon
   double inv = 1.0 / (double)P;
 #define OG_LAUNCH_BWD(A)                                                                                           \
   norm_bwd_reduce_kernel<A><<<grid, block, 0, stream>>>(y, g, Cy, P, ppb, mean, rstd, gamma, beta, slope, bstats); \
+  if (dgamma && groups == 1)                                                                                       \
+    norm_param_grad_kernel<<<og_cdiv(Cy, 256), 256, 0, stream>>>(bstats, Cy, dgamma, dbeta, accumulate_param_grads); \
+  norm_bwd_coef_kernel<<<og_cdiv((long long)groups * Cy, 256), 256, 0, stream>>>(bstats, (long long)groups * Cy, inv); \
   norm_bwd_apply_kernel<A><<<blocks, 256, 0, stream>>>(y, g, Cy, P, tp, mean, rstd, gamma, beta, slope, bstats, inv, dy, amax_dy);
   if (act == OG_NA_GLU) {
     OG_LAUNCH_BWD(OG_NA_GLU)
@@ -375,7 +408,5 @@ OG_API int og_norm_backward(const float* y, const float* g, int groups, long lon
     OG_LAUNCH_BWD(OG_NA_NONE)
   }
 #undef OG_LAUNCH_BWD
-  if (dgamma && groups == 1)
-    norm_param_grad_kernel<<<og_cdiv(Cy, 256), 256, 0, stream>>>(bstats, Cy, dgamma, dbeta, accumulate_param_grads);
   OG_RETURN_LAST_ERROR();
 }
