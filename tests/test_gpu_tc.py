@@ -164,3 +164,17 @@ def test_persistent_cta_pair_kernel_on_small_cases():
                        env=env, capture_output=True, text=True, timeout=600,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_persistent_cta_pair_kernel_all_tile_widths():
+    """conv_tcp for EVERY output-tile width (32 / 64 / 112 / 208 / 256: OG_TCP=2) on all parity cases of this file --
+    upsample phases (strided output pixels), space-to-depth stride-2 taps, ragged tiles, tiles spanning images."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, OG_TCP="2", OG_TCP_MIN="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k",
+                        "test_tc_conv_fwd_dgrad and f16x3"],
+                       env=env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
