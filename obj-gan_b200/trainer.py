@@ -259,14 +259,16 @@ class StepATrainer:
                 err = losses.patD_loss(d, inp["imgs"][i], fake_imgs[i], sent)
                 err.backward()
                 out[f"errPatD{i}"] = err.detach()
+                # the gradient exchange and the optimiser step of this discriminator stay on ITS branch: the
+                # all-reduce of the small 64 / 128 discriminators runs under the backward pass of the 256 one
+                # (every rank issues the three collectives in the same program order)
+                w = self._allreduce(b)
+                if w is not None:
+                    w.wait()
+                b.adam(lr_d, gs)
         for i, b in enumerate(self.bD):
             if streams:
                 main.wait_stream(streams[i])
-            works.append(self._allreduce(b))
-        for w, b in zip(works, self.bD):
-            if w is not None:
-                w.wait()
-            b.adam(lr_d, gs)
         # (4) update G through the updated discriminators (their weight gradients are not needed)
         for b in self.bD:
             b.requires_grad_(False)

@@ -748,6 +748,57 @@ def step_a(state: StepAState, inp: dict, *, lr=2e-4, keep=None):
     return losses
 
 
+def step_a_dp(state: StepAState, shards: list, *, lr=2e-4, keep=None):
+    """Step-A under data parallelism over len(shards) equal shards: every shard runs the reference
+    step on its own samples (local BatchNorm statistics, local "wrong pair" shift, local mask quirk), the gradients of
+    each network are AVERAGED over the shards (what one NCCL all-reduce per bucket + 1/N does) and one Adam step is
+    taken from the averaged gradient; the generator update goes through the discriminators after THEIR averaged step.
+    Returns per-shard losses; ``keep`` receives the averaged gradients."""
+    state.step += 1
+    t, n = state.step, len(shards)
+    g_live, g_leaves = _with_grad(state.g, state.g_keys)
+    outs = []
+    for i, inp in enumerate(shards):
+        live_i = g_live if i == 0 else dict(g_live)           # BatchNorm buffer updates of shard 0 are kept
+        outs.append(g_net_forward(live_i, inp))
+    for k, v in g_live.items():
+        if k not in g_leaves:
+            state.g[k] = v
+    losses = [dict() for _ in shards]
+    d_grads = []
+    for j, d in enumerate(state.ds):
+        d_live, d_leaves = _with_grad(d, state.d_keys[j])
+        total = 0
+        for i, inp in enumerate(shards):
+            live_i = d_live if i == 0 else dict(d_live)
+            err = pat_d_loss(live_i, inp["imgs"][j], outs[i][0][j], inp["sent_emb"])
+            losses[i][f"errPatD{j}"] = float(err.detach())
+            total = total + err / n
+        grads = torch.autograd.grad(total, [d_leaves[k] for k in state.d_keys[j]])
+        for k, v in d_live.items():
+            if k not in d_leaves:
+                d[k] = v
+        for k, gk in zip(state.d_keys[j], grads):
+            adam_step(d[k], gk, state.d_m[j][k], state.d_v[j][k], t, lr)
+        d_grads.append(dict(zip(state.d_keys[j], grads)))
+    total = 0
+    for i, inp in enumerate(shards):
+        ds_i = state.ds if i == 0 else [dict(d) for d in state.ds]
+        errg = g_loss_pat(ds_i, outs[i][0], inp["sent_emb"])
+        kl = kl_loss(outs[i][4], outs[i][5])
+        losses[i]["errG"], losses[i]["kl"] = float(errg.detach()), float(kl.detach())
+        total = total + (errg + kl) / n
+    ggrads = torch.autograd.grad(total, [g_leaves[k] for k in state.g_keys])
+    for k, gk in zip(state.g_keys, ggrads):
+        adam_step(state.g[k], gk, state.g_m[k], state.g_v[k], t, lr)
+        ema_update(state.g_avg[k], state.g[k])
+    if keep is not None:
+        keep["g_grads"] = dict(zip(state.g_keys, ggrads))
+        keep["d_grads"] = d_grads
+        keep["fake"] = [[f.detach() for f in o[0]] for o in outs]
+    return losses
+
+
 # --------------------------------------------------------------------------------------
 # Step-B: the reference's complete step (trainer.py:385-462) -- SURVEY.md section 8, row a21 in full
 # --------------------------------------------------------------------------------------

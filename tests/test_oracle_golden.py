@@ -275,3 +275,28 @@ def test_roi_align_edge_cases_bit_exact():
         assert np.array_equal(out, want), (ah, aw)
     empty = np.zeros((0, 5), dtype=np.float32)
     assert O.roi_align_forward_np(feat, empty, 6, 6, 1.0 / s).shape == (0, C, 6, 6)
+
+
+def test_step_a_dp_one_shard_is_step_a():
+    """oracle.step_a_dp (mean of the shards' gradients) with a single shard is oracle.step_a."""
+    from objgan_b200 import lib, model, synth
+    lib.DRY_RUN, model.FAST_INIT = True, False
+    try:
+        torch.manual_seed(5)
+        g = model.G_NET(80)
+        ds = [model.PAT_D_NET64(), model.PAT_D_NET128(), model.PAT_D_NET256()]
+        for m in [g, *ds]:
+            m.apply(model.weights_init)
+    finally:
+        lib.DRY_RUN = False
+    sd = lambda m: {k: v.detach().clone() for k, v in m.state_dict().items()}
+    inp = synth.make_inputs(2, seed=14, parity=True)
+    a, b = O.StepAState(sd(g), [sd(d) for d in ds]), O.StepAState(sd(g), [sd(d) for d in ds])
+    ka, kb = {}, {}
+    la = O.step_a(a, inp, keep=ka)
+    lb = O.step_a_dp(b, [inp], keep=kb)[0]
+    for k in la:
+        assert abs(la[k] - lb[k]) <= 1e-6 * max(1.0, abs(la[k])), k
+    for k in a.g_keys:
+        assert torch.allclose(ka["g_grads"][k], kb["g_grads"][k], rtol=1e-4, atol=1e-7), k
+        assert torch.allclose(a.g[k], b.g[k], rtol=0, atol=4.1e-4), k
