@@ -10,6 +10,7 @@
 // The grid attention streams h_code once (4*C bytes / query), writes the context once and the
 // attention map once: algorithmic bytes 4*Q*(2C + L) per image.
 #include "common.cuh"
+#include <stdlib.h>
 
 constexpr int LMAX = 32;   // max caption length handled in registers (reference uses 12..18)
 
@@ -212,10 +213,148 @@ att_general_fwd_kernel(const float* __restrict__ h, const float* __restrict__ sr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident variant for the large maps (Q >= 4096, L <= 20): NO shared-memory transposes.  A thread owns QPT
+// queries (rows q0 + t + u * 128); it streams each of its rows straight from global memory with 16-byte loads (the
+// 32 lanes of a warp walk 32 adjacent rows, so every byte of every cache line fetched is consumed by the following
+// loads of the same warp), keeps the QPT x 20 scores / probabilities in registers, and writes its context rows
+// with 16-byte stores.  The only shared memory is the 48 x 20 word-projection table, read with broadcast LDS.128 that
+// each feed 4 * QPT FMAs -- with QPT = 4 the instruction stream is ~80 % FFMA2 (one query per thread: ~35 %).
+// ---------------------------------------------------------------------------------------------
+template <int QPT>
+__global__ void __launch_bounds__(ATT_Q)
+att_general_fwd_reg_kernel(const float* __restrict__ h, const float* __restrict__ src,
+                           const unsigned char* __restrict__ mask, int B, int Q, int idf, int cs, int L,
+                           float* __restrict__ wc, float* __restrict__ attn) {
+  constexpr int LM = 20;
+  extern __shared__ __align__(16) float ssrc[];          // [idf][LM], zero padded beyond L
+  const int b = blockIdx.y, q0 = blockIdx.x * (ATT_Q * QPT), t = threadIdx.x;
+  for (int i = t; i < idf * LM; i += ATT_Q) {
+    const int c = i / LM, l = i - c * LM;
+    ssrc[i] = l < L ? src[((long long)b * idf + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+  int q[QPT];
+  bool live[QPT];
+  const float* hrow[QPT];
+#pragma unroll
+  for (int u = 0; u < QPT; ++u) {
+    q[u] = q0 + t + u * ATT_Q;
+    live[u] = q[u] < Q;
+    hrow[u] = h + ((long long)b * Q + (live[u] ? q[u] : 0)) * cs;
+  }
+  float2 s2[QPT][LM / 2];
+#pragma unroll
+  for (int u = 0; u < QPT; ++u)
+#pragma unroll
+    for (int l = 0; l < LM / 2; ++l) s2[u][l] = make_float2(0.f, 0.f);
+  for (int c4 = 0; c4 < idf; c4 += 4) {
+    float4 hv[QPT];
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) hv[u] = ldg4(hrow[u] + c4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c4 + k < idf) {
+        const float4* sr = reinterpret_cast<const float4*>(ssrc + (c4 + k) * LM);
+        float2 hv2[QPT];
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+          const float x = k == 0 ? hv[u].x : k == 1 ? hv[u].y : k == 2 ? hv[u].z : hv[u].w;
+          hv2[u] = make_float2(x, x);
+        }
+#pragma unroll
+        for (int l4 = 0; l4 < LM / 4; ++l4) {
+          const float4 w = sr[l4];
+#pragma unroll
+          for (int u = 0; u < QPT; ++u) {
+            s2[u][2 * l4] = ffma2(hv2[u], make_float2(w.x, w.y), s2[u][2 * l4]);
+            s2[u][2 * l4 + 1] = ffma2(hv2[u], make_float2(w.z, w.w), s2[u][2 * l4 + 1]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < QPT; ++u) {
+    float sc[LM];
+#pragma unroll
+    for (int l = 0; l < LM / 2; ++l) {
+      sc[2 * l] = s2[u][l].x;
+      sc[2 * l + 1] = s2[u][l].y;
+    }
+    float mx = -INFINITY;
+    if (mask && live[u]) {
+      const unsigned char* mr = mask + (((long long)b * Q + q[u]) % B) * L;
+#pragma unroll
+      for (int l = 0; l < LM; ++l)
+        if (l < L && mr[l]) sc[l] = -INFINITY;
+    }
+#pragma unroll
+    for (int l = 0; l < LM; ++l)
+      if (l < L) mx = fmaxf(mx, sc[l]);
+    float sum = 0.f;
+#pragma unroll
+    for (int l = 0; l < LM; ++l) {
+      sc[l] = l < L ? expf(sc[l] - mx) : 0.f;
+      sum += sc[l];
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int l = 0; l < LM; ++l) {
+      sc[l] *= inv;
+      if (l < L && live[u]) attn[((long long)b * L + l) * Q + q[u]] = sc[l];
+    }
+#pragma unroll
+    for (int l = 0; l < LM / 2; ++l) s2[u][l] = make_float2(sc[2 * l], sc[2 * l + 1]);
+  }
+  for (int c4 = 0; c4 < cs; c4 += 4) {
+    float o[QPT][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c4 + k;
+      float2 a2[QPT], b2[QPT];
+#pragma unroll
+      for (int u = 0; u < QPT; ++u) a2[u] = b2[u] = make_float2(0.f, 0.f);
+      if (c < idf) {
+        const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
+#pragma unroll
+        for (int l4 = 0; l4 < LM / 4; ++l4) {
+          const float4 w = sr[l4];
+#pragma unroll
+          for (int u = 0; u < QPT; ++u) {
+            a2[u] = ffma2(make_float2(w.x, w.y), s2[u][2 * l4], a2[u]);
+            b2[u] = ffma2(make_float2(w.z, w.w), s2[u][2 * l4 + 1], b2[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < QPT; ++u) o[u][k] = (a2[u].x + b2[u].x) + (a2[u].y + b2[u].y);
+    }
+#pragma unroll
+    for (int u = 0; u < QPT; ++u)
+      if (live[u]) st4(wc + ((long long)b * Q + q[u]) * cs + c4, make_float4(o[u][0], o[u][1], o[u][2], o[u][3]));
+  }
+}
+
+template <int QPT>
+static int launch_att_reg(const float* h, const float* src, const unsigned char* mask, int B, int Q, int idf, int cs,
+                          int L, float* wc, float* attn, cudaStream_t stream) {
+  const size_t sm = sizeof(float) * idf * 20;
+  dim3 grid(og_cdiv(Q, ATT_Q * QPT), B);
+  att_general_fwd_reg_kernel<QPT><<<grid, ATT_Q, sm, stream>>>(h, src, mask, B, Q, idf, cs, L, wc, attn);
+  OG_RETURN_LAST_ERROR();
+}
+
 OG_API int og_att_general_fwd(const float* h, const float* src, const unsigned char* mask, int B, int Q, int idf,
                               int cs, int L, float* wc, float* attn, cudaStream_t stream) {
   if (L > LMAX || cs % 4 || idf > cs) return (int)cudaErrorInvalidValue;
   if (B == 0 || Q == 0) return 0;
+  static const int reg_qpt = getenv("OG_ATT_QPT") ? atoi(getenv("OG_ATT_QPT")) : 4;
+  if (reg_qpt > 0 && L <= 20 && Q >= 4096 && idf * 20 * sizeof(float) <= 48 * 1024) {
+    if (reg_qpt == 1) return launch_att_reg<1>(h, src, mask, B, Q, idf, cs, L, wc, attn, stream);
+    if (reg_qpt == 2) return launch_att_reg<2>(h, src, mask, B, Q, idf, cs, L, wc, attn, stream);
+    return launch_att_reg<4>(h, src, mask, B, Q, idf, cs, L, wc, attn, stream);
+  }
   if (L <= 20 && Q >= 4096) {   // the large maps of the hot path: two queries per thread
     constexpr int QPT = 2;
     const size_t sm = sizeof(float) * (ATT_Q * QPT * (cs + 1) + idf * 20);
@@ -350,12 +489,166 @@ __global__ void __launch_bounds__(ATT_Q) att_general_bwd_kernel(const float* __r
   }
 }
 
+// Backward for L <= 20 (the hot path): same arithmetic as above with the forward kernel's register blocking --
+// word-projection rows of 20 floats read with broadcast LDS.128, packed FFMA2, no `l < L` predicates (rows are zero
+// padded).  Phases: (A) gA = g_wc . src, softmax backward -> gS in registers; (C) the block's contribution to g_src
+// ([48 c x 2 halves of 10 words] threads, reduction over the block's 128 queries from shared memory); (B) g_h rows.
+__global__ void __launch_bounds__(ATT_Q, 3)
+att_general_bwd20_kernel(const float* __restrict__ h, const float* __restrict__ src, const float* __restrict__ attn,
+                         const float* __restrict__ g_wc, const float* __restrict__ g_attn, int B, int Q, int idf,
+                         int cs, int L, float* __restrict__ g_h, float* __restrict__ g_src) {
+  constexpr int LM = 20;
+  extern __shared__ __align__(16) float smem[];
+  const int pitch = cs + 1;
+  float* ssrc = smem;                         // [idf][LM] zero padded
+  float* sA = ssrc + idf * LM;                // [ATT_Q][LM]
+  float* sG = sA + ATT_Q * LM;                // [ATT_Q][LM]
+  float* th = sG + ATT_Q * LM;                // [ATT_Q][pitch]  h rows, later g_h rows
+  float* tg = th + ATT_Q * pitch;             // [ATT_Q][pitch]  g_wc rows
+  const int b = blockIdx.y, q0 = blockIdx.x * ATT_Q, t = threadIdx.x;
+  const int nq = min(ATT_Q, Q - q0);
+  for (int i = t; i < idf * LM; i += ATT_Q) {
+    const int c = i / LM, l = i - c * LM;
+    ssrc[i] = l < L ? src[((long long)b * idf + c) * L + l] : 0.f;
+  }
+  const float* hb = h + ((long long)b * Q + q0) * cs;
+  const float* gb = g_wc + ((long long)b * Q + q0) * cs;
+  const int cs4 = cs >> 2;
+  for (int r = t / cs4, c4 = t - (t / cs4) * cs4, i = t; i < ATT_Q * cs4; i += ATT_Q) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), w = v;
+    if (r < nq) {
+      v = ldg4(hb + i * 4);
+      w = ldg4(gb + i * 4);
+    }
+    float* d = th + r * pitch + c4 * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    float* e = tg + r * pitch + c4 * 4;
+    e[0] = w.x; e[1] = w.y; e[2] = w.z; e[3] = w.w;
+    c4 += ATT_Q % cs4;
+    r += ATT_Q / cs4;
+    if (c4 >= cs4) { c4 -= cs4; ++r; }
+  }
+  __syncthreads();
+  // (A) gA[l] = sum_c g_wc[q][c] * src[c][l]
+  float2 s2[LM / 2];
+#pragma unroll
+  for (int l = 0; l < LM / 2; ++l) s2[l] = make_float2(0.f, 0.f);
+  {
+    const float* grow = tg + t * pitch;
+    for (int c = 0; c < idf; ++c) {
+      const float gv = grow[c];
+      const float2 g2 = make_float2(gv, gv);
+      const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
+#pragma unroll
+      for (int l4 = 0; l4 < LM / 4; ++l4) {
+        const float4 w = sr[l4];
+        s2[2 * l4] = ffma2(g2, make_float2(w.x, w.y), s2[2 * l4]);
+        s2[2 * l4 + 1] = ffma2(g2, make_float2(w.z, w.w), s2[2 * l4 + 1]);
+      }
+    }
+  }
+  {
+    float A[LM], gA[LM];
+    const int q = q0 + t;
+    const bool live = t < nq;
+#pragma unroll
+    for (int l = 0; l < LM / 2; ++l) {
+      gA[2 * l] = s2[l].x;
+      gA[2 * l + 1] = s2[l].y;
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int l = 0; l < LM; ++l) {
+      A[l] = 0.f;
+      if (l < L && live) {
+        A[l] = attn[((long long)b * L + l) * Q + q];
+        if (g_attn) gA[l] += g_attn[((long long)b * L + l) * Q + q];
+      }
+      dot = fmaf(gA[l], A[l], dot);
+    }
+#pragma unroll
+    for (int l = 0; l < LM; ++l) gA[l] = A[l] * (gA[l] - dot);          // gS (zero for dead rows and l >= L)
+#pragma unroll
+    for (int l4 = 0; l4 < LM / 4; ++l4) {
+      *reinterpret_cast<float4*>(sA + t * LM + 4 * l4) = make_float4(A[4 * l4], A[4 * l4 + 1], A[4 * l4 + 2], A[4 * l4 + 3]);
+      *reinterpret_cast<float4*>(sG + t * LM + 4 * l4) =
+          make_float4(gA[4 * l4], gA[4 * l4 + 1], gA[4 * l4 + 2], gA[4 * l4 + 3]);
+    }
+#pragma unroll
+    for (int l = 0; l < LM / 2; ++l) s2[l] = make_float2(gA[2 * l], gA[2 * l + 1]);
+  }
+  __syncthreads();
+  // (C) block-partial g_src[c][l] = sum_r h[r][c] * gS[r][l] + g_wc[r][c] * A[r][l]
+  if (t < 2 * idf && idf <= 64) {
+    const int c = t % idf, half = t / idf;              // words [10 * half, 10 * half + 10)
+    float2 acc[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[k] = make_float2(0.f, 0.f);
+    for (int r = 0; r < ATT_Q; ++r) {
+      const float hv = th[r * pitch + c], gv = tg[r * pitch + c];
+      const float2 h2 = make_float2(hv, hv), g2 = make_float2(gv, gv);
+      const float2* pg = reinterpret_cast<const float2*>(sG + r * LM + 10 * half);
+      const float2* pa = reinterpret_cast<const float2*>(sA + r * LM + 10 * half);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc[k] = ffma2(h2, pg[k], ffma2(g2, pa[k], acc[k]));
+    }
+    float* dst = g_src + ((long long)b * idf + c) * L;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int l = 10 * half + 2 * k;
+      if (l < L) atomicAdd(dst + l, acc[k].x);
+      if (l + 1 < L) atomicAdd(dst + l + 1, acc[k].y);
+    }
+  }
+  __syncthreads();
+  // (B) g_h[c] = sum_l gS[l] * src[c][l], written over the h rows
+  {
+    float* row = th + t * pitch;
+    for (int c = 0; c < cs; ++c) {
+      float acc = 0.f;
+      if (c < idf) {
+        const float4* sr = reinterpret_cast<const float4*>(ssrc + c * LM);
+        float2 a2 = make_float2(0.f, 0.f), b2 = a2;
+#pragma unroll
+        for (int l4 = 0; l4 < LM / 4; ++l4) {
+          const float4 w = sr[l4];
+          a2 = ffma2(make_float2(w.x, w.y), s2[2 * l4], a2);
+          b2 = ffma2(make_float2(w.z, w.w), s2[2 * l4 + 1], b2);
+        }
+        acc = (a2.x + b2.x) + (a2.y + b2.y);
+      }
+      row[c] = acc;
+    }
+  }
+  __syncthreads();
+  float* ob = g_h + ((long long)b * Q + q0) * cs;
+  for (int r = t / cs4, c4 = t - (t / cs4) * cs4, i = t; i < nq * cs4; i += ATT_Q) {
+    const float* d = th + r * pitch + c4 * 4;
+    st4(ob + i * 4, make_float4(d[0], d[1], d[2], d[3]));
+    c4 += ATT_Q % cs4;
+    r += ATT_Q / cs4;
+    if (c4 >= cs4) { c4 -= cs4; ++r; }
+  }
+}
+
 OG_API int og_att_general_bwd(const float* h, const float* src, const float* attn, const float* g_wc,
                               const float* g_attn, int B, int Q, int idf, int cs, int L, float* g_h, float* g_src,
                               cudaStream_t stream) {
   if (L > LMAX || cs % 4 || idf > cs) return (int)cudaErrorInvalidValue;
   OG_CHECK(cudaMemsetAsync(g_src, 0, sizeof(float) * (size_t)B * idf * L, stream));
   if (B == 0 || Q == 0) return 0;
+  static const bool old_bwd = getenv("OG_ATT_OLD_BWD") != nullptr;
+  if (!old_bwd && L <= 20 && idf <= 64) {
+    const size_t sm20 = sizeof(float) * ((size_t)idf * 20 + 2 * ATT_Q * 20 + 2 * (size_t)ATT_Q * (cs + 1));
+    static size_t configured20 = 0;
+    if (sm20 > configured20) {
+      OG_CHECK(cudaFuncSetAttribute(att_general_bwd20_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm20));
+      configured20 = sm20;
+    }
+    dim3 grid20(og_cdiv(Q, ATT_Q), B);
+    att_general_bwd20_kernel<<<grid20, ATT_Q, sm20, stream>>>(h, src, attn, g_wc, g_attn, B, Q, idf, cs, L, g_h, g_src);
+    OG_RETURN_LAST_ERROR();
+  }
   size_t sm = sizeof(float) * (2 * ATT_Q * (cs + 1) + 2 * ATT_Q * L + idf * L);
   OG_CHECK(cudaFuncSetAttribute(att_general_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   dim3 grid(og_cdiv(Q, ATT_Q), B);
@@ -482,9 +775,59 @@ __global__ void __launch_bounds__(256) paint_max_fwd_kernel(const float* __restr
     out[((long long)b * P + p0 + j) * dstride + doff + k] = v;
   }
 }
+// Vectorised variant: a thread produces FOUR consecutive channels of one pixel (one 16-byte store; a warp writes
+// whole 128-byte lines of the NHWC row), the roi features sit in shared memory channel-contiguous (one LDS.128 per roi),
+// the block's mask tile is read once, and the (pixel, channel-quad) walk has no divisions.  Channels [num, 4*nq4) are
+// written as zeros (the pad lanes of the NHWC tensor), so the caller needs no separate zero fill.
+constexpr int PAINT2_PIX = 128;
+__global__ void __launch_bounds__(256) paint_max_fwd4_kernel(const float* __restrict__ f, const float* __restrict__ m,
+                                                             int num, int nq4, int R, int Rtot, long long P,
+                                                             float* __restrict__ out, int dstride, int doff) {
+  extern __shared__ __align__(16) float smem[];
+  float* sf = smem;                      // [R][4 * nq4]  (channel-contiguous, zero padded)
+  float* sm = smem + R * 4 * nq4;        // [R][PAINT2_PIX]
+  const int b = blockIdx.y, t = threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * PAINT2_PIX;
+  const int np = (int)min((long long)PAINT2_PIX, P - p0);
+  const int nc = 4 * nq4;
+  for (int i = t; i < R * nc; i += 256) {
+    const int r = i / nc, k = i - r * nc;
+    sf[i] = k < num ? f[((long long)b * num + k) * R + r] : 0.f;
+  }
+  for (int i = t; i < R * PAINT2_PIX; i += 256) {
+    const int r = i / PAINT2_PIX, j = i - r * PAINT2_PIX;
+    sm[i] = j < np ? m[((long long)b * Rtot + r) * P + p0 + j] : 0.f;
+  }
+  __syncthreads();
+  const int dj = 256 / nq4, dk = 256 - dj * nq4;
+  int j = t / nq4, k4 = t - j * nq4;
+  for (; j < np; j += dj, k4 += dk) {
+    if (k4 >= nq4) { k4 -= nq4; ++j; if (j >= np) break; }
+    const float4 f0 = *reinterpret_cast<const float4*>(sf + 4 * k4);
+    const float m0 = sm[j];
+    float4 v = make_float4(f0.x * m0, f0.y * m0, f0.z * m0, f0.w * m0);
+    for (int r = 1; r < R; ++r) {
+      const float4 fr = *reinterpret_cast<const float4*>(sf + r * nc + 4 * k4);
+      const float mr = sm[r * PAINT2_PIX + j];
+      v.x = fmaxf(v.x, fr.x * mr); v.y = fmaxf(v.y, fr.y * mr);
+      v.z = fmaxf(v.z, fr.z * mr); v.w = fmaxf(v.w, fr.w * mr);
+    }
+    st4(out + ((long long)b * P + p0 + j) * dstride + doff + 4 * k4, v);
+  }
+}
+
 OG_API int og_paint_max_fwd(const float* f, const float* m, int B, int num, int R, int Rtot, long long P, float* out,
                             int dstride, int doff, cudaStream_t stream) {
   if (B == 0 || P == 0) return 0;
+  if (R > 0 && dstride % 4 == 0 && doff % 4 == 0 && (num + 3) / 4 * 4 + doff <= dstride && (num + 3) / 4 <= 256) {
+    const int nq4 = (num + 3) / 4;
+    const size_t smb = sizeof(float) * ((size_t)R * 4 * nq4 + (size_t)R * PAINT2_PIX);
+    if (smb <= 48 * 1024) {
+      dim3 grid4(og_cdiv(P, PAINT2_PIX), B);
+      paint_max_fwd4_kernel<<<grid4, 256, smb, stream>>>(f, m, num, nq4, R, Rtot, P, out, dstride, doff);
+      OG_RETURN_LAST_ERROR();
+    }
+  }
   if (R == 0) {   // no boxes in the whole batch: the painted maps are zero (ref: model.py:571-576, 689-694)
     OG_CHECK(cudaMemset2DAsync(out + doff, sizeof(float) * (size_t)dstride, 0, sizeof(float) * (size_t)num,
                                (size_t)B * (size_t)P, stream));

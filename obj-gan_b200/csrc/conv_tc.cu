@@ -1639,7 +1639,7 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
     mbl = mbh;
   }
   // persistent CTA pairs (cta_group::2, double-buffered accumulators): every BN = 208 / 256 problem with enough tiles
-  static const int tcp = getenv("OG_TCP") ? atoi(getenv("OG_TCP")) : 1;
+  static const int tcp = getenv("OG_TCP") ? atoi(getenv("OG_TCP")) : 2;
   static const long long tcp_min = getenv("OG_TCP_MIN") ? atoll(getenv("OG_TCP_MIN")) : 64;
   if (tcp && p.ksplit == 1 && (tcp > 1 || BNsel == 208 || BNsel == 256) && (long long)grid.x * grid.y >= tcp_min) {
     CUtensorMap pbh, pbl;
