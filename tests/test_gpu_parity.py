@@ -348,6 +348,29 @@ def test_roi_align_avg_and_backward():
     close(fg2.grad, torch.from_numpy(want_g), 1e-5, what="bwd")
 
 
+def test_torch_extension_roi_align_matches_c_abi():
+    """torch.ops.objgan_b200.roi_align_forward_cuda / backward_cuda (TORCH_LIBRARY layer) and the RoIAlignFunction that
+    replaces the reference's functions/roi_align.py give the bits of the ctypes path (same launchers underneath)."""
+    from objgan_b200.torch_ext import RoIAlignFunction, roi_align
+    torch.manual_seed(4)
+    feat = torch.randn(3, 16, 32, 32, device=DEV)
+    rois = torch.from_numpy(_rois(3, 10, 32, 11)).to(DEV)
+    want = ops.roi_align(feat, rois, 6, 6, 1.0 / 16)
+    out = feat.new_zeros(rois.size(0), 16, 6, 6)
+    assert roi_align.roi_align_forward_cuda(6, 6, 1.0 / 16, feat, rois, out) == 1
+    assert torch.equal(out, want)
+    fg = feat.clone().requires_grad_(True)
+    y = RoIAlignFunction(6, 6, 1.0 / 16)(fg, rois)
+    assert torch.equal(y, want)
+    g = torch.randn_like(y)
+    y.backward(g)
+    fg2 = feat.clone().requires_grad_(True)
+    ops.roi_align(fg2, rois, 6, 6, 1.0 / 16).backward(g)
+    close(fg.grad, fg2.grad, 1e-5, what="grad through the extension")     # atomics: order differs run to run
+    with pytest.raises(RuntimeError):
+        roi_align.roi_align_forward_cuda(6, 6, 1.0 / 16, feat, rois[:, :4].contiguous(), out)
+
+
 @pytest.mark.parametrize("B,C,H", [(3, 8, 32), (32, 384, 64), (4, 768, 32)])
 def test_roi_align_avg_channels_last_is_bit_identical(B, C, H):
     """The channels-last fused RoIAlignAvg (what the object discriminators run) returns exactly the bits of the NCHW

@@ -300,3 +300,17 @@ def test_step_a_dp_one_shard_is_step_a():
     for k in a.g_keys:
         assert torch.allclose(ka["g_grads"][k], kb["g_grads"][k], rtol=1e-4, atol=1e-7), k
         assert torch.allclose(a.g[k], b.g[k], rtol=0, atol=4.1e-4), k
+
+
+def test_torch_extension_registers_reference_entry_points():
+    """The thin PyTorch C++ extension (north_star's boundary): torch.ops.objgan_b200 exposes roi_align_forward_cuda /
+    roi_align_backward_cuda with the reference's argument order (roi_align_cuda.h:1-5) on the CUDA dispatch key; no
+    compute here (no GPU) -- CPU tensors must be rejected, not silently handled."""
+    import objgan_b200.torch_ext as ext
+    ops_ = ext.load()
+    for name in ("roi_align_forward_cuda", "roi_align_backward_cuda"):
+        schema = getattr(ops_, name).default._schema
+        assert [a.name for a in schema.arguments][:3] == ["aligned_height", "aligned_width", "spatial_scale"]
+        assert len(schema.arguments) == 6
+    with pytest.raises(Exception):
+        ops_.roi_align_forward_cuda(6, 6, 1 / 16, torch.zeros(1, 2, 8, 8), torch.zeros(1, 5), torch.zeros(1, 2, 6, 6))
