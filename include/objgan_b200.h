@@ -262,6 +262,14 @@ int og_form_hmaps(const float* masks, const long long* cls, const long long* num
 int og_form_clabels_feat(const float* emb, const long long* cls, const long long* num_rois, int B, int R, int Rmax, int E,
                          int ncls, float* out, cudaStream_t stream);
 
+/* Whole-network weight re-packing after an optimiser step: og_amax + og_pack_weights_f16 for EVERY registered
+ * (weight, layout) of a network in one launch each, from a device-resident int64 job table.
+ *  amax job (4 fields): x, n, out word, first block index;  a block covers 4096 elements
+ *  pack job (14 fields): w (OIHW), hi, lo (or 0), amax word, Co, Ci, taps, Cip, Kp, split, splitp, transposed, total,
+ *                        first block index */
+int og_amax_multi(const long long* jobs, int njobs, int total_blocks, cudaStream_t stream);
+int og_pack_weights_f16_multi(const long long* jobs, int njobs, int total_blocks, cudaStream_t stream);
+
 /* zero-fill (a memset node when captured in a CUDA graph; no kernel launch) */
 int og_zero_bytes(float* p, long long bytes, cudaStream_t stream);
 

@@ -816,3 +816,100 @@ OG_API int og_unpack_upsample_wgrad(const float* dwp, int Co, int Ci, int Cip, i
   unpack_upsample_wgrad_kernel<<<blocks, 256, 0, stream>>>(dwp, Co, Ci, Cip, Kp, split, splitp, grad_oihw);
   OG_RETURN_LAST_ERROR();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-tensor weight re-packing: after an optimiser step EVERY convolution weight of a network needs its max|w| and
+// its fp16 hi/lo operand matrices again (og_amax + og_pack_weights_f16 per layer and layout: ~300 tiny launches per
+// training step).  These two kernels do the whole network in one launch each from a device-resident job table
+// (int64 fields), a block being assigned to (job, chunk) by its index.
+//   amax job : [x, n, out, block_start]                                  (blocks of 256 threads x 16 floats)
+//   pack job : [w, hi, lo, amax, Co, Ci, taps, Cip, Kp, split, splitp, transposed, total, block_start]
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int MJ_AMAX_FIELDS = 4, MJ_PACK_FIELDS = 14, MJ_CHUNK = 4096;
+
+__device__ __forceinline__ int mj_find(const long long* __restrict__ jobs, int njobs, int fields, int start_field,
+                                       long long blk) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {                       // last job whose block_start <= blk
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[(long long)mid * fields + start_field] <= blk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) amax_multi_kernel(const long long* __restrict__ jobs, int njobs) {
+  const int j = mj_find(jobs, njobs, MJ_AMAX_FIELDS, 3, blockIdx.x);
+  const long long* f = jobs + (long long)j * MJ_AMAX_FIELDS;
+  const float* x = reinterpret_cast<const float*>(f[0]);
+  const long long n = f[1];
+  unsigned* out = reinterpret_cast<unsigned*>(f[2]);
+  const long long base = ((long long)blockIdx.x - f[3]) * MJ_CHUNK;
+  float m = 0.f;
+  for (long long i = base + threadIdx.x; i < n && i < base + MJ_CHUNK; i += 256) m = fmaxf(m, fabsf(__ldg(x + i)));
+  m = warp_max(m);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) m = fmaxf(m, sm[k]);
+    atomicMax(out, __float_as_uint(m));
+  }
+}
+__global__ void amax_zero_multi_kernel(const long long* __restrict__ jobs, int njobs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < njobs) *reinterpret_cast<unsigned*>(jobs[(long long)j * MJ_AMAX_FIELDS + 2]) = 0u;
+}
+
+__global__ void __launch_bounds__(256) pack_multi_kernel(const long long* __restrict__ jobs, int njobs) {
+  const int j = mj_find(jobs, njobs, MJ_PACK_FIELDS, 13, blockIdx.x);
+  const long long* f = jobs + (long long)j * MJ_PACK_FIELDS;
+  const float* w = reinterpret_cast<const float*>(f[0]);
+  __half* hi = reinterpret_cast<__half*>(f[1]);
+  __half* lo = reinterpret_cast<__half*>(f[2]);
+  const float scale = og_exp2i(og_scale_exp(__ldg(reinterpret_cast<const unsigned*>(f[3]))));
+  const int Co = (int)f[4], Ci = (int)f[5], taps = (int)f[6], Cip = (int)f[7], Kp = (int)f[8];
+  const int split = (int)f[9], splitp = (int)f[10], transposed = (int)f[11];
+  const long long total = f[12];
+  const long long base = ((long long)blockIdx.x - f[13]) * MJ_CHUNK;
+  for (long long o = base + threadIdx.x; o < total && o < base + MJ_CHUNK; o += 256) {
+    int cm, ci, tap;
+    if (!transposed) {            // [(tap, ci)][cm]
+      cm = (int)(o % Kp);
+      const long long t = o / Kp;
+      ci = (int)(t % Cip);
+      tap = (int)(t / Cip);
+    } else {                      // [(tap, cm)][ci]
+      ci = (int)(o % Cip);
+      const long long t = o / Cip;
+      cm = (int)(t % Kp);
+      tap = (int)(t / Kp);
+    }
+    int co;
+    if (split > 0) {
+      if (cm < split) co = cm;
+      else if (cm >= splitp && cm < splitp + split) co = cm - (splitp - split);
+      else co = -1;
+    } else {
+      co = cm < Co ? cm : -1;
+    }
+    float v = 0.f;
+    if (co >= 0 && co < Co && ci < Ci) v = __ldg(w + ((long long)co * Ci + ci) * taps + tap);
+    store_hilo_f16(v, scale, hi, lo, o);
+  }
+}
+}  // namespace
+
+// jobs: device table of njobs x 4 int64 (see above), total_blocks = sum of ceil(n / 4096)
+OG_API int og_amax_multi(const long long* jobs, int njobs, int total_blocks, cudaStream_t stream) {
+  if (njobs <= 0) return 0;
+  amax_zero_multi_kernel<<<og_cdiv(njobs, 128), 128, 0, stream>>>(jobs, njobs);
+  if (total_blocks > 0) amax_multi_kernel<<<total_blocks, 256, 0, stream>>>(jobs, njobs);
+  OG_RETURN_LAST_ERROR();
+}
+// jobs: device table of njobs x 14 int64, total_blocks = sum of ceil(total / 4096)
+OG_API int og_pack_weights_f16_multi(const long long* jobs, int njobs, int total_blocks, cudaStream_t stream) {
+  if (njobs <= 0 || total_blocks <= 0) return 0;
+  pack_multi_kernel<<<total_blocks, 256, 0, stream>>>(jobs, njobs);
+  OG_RETURN_LAST_ERROR();
+}

@@ -116,7 +116,61 @@ class PackedWeights:
             _call("og_pack_weights_f16", _p(w), co, ci, kh, kw, cip, kp, split, splitp, transposed,
                   _p(self._amax(w)), _p(hi), _p(lo))
             self.hl[transposed] = (hi, lo, self._amax(w))
+            plan = getattr(w, "og_pack_plan", None)
+            if plan is not None:            # the owner re-packs all of its weights in one launch after its Adam step
+                plan.record(self, w, cip, kp, split, splitp, transposed, hi, lo, self._amax(w))
         return self.hl[transposed]
+
+
+class PackPlan:
+    """All (weight, layout) fp16 operand copies of ONE network, re-derived by two launches (og_amax_multi +
+    og_pack_weights_f16_multi) right after the network's optimiser step instead of lazily, layer by layer, at the next
+    use (~300 tiny launches per training step).  Jobs are recorded the first time a layer asks for a copy; from then on
+    ``run`` refreshes the SAME buffers and re-validates the layers' caches."""
+
+    def __init__(self):
+        self.jobs = []              # (cache, w, cip, kp, split, splitp, transposed, hi, lo, amax)
+        self._tables = None
+        self._n_built = 0
+
+    def record(self, cache, w, cip, kp, split, splitp, transposed, hi, lo, amax):
+        self.jobs.append((cache, w, cip, kp, split, splitp, transposed, hi, lo, amax))
+
+    def _build(self, device):
+        CH = 4096
+        arows, prows, ab, pb, seen = [], [], 0, 0, {}
+        for cache, w, cip, kp, split, splitp, tr, hi, lo, amax in self.jobs:
+            if id(amax) not in seen:
+                seen[id(amax)] = True
+                arows.append([w.data_ptr(), w.numel(), amax.data_ptr(), ab])
+                ab += (w.numel() + CH - 1) // CH
+            co, ci, kh, kw = w.shape
+            total = kh * kw * cip * kp
+            prows.append([w.data_ptr(), hi.data_ptr(), 0 if lo is None else lo.data_ptr(), amax.data_ptr(), co, ci,
+                          kh * kw, cip, kp, split, splitp, tr, total, pb])
+            pb += (total + CH - 1) // CH
+        mk = lambda rows: torch.tensor(rows, dtype=torch.int64).to(device)
+        self._tables = (mk(arows), len(arows), ab, mk(prows), len(prows), pb)
+        self._n_built = len(self.jobs)
+
+    def run(self):
+        """Call after the weights changed (and after the parameter epoch was bumped)."""
+        if not self.jobs or _lib.DRY_RUN:
+            return
+        if self._tables is None or self._n_built != len(self.jobs):
+            self._build(self.jobs[0][1].device)
+        at, an, ab, pt, pn, pb = self._tables
+        _call("og_amax_multi", _p(at), an, ab)
+        _call("og_pack_weights_f16_multi", _p(pt), pn, pb)
+        touched = {}
+        for cache, w, cip, kp, split, splitp, tr, hi, lo, amax in self.jobs:
+            if id(cache) not in touched:
+                touched[id(cache)] = cache
+                cache.key = (w.data_ptr(), w._version, _param_epoch[0], cip, kp, split)
+                cache.f = cache.t = None
+                cache.hl = {}
+                cache.amax = amax
+            cache.hl[tr] = (hi, lo, amax)
 
 
 # Contraction engine for the convolutions: "f16x3" = tcgen05 tensor cores with the error-compensated

@@ -49,6 +49,9 @@ class FlatBucket:
             p.og_grad_sink = p.grad          # the backward kernels accumulate here directly (ops._grad_sink)
         self.avg = self.flat.clone() if ema else None
         self.offsets = offs
+        self.plan = ops.PackPlan()           # fp16 operand copies of this network's conv weights: re-packed in one go
+        for p in self.params:
+            p.og_pack_plan = self.plan
         self.step = 0
         self.step_dev = torch.zeros((), device=dev, dtype=torch.int64)   # device mirror (CUDA-graph replay)
         ops.bump_param_epoch()
@@ -64,6 +67,7 @@ class FlatBucket:
         self.step += 1
         ops.adam_ema_(self.flat, self.grad, self.m, self.v, self.avg, self.step, lr=lr, b1=0.5, b2=0.999, eps=1e-8,
                       gscale=gscale, decay=0.999, step_dev=self.step_dev)
+        self.plan.run()                       # every tensor-core operand copy of this network, two launches
 
     def ema_state_dict(self):
         """EMA weights keyed like ``module.state_dict()`` (what the reference saves as netG_epoch_%d.pth,
