@@ -184,7 +184,9 @@ class StepATrainer:
     def capture(self, inp: dict, warmup: int = 2) -> None:
         """Capture one whole Step-A step (forward, backward, all-reduce, optimiser) into a CUDA graph.  ``inp`` fixes
         the shapes; later ``step`` calls copy their inputs into the captured static buffers and replay.  The ~1200
-        kernel launches of a step then cost one graph launch instead of ~0.1 ms of Python/ctypes each."""
+        kernel launches of a step then cost one graph launch instead of ~0.1 ms of Python/ctypes each.  The ``warmup``
+        eager steps it runs first are undone afterwards (weights, Adam state, EMA, BatchNorm buffers restored), so the
+        call does not advance training."""
         from . import lib as _l
         self._static = {}
         for k, v in inp.items():
@@ -197,10 +199,28 @@ class StepATrainer:
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
+        # the warm-up steps are REAL optimiser steps on the sample batch: snapshot everything they touch (weights, Adam
+        # moments, EMA, step counters, BatchNorm buffers) and put it back, so capture() leaves the training state as
+        # it found it
+        nets = [self.netG, *self.netsPatD]
+        snap = [(b, b.flat.clone(), b.m.clone(), b.v.clone(), None if b.avg is None else b.avg.clone(), b.step,
+                 b.step_dev.clone()) for b in [self.bG, *self.bD]]
+        bufs = [[t.clone() for t in m.buffers()] for m in nets]
         with torch.cuda.stream(side):
             for _ in range(warmup):          # allocator / kernel-attribute / packed-weight-cache steady state
                 self._eager_step(self._static)
         cur.wait_stream(side)
+        torch.cuda.synchronize()
+        for b, flat, m, v, avg, step, step_dev in snap:
+            b.flat.copy_(flat); b.m.copy_(m); b.v.copy_(v); b.step = step; b.step_dev.copy_(step_dev)
+            if avg is not None:
+                b.avg.copy_(avg)
+        for mod, saved in zip(nets, bufs):
+            for t, s0 in zip(mod.buffers(), saved):
+                t.copy_(s0)
+        ops.bump_param_epoch()
+        for b in [self.bG, *self.bD]:
+            b.plan.run()                     # operand copies of the restored weights
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         n0 = _l.get().launches
@@ -211,7 +231,6 @@ class StepATrainer:
         self.launches_per_step = _l.get().launches - n0
         for b in [self.bG, *self.bD]:
             b.step -= 1          # the captured pass was recorded, not executed
-        ops.bump_param_epoch()
 
     def _load_static(self, inp: dict) -> None:
         for k, v in inp.items():
@@ -237,6 +256,13 @@ class StepATrainer:
         ops.bump_param_epoch()
         return self._static_out
 
+    @staticmethod
+    def _nvtx(name):
+        """NVTX range around a phase of the step (OBJGAN_NVTX=1; shows up in Nsight timelines), else a no-op."""
+        if os.environ.get("OBJGAN_NVTX") == "1" and torch.cuda.is_available():
+            return torch.cuda.nvtx.range(name)
+        return contextlib.nullcontext()
+
     def _eager_step(self, inp: dict) -> dict:
         """One Step-A step on device-resident inputs.  Returns losses as device scalars."""
         lr_d, lr_g = cfg.TRAIN.DISCRIMINATOR_LR, cfg.TRAIN.GENERATOR_LR
@@ -244,7 +270,8 @@ class StepATrainer:
         sent = inp["sent_emb"]
         # (2) generate fake images
         self.bG.requires_grad_(True)
-        fake_imgs, _bt_c, _att, _bt_att, mu, logvar = self.generate(inp)
+        with self._nvtx("G forward"):
+            fake_imgs, _bt_c, _att, _bt_att, mu, logvar = self.generate(inp)
         out = {}
         # (3-1) update the patch discriminators
         works = []
@@ -277,14 +304,16 @@ class StepATrainer:
         for b in self.bD:
             b.requires_grad_(False)
         self.bG.zero_grad()
-        err_g, _ = losses.G_loss_pat(self.netsPatD, fake_imgs, sent, streams)
-        kl = losses.KL_loss(mu, logvar)
-        total = err_g + kl
-        total.backward()
-        w = self._allreduce(self.bG)
-        if w is not None:
-            w.wait()
-        self.bG.adam(lr_g, gs)  # fused Adam + EMA (trainer.py:460-462)
+        with self._nvtx("G loss + backward"):
+            err_g, _ = losses.G_loss_pat(self.netsPatD, fake_imgs, sent, streams)
+            kl = losses.KL_loss(mu, logvar)
+            total = err_g + kl
+            total.backward()
+        with self._nvtx("G all-reduce + Adam + EMA"):
+            w = self._allreduce(self.bG)
+            if w is not None:
+                w.wait()
+            self.bG.adam(lr_g, gs)  # fused Adam + EMA (trainer.py:460-462)
         out["errG"] = err_g.detach()
         out["kl"] = kl.detach()
         out["fake_imgs"] = [f.detach() for f in fake_imgs]

@@ -610,7 +610,9 @@ def test_cuda_graph_replay_matches_eager():
     a = trainer.StepATrainer(device=DEV, seed=5)
     b = trainer.StepATrainer(device=DEV, seed=5)
     da, db = a.to_device(inp), b.to_device(inp)
-    b.capture(db, warmup=2)                      # two eager warm-up steps, then the capture itself (not executed)
+    p_before = b.bG.flat.clone()
+    b.capture(db, warmup=2)                      # two eager warm-up steps (undone afterwards), then the capture
+    assert torch.equal(b.bG.flat, p_before) and b.bG.step == 0 and int(b.bG.step_dev) == 0   # training state untouched
     # bring the eager trainer to exactly b's state (weights, Adam moments, EMA, BatchNorm buffers, step counters)
     for x, y in zip([a.bG, *a.bD], [b.bG, *b.bD]):
         for name in ("flat", "m", "v"):
@@ -630,7 +632,7 @@ def test_cuda_graph_replay_matches_eager():
     for i in range(3):
         close(ob["fake_imgs"][i], oa["fake_imgs"][i], 1e-4, what=f"fake{i}")   # forward is deterministic
     assert rel_l2(b.bG.grad, a.bG.grad) < 1e-2                                  # backward has atomics (order varies)
-    assert int(b.bG.step_dev) == int(a.bG.step_dev) == 3 and b.bG.step == 3
+    assert int(b.bG.step_dev) == int(a.bG.step_dev) == 1 and b.bG.step == 1
 
 
 @pytest.mark.parametrize("engine,l2,mx", [("simt", 5e-3, 3e-2), ("f16x3", 3e-2, 1e-1)])
