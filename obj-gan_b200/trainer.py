@@ -23,6 +23,8 @@ from . import losses, model, ops
 from .config import cfg
 
 ALIGN = 64  # floats; keeps every parameter view 256-byte aligned inside its bucket
+BRANCH_ADAM = os.environ.get("OBJGAN_BRANCH_ADAM", "1") == "1"   # exchange + optimiser step of each D on its own stream
+PACK_PLAN = os.environ.get("OBJGAN_PACK_PLAN", "1") == "1"       # re-pack a network's operand copies right after Adam
 
 
 class FlatBucket:
@@ -67,7 +69,8 @@ class FlatBucket:
         self.step += 1
         ops.adam_ema_(self.flat, self.grad, self.m, self.v, self.avg, self.step, lr=lr, b1=0.5, b2=0.999, eps=1e-8,
                       gscale=gscale, decay=0.999, step_dev=self.step_dev)
-        self.plan.run()                       # every tensor-core operand copy of this network, two launches
+        if PACK_PLAN:
+            self.plan.run()                   # every tensor-core operand copy of this network, two launches
 
     def ema_state_dict(self):
         """EMA weights keyed like ``module.state_dict()`` (what the reference saves as netG_epoch_%d.pth,
@@ -219,8 +222,9 @@ class StepATrainer:
             for t, s0 in zip(mod.buffers(), saved):
                 t.copy_(s0)
         ops.bump_param_epoch()
-        for b in [self.bG, *self.bD]:
-            b.plan.run()                     # operand copies of the restored weights
+        if PACK_PLAN:
+            for b in [self.bG, *self.bD]:
+                b.plan.run()                 # operand copies of the restored weights
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         n0 = _l.get().launches
@@ -293,13 +297,20 @@ class StepATrainer:
                 # the gradient exchange and the optimiser step of this discriminator stay on ITS branch: the
                 # all-reduce of the small 64 / 128 discriminators runs under the backward pass of the 256 one
                 # (every rank issues the three collectives in the same program order)
-                w = self._allreduce(b)
-                if w is not None:
-                    w.wait()
-                b.adam(lr_d, gs)
+                if BRANCH_ADAM:
+                    w = self._allreduce(b)
+                    if w is not None:
+                        w.wait()
+                    b.adam(lr_d, gs)
         for i, b in enumerate(self.bD):
             if streams:
                 main.wait_stream(streams[i])
+        if not BRANCH_ADAM:
+            works = [self._allreduce(b) for b in self.bD]
+            for w, b in zip(works, self.bD):
+                if w is not None:
+                    w.wait()
+                b.adam(lr_d, gs)
         # (4) update G through the updated discriminators (their weight gradients are not needed)
         for b in self.bD:
             b.requires_grad_(False)
