@@ -270,6 +270,10 @@ int og_form_clabels_feat(const float* emb, const long long* cls, const long long
 int og_amax_multi(const long long* jobs, int njobs, int total_blocks, cudaStream_t stream);
 int og_pack_weights_f16_multi(const long long* jobs, int njobs, int total_blocks, cudaStream_t stream);
 
+/* out[b][c] = x[b][perm[b][c]] over NCHW planes of P floats (permute_seg's class-channel shuffle, utils.py:445-462) */
+int og_permute_channels(const float* x, const long long* perm, int B, int C, long long P, float* out,
+                        cudaStream_t stream);
+
 /* zero-fill (a memset node when captured in a CUDA graph; no kernel launch) */
 int og_zero_bytes(float* p, long long bytes, cudaStream_t stream);
 

@@ -349,7 +349,9 @@ OG_API int og_att_general_fwd(const float* h, const float* src, const unsigned c
                               int cs, int L, float* wc, float* attn, cudaStream_t stream) {
   if (L > LMAX || cs % 4 || idf > cs) return (int)cudaErrorInvalidValue;
   if (B == 0 || Q == 0) return 0;
-  static const int reg_qpt = getenv("OG_ATT_QPT") ? atoi(getenv("OG_ATT_QPT")) : 4;
+  // measured (B200, Q = 16384, B = 16): staged kernel below 49 us, this register-resident variant 61 us at QPT = 4 (its
+  // row-strided 16-byte loads cost 32 L1 wavefronts each): kept selectable, not the default
+  static const int reg_qpt = getenv("OG_ATT_QPT") ? atoi(getenv("OG_ATT_QPT")) : 0;
   if (reg_qpt > 0 && L <= 20 && Q >= 4096 && idf * 20 * sizeof(float) <= 48 * 1024) {
     if (reg_qpt == 1) return launch_att_reg<1>(h, src, mask, B, Q, idf, cs, L, wc, attn, stream);
     if (reg_qpt == 2) return launch_att_reg<2>(h, src, mask, B, Q, idf, cs, L, wc, attn, stream);

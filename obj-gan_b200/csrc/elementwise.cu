@@ -655,3 +655,29 @@ OG_API int og_form_clabels_feat(const float* emb, const long long* cls, const lo
   form_clabels_feat_kernel<<<og_cdiv(total, 256), 256, 0, stream>>>(emb, cls, num_rois, R, Rmax, E, ncls, total, out);
   OG_RETURN_LAST_ERROR();
 }
+
+// out[b][c][:] = x[b][perm[b][c]][:]  (NCHW planes of P floats): the per-sample class-channel shuffle of permute_seg
+// (ref: miscc/utils.py:445-462) as ONE pass over the maps, with the permutation table built on the host
+__global__ void __launch_bounds__(256) permute_channels_kernel(const float* __restrict__ x,
+                                                               const long long* __restrict__ perm, int C, long long P,
+                                                               float* __restrict__ out) {
+  const int c = blockIdx.y, b = blockIdx.z;
+  const long long src = perm[(long long)b * C + c];
+  const float* xp = x + ((long long)b * C + src) * P;
+  float* op = out + ((long long)b * C + c) * P;
+  if ((P & 3) == 0) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P / 4; i += (long long)gridDim.x * blockDim.x)
+      st4(op + i * 4, ldg4(xp + i * 4));
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x)
+      op[i] = xp[i];
+  }
+}
+OG_API int og_permute_channels(const float* x, const long long* perm, int B, int C, long long P, float* out,
+                               cudaStream_t stream) {
+  if (B == 0 || C == 0 || P == 0) return 0;
+  int bx = og_cdiv(P / 4 > 0 ? P / 4 : P, 256);
+  if (bx > 64) bx = 64;
+  permute_channels_kernel<<<dim3(bx, C, B), 256, 0, stream>>>(x, perm, C, P, out);
+  OG_RETURN_LAST_ERROR();
+}

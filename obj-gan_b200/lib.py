@@ -85,5 +85,7 @@ def get() -> _Lib:
 
 
 def stream() -> int:
+    """Raw cudaStream_t of torch's current stream on the current device (the C-level query: torch.cuda.current_stream()
+    builds a Stream object through several Python layers, ~10 us per kernel launch)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())

@@ -77,16 +77,19 @@ def KL_loss(mu, logvar):
 
 def permute_seg(seg_conditions, rois, num_rois):
     """ref: miscc/utils.py:445-462 -- per sample, shuffle the segmentation channels of the classes present (host
-    `random.shuffle`, like the reference); returns the permuted maps and the indices of the samples that changed."""
+    `random.shuffle`, drawn in the reference's order); returns the permuted maps and the indices of the samples that
+    changed.  The shuffles become one (B, C) channel-permutation table, applied by ONE kernel pass
+    (``og_permute_channels``) instead of a clone plus two indexed copies per sample."""
     import random
     from copy import deepcopy
 
     import numpy as np
-    new_seg = seg_conditions.clone()
     rois_np = rois.detach().cpu().numpy() if torch.is_tensor(rois) else np.asarray(rois)
     nums = num_rois.detach().cpu().numpy().tolist() if torch.is_tensor(num_rois) else list(num_rois)
+    bsz, nch = seg_conditions.size(0), seg_conditions.size(1)
+    perm = np.tile(np.arange(nch, dtype=np.int64), (bsz, 1))
     valid = []
-    for b in range(seg_conditions.size(0)):
+    for b in range(bsz):
         if nums[b] == 0:
             continue
         classes = list(np.unique(rois_np[b, :nums[b], 4]).astype(int))
@@ -94,8 +97,10 @@ def permute_seg(seg_conditions, rois, num_rois):
         random.shuffle(shuffled)
         if classes != shuffled:
             valid.append(b)
-            new_seg[b, classes] = seg_conditions[b, shuffled]
-    return new_seg, valid
+            perm[b, classes] = shuffled                 # new_seg[b, classes] = seg[b, shuffled]
+    if not valid:
+        return seg_conditions, valid                    # nothing changed (the reference returns an equal clone)
+    return ops.permute_channels(seg_conditions, ops.h2d(perm, seg_conditions.device)), valid
 
 
 def shpD_loss(netShpD, real_imgs, fake_imgs, seg_conditions, rois, num_rois):
@@ -107,7 +112,7 @@ def shpD_loss(netShpD, real_imgs, fake_imgs, seg_conditions, rois, num_rois):
     err = ops.bce(net.UNCOND_DNET(real_features), 1.0, 1.0)
     fake_err = ops.bce(net.UNCOND_DNET(fake_features), 0.0, 1.0)
     if len(valid) > 0:
-        idx = torch.as_tensor(valid, device=real_imgs.device)
+        idx = ops.h2d(valid, real_imgs.device, torch.int64)
         wrong = netShpD(real_imgs[idx], fake_seg[idx])
         return err + (fake_err + ops.bce(net.UNCOND_DNET(wrong), 0.0, 1.0)) / 2.0
     return err + fake_err
@@ -136,8 +141,8 @@ def feat_select(pooled_feat, raw_bt_c_codes, fm_rois, num_rois, is_large_scale=F
             classes.append(int(fm[b, r, 4]))
     if not flat:
         return [], [], []
-    idx = torch.as_tensor(flat, dtype=torch.int64, device=pooled_feat.device)
-    idx_c = torch.as_tensor(flat_c, dtype=torch.int64, device=pooled_feat.device)
+    idx = ops.h2d(flat, pooled_feat.device, torch.int64)
+    idx_c = ops.h2d(flat_c, pooled_feat.device, torch.int64)
     feats = ops.gather_rows(pooled_feat.reshape((-1,) + tuple(pooled_feat.shape[2:])), idx)
     codes = ops.gather_rows(raw_bt_c_codes.reshape(-1, raw_bt_c_codes.shape[-1]), idx_c)
     return feats, np.asarray(classes, dtype=np.int64), codes
@@ -152,7 +157,7 @@ def objD_loss(netObjD, real_imgs, fake_imgs, seg_conditions, raw_conditions, raw
     dev = real_imgs.device
 
     def lookup(cls_idx, codes):
-        idx = torch.as_tensor(cls_idx, dtype=torch.int64, device=dev)
+        idx = ops.h2d([int(c) for c in cls_idx], dev, torch.int64)
         return ops.cat_rows_const(ops.gather_rows(raw_conditions.detach(), idx), codes)
 
     real_pooled = netObjD(real_imgs, seg_conditions, fm_rois, num_rois)
@@ -162,11 +167,11 @@ def objD_loss(netObjD, real_imgs, fake_imgs, seg_conditions, raw_conditions, raw
     fake_seg, valid = permute_seg(seg_conditions, fm_rois, num_rois)
     classes2 = []
     if len(valid) > 0:
-        vi = torch.as_tensor(valid, device=dev)
+        vi = ops.h2d(valid, dev, torch.int64)
         fm_t = fm_rois if torch.is_tensor(fm_rois) else torch.as_tensor(fm_rois)
         nr_t = num_rois if torch.is_tensor(num_rois) else torch.as_tensor(num_rois)
         # index the (host or device) box tables with an index on THEIR device: no device -> host read of `valid`
-        sel = lambda t: t[torch.as_tensor(valid, device=t.device)]
+        sel = lambda t: t[ops.h2d(valid, t.device, torch.int64)]
         pooled2 = netObjD(real_imgs[vi], fake_seg[vi], sel(fm_t), sel(nr_t))
         fake_features2, classes2, bt_c_codes2 = feat_select(pooled2, raw_bt_c_codes, sel(fm_t), sel(nr_t),
                                                             is_large_scale)
@@ -207,7 +212,7 @@ def _class_masks(class_ids, batch_size, device):
     ids = np.asarray(class_ids)
     m = (ids.reshape(-1, 1) == ids.reshape(1, -1)).astype(np.uint8)
     np.fill_diagonal(m, 0)
-    return torch.from_numpy(m[:batch_size, :batch_size].copy()).to(device)
+    return ops.h2d(m[:batch_size, :batch_size].copy(), device)
 
 
 def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8, top1=True, is_training=True):
@@ -236,7 +241,7 @@ def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size,
     if torch.is_tensor(cap_lens) and cap_lens.device == dev:
         lens_dev = cap_lens.to(torch.int64).contiguous()
     else:
-        lens_dev = torch.as_tensor([int(v) for v in cap_lens], dtype=torch.int64).to(dev, non_blocking=True)
+        lens_dev = ops.h2d([int(v) for v in cap_lens], dev, torch.int64)
     sim, attn = ops.words_pairs(img_features, words_emb.detach(), lens_dev[:batch_size], cfg.TRAIN.SMOOTH.GAMMA1,
                                 cfg.TRAIN.SMOOTH.GAMMA2)                     # sim[image, caption]
     diag = attn[torch.arange(batch_size, device=dev), torch.arange(batch_size, device=dev)] if need_att_maps else None
@@ -259,7 +264,7 @@ def _obj_g_term(netObjD, fake_img, seg, slabels_emb, raw_bt_c_codes, rois, num_r
     feats, classes, codes = feat_select(pooled, raw_bt_c_codes, rois, num_rois, is_large_scale)
     if len(classes) == 0:
         return None
-    idx = torch.as_tensor(classes, dtype=torch.int64, device=fake_img.device)
+    idx = ops.h2d([int(c) for c in classes], fake_img.device, torch.int64)
     conditions = ops.cat_rows(ops.gather_rows(slabels_emb.detach(), idx), codes)
     err = ops.bce(net.COND_DNET(feats, conditions), 1.0, 1.0)
     if net.UNCOND_DNET is not None:

@@ -629,7 +629,7 @@ class _ObjD(_Base):
         x_s = ops.cat_channels([x, new_s], [x_var.shape[1], self.ngf])
         code = self.img_code(x_s)                                           # NHWC (B, S/2^n, S/2^n, feat_dim)
         rois = _get_rois_blob(fm.reshape(b * fm.shape[1], fm.shape[2])[:, :4], np.array([1] * b * cfg.ROI.BOXES_NUM))
-        rois_t = torch.from_numpy(rois).to(x_var.device)
+        rois_t = ops.h2d(rois, x_var.device)
         # the feature map is channels-last already: the channels-last RoIAlignAvg kernel (same values as the
         # reference-ABI NCHW op behind self.RoIAlignAvg) feeds roi_code without any layout round trip
         pooled = ops.roi_align_avg_nhwc(code, rois_t, self.RoIAlignAvg.aligned_height, self.RoIAlignAvg.aligned_width,

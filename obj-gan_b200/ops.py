@@ -58,6 +58,13 @@ def bump_param_epoch():
     _param_epoch[0] += 1
 
 
+def _epoch_of(w):
+    """(global epoch, epoch of the network that owns w): a network's optimiser step only invalidates ITS operand
+    copies (a trainer attaches ``og_epoch`` = its bucket's counter to every parameter)."""
+    own = getattr(w, "og_epoch", None)
+    return (_param_epoch[0], own[0] if own is not None else 0)
+
+
 class PackedWeights:
     """Cache of kernel-native copies (fprop and dgrad operand) of one OIHW parameter."""
 
@@ -69,7 +76,7 @@ class PackedWeights:
         self.amax = None
 
     def _refresh(self, w, cip, kp, split):
-        key = (w.data_ptr(), w._version, _param_epoch[0], cip, kp, split)
+        key = (w.data_ptr(), w._version, _epoch_of(w), cip, kp, split)
         if key != self.key:
             self.key, self.f, self.t, self.hl, self.amax = key, None, None, {}, None
 
@@ -134,7 +141,13 @@ class PackPlan:
         self._n_built = 0
 
     def record(self, cache, w, cip, kp, split, splitp, transposed, hi, lo, amax):
-        self.jobs.append((cache, w, cip, kp, split, splitp, transposed, hi, lo, amax))
+        job = (cache, w, cip, kp, split, splitp, transposed, hi, lo, amax)
+        for i, j in enumerate(self.jobs):
+            if j[0] is cache and j[6] == transposed:      # same layer and layout packed again: new buffers
+                self.jobs[i] = job
+                self._tables = None
+                return
+        self.jobs.append(job)
 
     def _build(self, device):
         CH = 4096
@@ -149,7 +162,7 @@ class PackPlan:
             prows.append([w.data_ptr(), hi.data_ptr(), 0 if lo is None else lo.data_ptr(), amax.data_ptr(), co, ci,
                           kh * kw, cip, kp, split, splitp, tr, total, pb])
             pb += (total + CH - 1) // CH
-        mk = lambda rows: torch.tensor(rows, dtype=torch.int64).to(device)
+        mk = lambda rows: h2d(rows, device, torch.int64)
         self._tables = (mk(arows), len(arows), ab, mk(prows), len(prows), pb)
         self._n_built = len(self.jobs)
 
@@ -166,7 +179,7 @@ class PackPlan:
         for cache, w, cip, kp, split, splitp, tr, hi, lo, amax in self.jobs:
             if id(cache) not in touched:
                 touched[id(cache)] = cache
-                cache.key = (w.data_ptr(), w._version, _param_epoch[0], cip, kp, split)
+                cache.key = (w.data_ptr(), w._version, _epoch_of(w), cip, kp, split)
                 cache.f = cache.t = None
                 cache.hl = {}
                 cache.amax = amax
@@ -1164,6 +1177,36 @@ def expsumlog(s, gamma):
     return _ExpSumLog.apply(s, gamma)
 
 
+def h2d(data, device, dtype=None):
+    """Small host table (list / numpy array / CPU tensor) -> device WITHOUT stalling the host: staged in pinned memory
+    and copied asynchronously on the current stream (a pageable ``.to(device)`` blocks the calling thread until the GPU
+    has drained the stream, which serialises an eager step with its own kernels).  The caching pinned allocator only
+    reuses the staging block after the copy has executed."""
+    import numpy as np
+    if torch.is_tensor(data):
+        t = data if dtype is None else data.to(dtype)
+    elif isinstance(data, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(data))
+        t = t if dtype is None else t.to(dtype)
+    else:
+        t = torch.tensor(data, dtype=dtype)
+    dev = torch.device(device)
+    if dev.type != "cuda" or t.device.type == "cuda":
+        return t.to(dev)
+    return t.contiguous().pin_memory().to(dev, non_blocking=True)
+
+
+def permute_channels(x, perm):
+    """out[b, c] = x[b, perm[b, c]] for an NCHW tensor and a (B, C) int64 table on the device."""
+    _chk(x, perm)
+    x = x.detach().contiguous()
+    b, c, h, w = x.shape
+    assert perm.shape == (b, c) and perm.dtype == torch.int64
+    out = torch.empty_like(x)
+    _call("og_permute_channels", _p(x), _p(perm.contiguous()), b, c, h * w, _p(out))
+    return out
+
+
 def zeros(shape, device):
     """Zero-filled fp32 tensor through cudaMemsetAsync (a memset node inside a captured graph, no library kernel)."""
     t = torch.empty(shape, device=device, dtype=torch.float32)
@@ -1414,7 +1457,8 @@ def roi_align_avg_nhwc(features, rois, ah, aw, scale):
 
 
 # --------------------------------------------------------------------------------------------------
-def adam_ema_(p, g, m, v, avg, step, *, lr=2e-4, b1=0.5, b2=0.999, eps=1e-8, gscale=1.0, decay=0.999, step_dev=None):
+def adam_ema_(p, g, m, v, avg, step, *, lr=2e-4, b1=0.5, b2=0.999, eps=1e-8, gscale=1.0, decay=0.999, step_dev=None,
+              bump=True):
     """Fused Adam (+EMA) over flat fp32 buffers, in place.  ``step_dev`` (int64 device scalar) replaces the host
     step count and is incremented first, which keeps the call replayable from a CUDA graph."""
     _chk(p, g, m, v, avg, step_dev)
@@ -1422,4 +1466,5 @@ def adam_ema_(p, g, m, v, avg, step, *, lr=2e-4, b1=0.5, b2=0.999, eps=1e-8, gsc
         _call("og_inc_i64", _p(step_dev))
     _call("og_adam_ema", _p(p), _p(g), _p(m), _p(v), _p(avg), p.numel(), float(lr), float(b1), float(b2), float(eps),
           int(step), _p(step_dev), float(gscale), float(decay))
-    bump_param_epoch()
+    if bump:
+        bump_param_epoch()

@@ -52,8 +52,10 @@ class FlatBucket:
         self.avg = self.flat.clone() if ema else None
         self.offsets = offs
         self.plan = ops.PackPlan()           # fp16 operand copies of this network's conv weights: re-packed in one go
+        self.epoch = [0]                     # bumped by THIS network's optimiser step only (ops._epoch_of)
         for p in self.params:
             p.og_pack_plan = self.plan
+            p.og_epoch = self.epoch
         self.step = 0
         self.step_dev = torch.zeros((), device=dev, dtype=torch.int64)   # device mirror (CUDA-graph replay)
         ops.bump_param_epoch()
@@ -68,7 +70,8 @@ class FlatBucket:
     def adam(self, lr, gscale=1.0):
         self.step += 1
         ops.adam_ema_(self.flat, self.grad, self.m, self.v, self.avg, self.step, lr=lr, b1=0.5, b2=0.999, eps=1e-8,
-                      gscale=gscale, decay=0.999, step_dev=self.step_dev)
+                      gscale=gscale, decay=0.999, step_dev=self.step_dev, bump=False)
+        self.epoch[0] += 1
         if PACK_PLAN:
             self.plan.run()                   # every tensor-core operand copy of this network, two launches
 
