@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
   long long p = i / Co4;
   int c4i = (int)(i - p * Co4);
   long long g = p / P, pg = p - g * P;
+#pragma unroll 2
   for (; i < total; i += stride, p += dp, pg += dp, c4i += dc) {
     if (c4i >= Co4) { c4i -= Co4; ++p; ++pg; }
     while (pg >= P) { pg -= P; ++g; }
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __rest
   long long p = i / Co4;
   int c4i = (int)(i - p * Co4);
   long long grp = p / P, pg = p - grp * P;
+#pragma unroll 2
   for (; i < total; i += stride, p += dp, pg += dp, c4i += dc) {
     if (c4i >= Co4) { c4i -= Co4; ++p; ++pg; }
     while (pg >= P) { pg -= P; ++grp; }

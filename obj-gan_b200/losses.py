@@ -160,9 +160,11 @@ def objD_loss(netObjD, real_imgs, fake_imgs, seg_conditions, raw_conditions, raw
         idx = ops.h2d([int(c) for c in cls_idx], dev, torch.int64)
         return ops.cat_rows_const(ops.gather_rows(raw_conditions.detach(), idx), codes)
 
-    real_pooled = netObjD(real_imgs, seg_conditions, fm_rois, num_rois)
+    # the shape branch of the net sees the same segmentation map in the real and the fake pass: evaluate it once
+    shared = {"shape_features": net.shape_features(seg_conditions)} if hasattr(net, "shape_features") else {}
+    real_pooled = netObjD(real_imgs, seg_conditions, fm_rois, num_rois, **shared)
     real_features, classes, bt_c_codes = feat_select(real_pooled, raw_bt_c_codes, fm_rois, num_rois, is_large_scale)
-    fake_pooled = netObjD(fake_imgs.detach(), seg_conditions, fm_rois, num_rois)
+    fake_pooled = netObjD(fake_imgs.detach(), seg_conditions, fm_rois, num_rois, **shared)
     fake_features, _, _ = feat_select(fake_pooled, raw_bt_c_codes, fm_rois, num_rois, is_large_scale)
     fake_seg, valid = permute_seg(seg_conditions, fm_rois, num_rois)
     classes2 = []

@@ -617,15 +617,22 @@ class _ObjD(_Base):
         self.COND_DNET = D_GET_LOGITS(ndf // 2, nef, bcondition=True)
         self.ngf = ngf
 
-    def forward(self, x_var, s_var, fm_rois, num_rois, img_size=512):
+    def shape_features(self, s_var, img_size=512):
+        """The shape branch (ref: model.py:1217-1219: bilinear -> ReflPad + conv3x3 80->12 + bias -> InstanceNorm ->
+        LeakyReLU) of a segmentation map, NHWC.  It depends on the map and this net's weights only, so a loss that
+        runs the net on several images with the SAME map (objD_loss: real and fake) computes it once and passes it
+        to ``forward`` (autograd sums both uses' gradients): same values, one 80-channel 512^2 pass instead of two."""
+        s = ops.bilinear(ops.to_nhwc(s_var), img_size, img_size)
+        return ops.instance_norm_act(self.shp_code[1](s), NA_LRELU)
+
+    def forward(self, x_var, s_var, fm_rois, num_rois, img_size=512, shape_features=None):
         # (x, y, w, h) -> (x1, y1, x2, y2) on the host, on a COPY (the reference mutates a CPU caller's tensor in place,
         # ref: model.py:1213-1214; on CUDA it works on a copy too)
         fm = fm_rois.detach().cpu().numpy().astype(np.float64, copy=True)
         fm[:, :, [2, 3]] = fm[:, :, [0, 1]] + fm[:, :, [2, 3]]
         b = fm.shape[0]
         x = ops.bilinear(ops.to_nhwc(x_var), img_size, img_size)
-        s = ops.bilinear(ops.to_nhwc(s_var), img_size, img_size)
-        new_s = ops.instance_norm_act(self.shp_code[1](s), NA_LRELU)
+        new_s = shape_features if shape_features is not None else self.shape_features(s_var, img_size)
         x_s = ops.cat_channels([x, new_s], [x_var.shape[1], self.ngf])
         code = self.img_code(x_s)                                           # NHWC (B, S/2^n, S/2^n, feat_dim)
         rois = _get_rois_blob(fm.reshape(b * fm.shape[1], fm.shape[2])[:, :4], np.array([1] * b * cfg.ROI.BOXES_NUM))
