@@ -345,10 +345,19 @@ static int launch_att_reg(const float* h, const float* src, const unsigned char*
   OG_RETURN_LAST_ERROR();
 }
 
+// attention_tc.cu: the tcgen05 kernel for the large maps of the hot path; -1 = shape outside its envelope
+extern "C" int og_att_general_fwd_tc(const float* h, const float* src, const unsigned char* mask, int B, int Q, int idf,
+                                     int cs, int L, float* wc, float* attn, cudaStream_t stream);
+
 OG_API int og_att_general_fwd(const float* h, const float* src, const unsigned char* mask, int B, int Q, int idf,
                               int cs, int L, float* wc, float* attn, cudaStream_t stream) {
   if (L > LMAX || cs % 4 || idf > cs) return (int)cudaErrorInvalidValue;
   if (B == 0 || Q == 0) return 0;
+  static const int use_tc = getenv("OG_ATT_TC") ? atoi(getenv("OG_ATT_TC")) : 1;
+  if (use_tc && Q >= 4096) {
+    const int rc = og_att_general_fwd_tc(h, src, mask, B, Q, idf, cs, L, wc, attn, stream);
+    if (rc >= 0) return rc;
+  }
   // measured (B200, Q = 16384, B = 16): staged kernel below 49 us, this register-resident variant 61 us at QPT = 4 (its
   // row-strided 16-byte loads cost 32 L1 wavefronts each): kept selectable, not the default
   static const int reg_qpt = getenv("OG_ATT_QPT") ? atoi(getenv("OG_ATT_QPT")) : 0;

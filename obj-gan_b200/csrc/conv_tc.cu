@@ -1574,7 +1574,8 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
   while (TH * 2 <= OH && TW * TH * 2 <= TC_BM) TH *= 2;
   int TN = TC_BM / (TW * TH);
   // a tile must not straddle two space-to-depth phase blocks of the source (image index n + dn)
-  if (SN != N && (N % TN) != 0) return (int)cudaErrorInvalidValue;
+  // N need not be a multiple of TN: GEMM rows are independent, the last tile's rows n >= N are never stored (row_ok),
+  // whatever they read (zero fill past the tensor, or -- in a phase-stacked source -- images of the next phase block)
   p.TN = TN; p.TH = TH; p.TW = TW;
   p.bias = bias; p.act = act; p.slope = slope;
   p.tall = 0;
@@ -1745,11 +1746,12 @@ OG_API int og_conv2d_wgrad_tc(const void* gh, const void* gl, const unsigned* am
   int chh = 1;
   while (cw * chh * 2 <= WG_PIX && OH % (chh * 2) == 0) chh *= 2;
   const int cn = WG_PIX / (cw * chh);
-  if (N % cn != 0) return (int)cudaErrorInvalidValue;
+  // a last image group with n >= N contributes nothing as long as ONE operand is unstacked (TMA zero-fills it there)
+  if (N % cn != 0 && GN != N && XN != N) return (int)cudaErrorInvalidValue;
   p.cw = cw; p.chh = chh; p.cn = cn;
   p.wchunks = OW / cw;
   p.hchunks = OH / chh;
-  p.total_chunks = p.wchunks * p.hchunks * (N / cn);
+  p.total_chunks = p.wchunks * p.hchunks * og_cdiv(N, cn);
   p.Kp = Kp; p.C = C; p.nsplit = nsplit; p.dw = dw;
   p.amax_g = amax_g; p.amax_x = amax_x;
   for (int i = 0; i < nentries; ++i) {

@@ -15,6 +15,9 @@
 #include "common.cuh"
 
 // grid: (ceil(C4/32), chunks, groups)   block: (32, 8)
+// A thread owns one channel quad and walks the rows p0 + ty, p0 + ty + 8, ...: four rows are loaded back to back (four
+// 16-byte loads in flight), summed pairwise in fp32 (<= 2 roundings: ~1e-7 relative, random) and only the 4-row partial
+// enters the fp64 accumulators -- a quarter of the F2F / DADD / DFMA issue slots of per-element fp64.
 __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ x, int C, long long P,
                                                          int pix_per_block, double* __restrict__ stats) {
   const int c4 = blockIdx.x * 32 + threadIdx.x;
@@ -25,7 +28,16 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict
   double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   if (c4 < C4) {
     const float* base = x + (g * P) * C + c4 * 4;
-    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+    long long p = p0 + threadIdx.y;
+    for (; p + 24 < p1; p += 32) {
+      const float4 a = ldg4(base + p * C), b = ldg4(base + (p + 8) * C);
+      const float4 c = ldg4(base + (p + 16) * C), d = ldg4(base + (p + 24) * C);
+      s[0] += (double)((a.x + b.x) + (c.x + d.x)); q[0] += (double)((a.x * a.x + b.x * b.x) + (c.x * c.x + d.x * d.x));
+      s[1] += (double)((a.y + b.y) + (c.y + d.y)); q[1] += (double)((a.y * a.y + b.y * b.y) + (c.y * c.y + d.y * d.y));
+      s[2] += (double)((a.z + b.z) + (c.z + d.z)); q[2] += (double)((a.z * a.z + b.z * b.z) + (c.z * c.z + d.z * d.z));
+      s[3] += (double)((a.w + b.w) + (c.w + d.w)); q[3] += (double)((a.w * a.w + b.w * b.w) + (c.w * c.w + d.w * d.w));
+    }
+    for (; p < p1; p += 8) {
       float4 v = ldg4(base + p * C);
       s[0] += v.x; q[0] += (double)v.x * v.x;
       s[1] += v.y; q[1] += (double)v.y * v.y;
@@ -82,17 +94,26 @@ __device__ __forceinline__ float amax4(float m, const float4& o) {
 }
 __device__ __forceinline__ void block_amax_256(float m, unsigned* amax) {
   __shared__ float sm_amax[8];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;       // 256 threads as (256) or (32, 8)
   m = warp_max(m);
-  if ((threadIdx.x & 31) == 0) sm_amax[threadIdx.x >> 5] = m;
+  if ((tid & 31) == 0) sm_amax[tid >> 5] = m;
   __syncthreads();
-  if (threadIdx.x < 8) {
-    m = sm_amax[threadIdx.x];
+  if (tid < 8) {
+    m = sm_amax[tid];
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
-    if (threadIdx.x == 0) atomicMax(amax, __float_as_uint(m));
+    if (tid == 0) atomicMax(amax, __float_as_uint(m));
   }
 }
 
+// sigmoid on the SFU: ex2.approx + rcp.approx (~2 ulp; the libm expf + IEEE division it replaces made the GLU passes
+// issue bound at half of the HBM bandwidth).  exp(-x) overflowing to +inf gives exactly 0.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// Flat grid-stride walk over (pixel, channel quad): every lane of every warp carries a 16-byte load, which measured
+// 0.92 of the copy bandwidth for the plain / LeakyReLU / residual forms (the channel-fixed mapping of the backward
+// kernels below, with its idle lanes when C/4 is not a multiple of 32, measured 0.74 here).  The (pixel, quad, group)
+// indices advance incrementally: no division per element.
 template <int ACT>
 __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict__ y, int Cy, long long P,
                                                          long long total_pix, const float* __restrict__ mean,
@@ -113,7 +134,6 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
   long long p = i / Co4;
   int c4i = (int)(i - p * Co4);
   long long g = p / P, pg = p - g * P;
-#pragma unroll 2
   for (; i < total; i += stride, p += dp, pg += dp, c4i += dc) {
     if (c4i >= Co4) { c4i -= Co4; ++p; ++pg; }
     while (pg >= P) { pg -= P; ++g; }
@@ -135,10 +155,10 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
       float4 m2 = ldg4(mrow + Co + c), r2 = ldg4(rrow + Co + c);
       float4 ga2 = gamma ? ldg4(gamma + Co + c) : make_float4(1.f, 1.f, 1.f, 1.f);
       float4 be2 = beta ? ldg4(beta + Co + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      o.x = a.x * og_sigmoid((v2.x - m2.x) * r2.x * ga2.x + be2.x);
-      o.y = a.y * og_sigmoid((v2.y - m2.y) * r2.y * ga2.y + be2.y);
-      o.z = a.z * og_sigmoid((v2.z - m2.z) * r2.z * ga2.z + be2.z);
-      o.w = a.w * og_sigmoid((v2.w - m2.w) * r2.w * ga2.w + be2.w);
+      o.x = a.x * sigmoid_fast((v2.x - m2.x) * r2.x * ga2.x + be2.x);
+      o.y = a.y * sigmoid_fast((v2.y - m2.y) * r2.y * ga2.y + be2.y);
+      o.z = a.z * sigmoid_fast((v2.z - m2.z) * r2.z * ga2.z + be2.z);
+      o.w = a.w * sigmoid_fast((v2.w - m2.w) * r2.w * ga2.w + be2.w);
     } else if (ACT == OG_NA_LRELU) {
       o.x = a.x > 0.f ? a.x : a.x * slope;
       o.y = a.y > 0.f ? a.y : a.y * slope;
@@ -157,30 +177,39 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
   if (amax) block_amax_256(mx, amax);
 }
 
-// gradient of the fused activation w.r.t. the normalised (+affine) values n, for 4 channels.
-// Returns dn for the "a" half (and dn2 for the gate half when GLU).
+// Per-thread constants of the backward passes: statistics and affine parameters of the thread's channel quad (and of
+// the gate quad Co channels further for GLU), loaded once.
+struct ChanConst {
+  float4 m, r, ga, be, m2, r2, ga2, be2;
+};
 template <int ACT>
-__device__ __forceinline__ void act_grad4(const float* __restrict__ y, const float* __restrict__ g, long long p,
-                                          int Cy, int c, const float* mrow, const float* rrow,
+__device__ __forceinline__ void load_chan(ChanConst& k, const float* __restrict__ mean, const float* __restrict__ rstd,
                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                          float slope, float4& xh, float4& dn, float4& xh2, float4& dn2) {
-  const int Co = (ACT == OG_NA_GLU) ? Cy / 2 : Cy;
-  float4 v = ldg4(y + p * Cy + c);
-  float4 m = ldg4(mrow + c), r = ldg4(rrow + c);
-  float4 go = ldg4(g + p * Co + c);
-  xh.x = (v.x - m.x) * r.x; xh.y = (v.y - m.y) * r.y; xh.z = (v.z - m.z) * r.z; xh.w = (v.w - m.w) * r.w;
-  float4 ga = gamma ? ldg4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
-  float4 be = beta ? ldg4(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 n;
-  n.x = xh.x * ga.x + be.x; n.y = xh.y * ga.y + be.y; n.z = xh.z * ga.z + be.z; n.w = xh.w * ga.w + be.w;
+                                          long long grp, int Cy, int Co, int c) {
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  k.m = ldg4(mean + grp * Cy + c); k.r = ldg4(rstd + grp * Cy + c);
+  k.ga = gamma ? ldg4(gamma + c) : one; k.be = beta ? ldg4(beta + c) : zero;
+  k.m2 = zero; k.r2 = one; k.ga2 = one; k.be2 = zero;
   if (ACT == OG_NA_GLU) {
-    float4 v2 = ldg4(y + p * Cy + Co + c);
-    float4 m2 = ldg4(mrow + Co + c), r2 = ldg4(rrow + Co + c);
-    xh2.x = (v2.x - m2.x) * r2.x; xh2.y = (v2.y - m2.y) * r2.y; xh2.z = (v2.z - m2.z) * r2.z; xh2.w = (v2.w - m2.w) * r2.w;
-    float4 ga2 = gamma ? ldg4(gamma + Co + c) : make_float4(1.f, 1.f, 1.f, 1.f);
-    float4 be2 = beta ? ldg4(beta + Co + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float sx = og_sigmoid(xh2.x * ga2.x + be2.x), sy = og_sigmoid(xh2.y * ga2.y + be2.y);
-    float sz = og_sigmoid(xh2.z * ga2.z + be2.z), sw = og_sigmoid(xh2.w * ga2.w + be2.w);
+    k.m2 = ldg4(mean + grp * Cy + Co + c); k.r2 = ldg4(rstd + grp * Cy + Co + c);
+    if (gamma) k.ga2 = ldg4(gamma + Co + c);
+    if (beta) k.be2 = ldg4(beta + Co + c);
+  }
+}
+
+// gradient of the fused activation w.r.t. the normalised (+affine) values n, for 4 channels: v / v2 = the conv outputs
+// of the "a" and gate quads, go = the incoming gradient.  Returns xhat and dn for the "a" half (and the gate half's).
+template <int ACT>
+__device__ __forceinline__ void act_grad4(const ChanConst& k, const float4& v, const float4& v2, const float4& go,
+                                          float slope, float4& xh, float4& dn, float4& xh2, float4& dn2) {
+  xh.x = (v.x - k.m.x) * k.r.x; xh.y = (v.y - k.m.y) * k.r.y; xh.z = (v.z - k.m.z) * k.r.z; xh.w = (v.w - k.m.w) * k.r.w;
+  float4 n;
+  n.x = xh.x * k.ga.x + k.be.x; n.y = xh.y * k.ga.y + k.be.y; n.z = xh.z * k.ga.z + k.be.z; n.w = xh.w * k.ga.w + k.be.w;
+  if (ACT == OG_NA_GLU) {
+    xh2.x = (v2.x - k.m2.x) * k.r2.x; xh2.y = (v2.y - k.m2.y) * k.r2.y;
+    xh2.z = (v2.z - k.m2.z) * k.r2.z; xh2.w = (v2.w - k.m2.w) * k.r2.w;
+    const float sx = sigmoid_fast(xh2.x * k.ga2.x + k.be2.x), sy = sigmoid_fast(xh2.y * k.ga2.y + k.be2.y);
+    const float sz = sigmoid_fast(xh2.z * k.ga2.z + k.be2.z), sw = sigmoid_fast(xh2.w * k.ga2.w + k.be2.w);
     dn.x = go.x * sx; dn.y = go.y * sy; dn.z = go.z * sz; dn.w = go.w * sw;
     dn2.x = go.x * n.x * sx * (1.f - sx); dn2.y = go.y * n.y * sy * (1.f - sy);
     dn2.z = go.z * n.z * sz * (1.f - sz); dn2.w = go.w * n.w * sw * (1.f - sw);
@@ -193,7 +222,8 @@ __device__ __forceinline__ void act_grad4(const float* __restrict__ y, const flo
 }
 
 // backward reduce: per (group, channel of y):  bstats[.,0] = sum dn,  bstats[.,1] = sum dn * xhat   (fp64)
-// grid: (ceil(Co4/32), chunks, groups)  block (32, 8)
+// grid: (ceil(Co4/32), chunks, groups)  block (32, 8).  Two rows per trip: their contributions are added in fp32 and the
+// pair enters the fp64 accumulators (half of the fp64 issue slots; the pair sum costs one fp32 rounding).
 template <int ACT>
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __restrict__ y,
                                                               const float* __restrict__ g, int Cy, long long P,
@@ -213,11 +243,37 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0;
   if (c4 < Co4) {
-    const float* mrow = mean + grp * Cy;
-    const float* rrow = rstd + grp * Cy;
-    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+    const int c = c4 * 4;
+    ChanConst k;
+    load_chan<ACT>(k, mean, rstd, gamma, beta, grp, Cy, Co, c);
+    const float* yb = y + (grp * P) * Cy + c;
+    const float* gb = g + (grp * P) * Co + c;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long p = p0 + threadIdx.y;
+    for (; p + 8 < p1; p += 16) {
+      const float4 va = ldg4(yb + p * Cy), vb = ldg4(yb + (p + 8) * Cy);
+      const float4 ga_ = ldg4(gb + p * Co), gb_ = ldg4(gb + (p + 8) * Co);
+      float4 v2a = zero, v2b = zero;
+      if (ACT == OG_NA_GLU) { v2a = ldg4(yb + p * Cy + Co); v2b = ldg4(yb + (p + 8) * Cy + Co); }
+      float4 xa, da, x2a, d2a, xb, db, x2b, d2b;
+      act_grad4<ACT>(k, va, v2a, ga_, slope, xa, da, x2a, d2a);
+      act_grad4<ACT>(k, vb, v2b, gb_, slope, xb, db, x2b, d2b);
+      acc[0] += (double)(da.x + db.x); acc[1] += (double)(da.y + db.y);
+      acc[2] += (double)(da.z + db.z); acc[3] += (double)(da.w + db.w);
+      acc[4] += (double)(da.x * xa.x + db.x * xb.x); acc[5] += (double)(da.y * xa.y + db.y * xb.y);
+      acc[6] += (double)(da.z * xa.z + db.z * xb.z); acc[7] += (double)(da.w * xa.w + db.w * xb.w);
+      if (ACT == OG_NA_GLU) {
+        acc[NV - 8] += (double)(d2a.x + d2b.x); acc[NV - 7] += (double)(d2a.y + d2b.y);
+        acc[NV - 6] += (double)(d2a.z + d2b.z); acc[NV - 5] += (double)(d2a.w + d2b.w);
+        acc[NV - 4] += (double)(d2a.x * x2a.x + d2b.x * x2b.x); acc[NV - 3] += (double)(d2a.y * x2a.y + d2b.y * x2b.y);
+        acc[NV - 2] += (double)(d2a.z * x2a.z + d2b.z * x2b.z); acc[NV - 1] += (double)(d2a.w * x2a.w + d2b.w * x2b.w);
+      }
+    }
+    for (; p < p1; p += 8) {
+      const float4 v = ldg4(yb + p * Cy), go = ldg4(gb + p * Co);
+      const float4 v2 = (ACT == OG_NA_GLU) ? ldg4(yb + p * Cy + Co) : zero;
       float4 xh, dn, xh2, dn2;
-      act_grad4<ACT>(y, g, grp * P + p, Cy, c4 * 4, mrow, rrow, gamma, beta, slope, xh, dn, xh2, dn2);
+      act_grad4<ACT>(k, v, v2, go, slope, xh, dn, xh2, dn2);
       acc[0] += dn.x; acc[1] += dn.y; acc[2] += dn.z; acc[3] += dn.w;
       acc[4] += (double)dn.x * xh.x; acc[5] += (double)dn.y * xh.y;
       acc[6] += (double)dn.z * xh.z; acc[7] += (double)dn.w * xh.w;
@@ -248,67 +304,66 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
   }
 }
 
-// backward apply: dy = rstd * gamma * (dn - S1/cnt - xhat * S2/cnt)
+// backward apply: dy = rstd * gamma * (dn - S1/cnt - xhat * S2/cnt).  Same thread mapping as the forward apply: the
+// channel quad's statistics, affine parameters and the two reduction coefficients per channel stay in registers.
 template <int ACT>
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __restrict__ y,
                                                              const float* __restrict__ g, int Cy, long long P,
-                                                             long long total_pix, const float* __restrict__ mean,
+                                                             int pix_per_block, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float slope,
-                                                             const double* __restrict__ bstats, double inv_count,
+                                                             const double* __restrict__ bstats,
                                                              float* __restrict__ dy, unsigned* __restrict__ amax) {
   const int Co = (ACT == OG_NA_GLU) ? Cy / 2 : Cy;
   const int Co4 = Co >> 2;
-  const long long total = total_pix * Co4;
+  const int c4 = blockIdx.x * 32 + threadIdx.x;
+  const long long grp = blockIdx.z;
+  const long long p0 = (long long)blockIdx.y * pix_per_block;
+  const long long p1 = min(P, p0 + pix_per_block);
   float mx = 0.f;
-  (void)inv_count;
-  // coef[(grp * Cy + ch) * 4 + {0, 1}] = (float)(S1 / count), (float)(S2 / count): written over the fp64 sums by
-  // norm_bwd_coef_kernel (same float values the per-element double products gave)
-  const float* coef = reinterpret_cast<const float*>(bstats);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long dp = stride / Co4;
-  const int dc = (int)(stride - dp * Co4);
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long p = i / Co4;
-  int c4i = (int)(i - p * Co4);
-  long long grp = p / P, pg = p - grp * P;
-#pragma unroll 2
-  for (; i < total; i += stride, p += dp, pg += dp, c4i += dc) {
-    if (c4i >= Co4) { c4i -= Co4; ++p; ++pg; }
-    while (pg >= P) { pg -= P; ++grp; }
-    const int c = c4i * 4;
-    const float* mrow = mean + grp * Cy;
-    const float* rrow = rstd + grp * Cy;
-    float4 xh, dn, xh2, dn2;
-    act_grad4<ACT>(y, g, p, Cy, c, mrow, rrow, gamma, beta, slope, xh, dn, xh2, dn2);
-    {
-      const float* bs = coef + (grp * Cy + c) * 4;
-      const float2 k0 = *reinterpret_cast<const float2*>(bs), k1 = *reinterpret_cast<const float2*>(bs + 4);
-      const float2 k2 = *reinterpret_cast<const float2*>(bs + 8), k3 = *reinterpret_cast<const float2*>(bs + 12);
-      float4 r = ldg4(rrow + c);
-      float4 ga = gamma ? ldg4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
-      float4 o;
-      o.x = r.x * ga.x * (dn.x - k0.x - xh.x * k0.y);
-      o.y = r.y * ga.y * (dn.y - k1.x - xh.y * k1.y);
-      o.z = r.z * ga.z * (dn.z - k2.x - xh.z * k2.y);
-      o.w = r.w * ga.w * (dn.w - k3.x - xh.w * k3.y);
-      st4(dy + p * Cy + c, o);
-      mx = amax4(mx, o);
-    }
+  if (c4 < Co4) {
+    const int c = c4 * 4;
+    ChanConst k;
+    load_chan<ACT>(k, mean, rstd, gamma, beta, grp, Cy, Co, c);
+    // coef[(grp * Cy + ch) * 4 + {0, 1}] = (float)(S1 / count), (float)(S2 / count): written over the fp64 sums by
+    // norm_bwd_coef_kernel (same float values the per-element double products gave)
+    const float* coef = reinterpret_cast<const float*>(bstats);
+    const float* bs = coef + (grp * Cy + c) * 4;
+    const float2 k0 = *reinterpret_cast<const float2*>(bs), k1 = *reinterpret_cast<const float2*>(bs + 4);
+    const float2 k2 = *reinterpret_cast<const float2*>(bs + 8), k3 = *reinterpret_cast<const float2*>(bs + 12);
+    float2 j0 = make_float2(0.f, 0.f), j1 = j0, j2 = j0, j3 = j0;
     if (ACT == OG_NA_GLU) {
-      const float* bs = coef + (grp * Cy + Co + c) * 4;
-      const float2 k0 = *reinterpret_cast<const float2*>(bs), k1 = *reinterpret_cast<const float2*>(bs + 4);
-      const float2 k2 = *reinterpret_cast<const float2*>(bs + 8), k3 = *reinterpret_cast<const float2*>(bs + 12);
-      float4 r = ldg4(rrow + Co + c);
-      float4 ga = gamma ? ldg4(gamma + Co + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float* bs2 = coef + (grp * Cy + Co + c) * 4;
+      j0 = *reinterpret_cast<const float2*>(bs2); j1 = *reinterpret_cast<const float2*>(bs2 + 4);
+      j2 = *reinterpret_cast<const float2*>(bs2 + 8); j3 = *reinterpret_cast<const float2*>(bs2 + 12);
+    }
+    const float* yb = y + (grp * P) * Cy + c;
+    const float* gb = g + (grp * P) * Co + c;
+    float* db = dy + (grp * P) * Cy + c;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll(ACT == OG_NA_GLU ? 2 : 4)
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+      const float4 v = ldg4(yb + p * Cy), go = ldg4(gb + p * Co);
+      const float4 v2 = (ACT == OG_NA_GLU) ? ldg4(yb + p * Cy + Co) : zero;
+      float4 xh, dn, xh2, dn2;
+      act_grad4<ACT>(k, v, v2, go, slope, xh, dn, xh2, dn2);
       float4 o;
-      o.x = r.x * ga.x * (dn2.x - k0.x - xh2.x * k0.y);
-      o.y = r.y * ga.y * (dn2.y - k1.x - xh2.y * k1.y);
-      o.z = r.z * ga.z * (dn2.z - k2.x - xh2.z * k2.y);
-      o.w = r.w * ga.w * (dn2.w - k3.x - xh2.w * k3.y);
-      st4(dy + p * Cy + Co + c, o);
+      o.x = k.r.x * k.ga.x * (dn.x - k0.x - xh.x * k0.y);
+      o.y = k.r.y * k.ga.y * (dn.y - k1.x - xh.y * k1.y);
+      o.z = k.r.z * k.ga.z * (dn.z - k2.x - xh.z * k2.y);
+      o.w = k.r.w * k.ga.w * (dn.w - k3.x - xh.w * k3.y);
+      st4(db + p * Cy, o);
       mx = amax4(mx, o);
+      if (ACT == OG_NA_GLU) {
+        float4 o2;
+        o2.x = k.r2.x * k.ga2.x * (dn2.x - j0.x - xh2.x * j0.y);
+        o2.y = k.r2.y * k.ga2.y * (dn2.y - j1.x - xh2.y * j1.y);
+        o2.z = k.r2.z * k.ga2.z * (dn2.z - j2.x - xh2.z * j2.y);
+        o2.w = k.r2.w * k.ga2.w * (dn2.w - j3.x - xh2.w * j3.y);
+        st4(db + p * Cy + Co, o2);
+        mx = amax4(mx, o2);
+      }
     }
   }
   if (amax) block_amax_256(mx, amax);
@@ -386,7 +441,6 @@ OG_API int og_norm_backward(const float* y, const float* g, int groups, long lon
                             const float* rstd, const float* gamma, const float* beta, int act, float slope,
                             double* bstats, float* dy, float* dgamma, float* dbeta, int accumulate_param_grads,
                             unsigned* amax_dy, cudaStream_t stream) {
-  long long tp = (long long)groups * P;
   int Co = act == OG_NA_GLU ? Cy / 2 : Cy;
   if (Cy % 4 || Co % 4) return (int)cudaErrorInvalidValue;
   OG_CHECK(cudaMemsetAsync(bstats, 0, sizeof(double) * 2 * groups * Cy, stream));
@@ -394,14 +448,13 @@ OG_API int og_norm_backward(const float* y, const float* g, int groups, long lon
   int cg = og_cdiv(Co / 4, 32);
   int ppb = pix_chunk(P, cg, groups);
   dim3 grid(cg, og_cdiv(P, ppb), groups), block(32, 8);
-  int blocks = elem_blocks(tp * (Co / 4));
   double inv = 1.0 / (double)P;
 #define OG_LAUNCH_BWD(A)                                                                                           \
   norm_bwd_reduce_kernel<A><<<grid, block, 0, stream>>>(y, g, Cy, P, ppb, mean, rstd, gamma, beta, slope, bstats); \
   if (dgamma && groups == 1)                                                                                       \
     norm_param_grad_kernel<<<og_cdiv(Cy, 256), 256, 0, stream>>>(bstats, Cy, dgamma, dbeta, accumulate_param_grads); \
   norm_bwd_coef_kernel<<<og_cdiv((long long)groups * Cy, 256), 256, 0, stream>>>(bstats, (long long)groups * Cy, inv); \
-  norm_bwd_apply_kernel<A><<<blocks, 256, 0, stream>>>(y, g, Cy, P, tp, mean, rstd, gamma, beta, slope, bstats, inv, dy, amax_dy);
+  norm_bwd_apply_kernel<A><<<grid, block, 0, stream>>>(y, g, Cy, P, ppb, mean, rstd, gamma, beta, slope, bstats, dy, amax_dy);
   if (act == OG_NA_GLU) {
     OG_LAUNCH_BWD(OG_NA_GLU)
   } else if (act == OG_NA_LRELU) {

@@ -272,18 +272,18 @@ def _tile_n(oh, ow):
 
 
 def _tc_kind(n, h, w, c, kh, kw, stride, pad, mode):
-    """Which tensor-core formulation (if any) applies to this convolution."""
+    """Which tensor-core formulation (if any) applies to this convolution.  The batch need not fill the last pixel
+    tile: GEMM rows are independent and rows past the batch are never stored."""
     if CONV_ENGINE not in ("f16x3", "f16") or _lib.DRY_RUN:
         return None
-    if kh == 3 and kw == 3 and stride == 1 and pad == 1:
-        oh, ow = (2 * h, 2 * w) if mode == UPSAMPLE2X else (h, w)
+    if kh == kw and stride == 1 and pad == 1 and (kh == 3 or (kh == 4 and mode == PAD_ZERO)):
+        # 3x3 (any padding mode), and the 4x4 stride-1 zero-padded roi_code layer of the object discriminators
+        oh, ow = _out_hw(h, w, kh, kw, stride, pad, mode)
         if n * oh * ow < TC_MIN_PIXELS:
-            return None
-        if mode == UPSAMPLE2X and n % _tile_n(h, w) != 0:
             return None
         return "s1"
     if kh == kw and kh in (3, 4) and stride == 2 and pad == 1 and mode == PAD_ZERO and h % 2 == 0 and w % 2 == 0:
-        if n * (h // 2) * (w // 2) < TC_MIN_PIXELS or n % _tile_n(h // 2, w // 2) != 0:
+        if n * (h // 2) * (w // 2) < TC_MIN_PIXELS:
             return None
         return "s2"
     return None
@@ -316,10 +316,15 @@ def _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act):
         taps = [(kh, kw, 0, kh * 3 + kw) for kw in range(3) for kh in range(3)]      # column by column (layout 1)
         _tc_launch(xs, n, ws, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act, layout=1)
     elif mode == PAD_ZERO:
+        k = weight.shape[2]
         xs = _split(x, 0)
-        y = torch.empty((n, h, w, kp), device=dev, dtype=torch.float32)
-        taps = [(kh - 1, kw - 1, 0, kh * 3 + kw) for kw in range(3) for kh in range(3)]
-        _tc_launch(xs, n, ws, 9, kp, y, h, w, kp, 1, (0, 0), taps, bias_p, act, layout=1)
+        oh, ow = h + 3 - k, w + 3 - k
+        y = torch.empty((n, oh, ow, kp), device=dev, dtype=torch.float32)
+        if k == 3:
+            taps = [(kh - 1, kw - 1, 0, kh * 3 + kw) for kw in range(3) for kh in range(3)]
+        else:
+            taps = [(kh - 1, kw - 1, 0, kh * k + kw) for kh in range(k) for kw in range(k)]
+        _tc_launch(xs, n, ws, k * k, kp, y, oh, ow, kp, 1, (0, 0), taps, bias_p, act, layout=1 if k == 3 else 0)
     else:  # UPSAMPLE2X: four output phases of 2x2 taps at low resolution, weights pre-summed per phase
         ws = cache.get_up_hilo(weight, c, kp, split, splitp, 1)
         xs = _split(x, 0)
@@ -366,9 +371,13 @@ def _tc_dgrad(kind, gs, n, cache, weight, c, kp, split, splitp, mode, h, w, oh, 
         _call("og_reflect_pad_bwd", _p(gpad), n, h, w, c, _p(gx))
         return gx
     if mode == PAD_ZERO:
+        k = weight.shape[2]
         gx = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
-        taps = [(1 - kh, 1 - kw, 0, kh * 3 + kw) for kw in range(3) for kh in (2, 1, 0)]
-        _tc_launch(gs, n, ws, 9, c, gx, h, w, c, 1, (0, 0), taps, layout=1)
+        if k == 3:
+            taps = [(1 - kh, 1 - kw, 0, kh * 3 + kw) for kw in range(3) for kh in (2, 1, 0)]
+        else:       # gx[i, j] = sum g[i + 1 - kh, j + 1 - kw] W[kh, kw]^T over the (oh, ow) gradient grid
+            taps = [(1 - kh, 1 - kw, 0, kh * k + kw) for kh in range(k) for kw in range(k)]
+        _tc_launch(gs, n, ws, k * k, c, gx, h, w, c, 1, (0, 0), taps, layout=1 if k == 3 else 0)
         return gx
     # UPSAMPLE2X: adjoint of the four phase convolutions: gx[i,j] = sum_{p,q,a,b} G_pq[i - off(p,a), j - off(q,b)] Wp^T
     ws = cache.get_up_hilo(weight, c, kp, split, splitp, 0)
@@ -389,7 +398,8 @@ def _tc_wgrad_ok(kind, mode, n, oh, ow):
     chh = 1
     while cw * chh * 2 <= 64 and oh % (chh * 2) == 0:
         chh *= 2
-    return n % (64 // (cw * chh)) == 0
+    # a last image group that the batch does not fill adds nothing (the unstacked operand is zero filled there)
+    return True
 
 
 def _grad_sink(param):
@@ -422,8 +432,8 @@ def _tc_wgrad(kind, xs, gs, n, h, w, oh, ow, weight, c, kp, split, splitp, mode,
         oh, ow, nt = h, w, 16
     else:
         off = 0 if mode == PAD_REFLECT else -1     # reflect: x copy carries the halo; zero pad: TMA fills
-        ent = [(0, kh + off, kw + off, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
-        nt = 9
+        ent = [(0, kh + off, kw + off, 0, kh * kw_ + kw) for kh in range(kh_) for kw in range(kw_)]
+        nt = kh_ * kw_
     arr = _int_array(ent)
     dwp = torch.empty(nt * kp * c, device=xh.device, dtype=torch.float32)
     _call("og_conv2d_wgrad_tc", _p(gh), _p(gl), _p(ag), n, gh.shape[0], oh, ow, kp, _p(xh), _p(xl), _p(ax),

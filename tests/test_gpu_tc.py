@@ -31,12 +31,19 @@ CASES = [
     (768, 1536, "s2", 0, 32, 8, 8),              # 4x4 outputs: wgrad pixel patch spans 2 images
     (40, 24, PAD_REFLECT, 0, 4, 16, 16),         # reflection halo on a 16-wide map (wgrad patch = 16 x 2)
     (24, 48, "s2k3", 0, 4, 64, 64),              # conv3x3 stride 2 (heat-map encoder) through the same phase blocks
+    (384, 384, "k4s1", 0, 130, 5, 5),            # roi_code of the object discriminators: 4x4 stride 1 pad 1 on 5x5 pooled rois
+    (384, 384, "k4s1", 0, 70, 5, 5),             # ... roi count that does not fill the last pixel tile / wgrad image group
+    (192, 384, "s2", 0, 13, 16, 16),             # sub-batch of the permuted-shape pass: 13 images, tiles span 2 images
+    (384, 768, "s2", 0, 11, 8, 8),               # ... 4x4 outputs, 8 images per tile
+    (96, 48, UPSAMPLE2X, 24, 3, 8, 8),           # upsample phases with a batch that does not fill the 2-image tile
 ]
 
 
 def _ref(x, w, mode):
     if mode in ("s2", "s2k3"):
         return F.conv2d(x, w, None, 2, 1)
+    if mode == "k4s1":
+        return F.conv2d(x, w, None, 1, 1)
     if mode == PAD_REFLECT:
         return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w)
     if mode == UPSAMPLE2X:
@@ -58,6 +65,8 @@ def test_tc_conv_fwd_dgrad(case, engine, tol, monkeypatch):
     torch.manual_seed(cin + cout + H)
     if mode in ("s2", "s2k3"):
         m = model.Conv2dP(cin, cout, 4 if mode == "s2" else 3, 2, 1).to(DEV)
+    elif mode == "k4s1":
+        m = model.Conv2dP(cin, cout, 4, 1, 1).to(DEV)
     else:
         m = model.Conv2dP(cin, cout, 3, 1, 1, mode=mode, split=split).to(DEV)
     x = torch.randn(N, cin, H, W)
@@ -68,8 +77,8 @@ def test_tc_conv_fwd_dgrad(case, engine, tol, monkeypatch):
     gy = torch.randn_like(yr)
     gxr, gwr = torch.autograd.grad(yr, (xr, wr), gy)
     xg = x.to(DEV).requires_grad_(True)
-    k, st = (4, 2) if mode == "s2" else (3, 2) if mode == "s2k3" else (3, 1)
-    assert ops._tc_kind(N, H, W, ops.cpad(cin), k, k, st, 1, PAD_ZERO if st == 2 else mode)
+    k, st = (4, 2) if mode == "s2" else (3, 2) if mode == "s2k3" else (4, 1) if mode == "k4s1" else (3, 1)
+    assert ops._tc_kind(N, H, W, ops.cpad(cin), k, k, st, 1, PAD_ZERO if (st == 2 or mode == "k4s1") else mode)
     y_nhwc = m(ops.to_nhwc(xg))
     if split:
         sp = ops.cpad(split)
