@@ -127,16 +127,36 @@ __device__ __forceinline__ uint32_t at_sw_off(int r, int k) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2);
 }
 
-// a = a1 + a2 + a3 (three bf16 terms, 24 mantissa bits); returns the raw 16-bit patterns
-__device__ __forceinline__ void at_split3(float v, unsigned short& a1, unsigned short& a2, unsigned short& a3) {
-  const __nv_bfloat16 h1 = __float2bfloat16_rn(v);
-  float r = v - __bfloat162float(h1);
-  const __nv_bfloat16 h2 = __float2bfloat16_rn(r);
-  r -= __bfloat162float(h2);
-  const __nv_bfloat16 h3 = __float2bfloat16_rn(r);
-  a1 = __bfloat16_as_ushort(h1); a2 = __bfloat16_as_ushort(h2); a3 = __bfloat16_as_ushort(h3);
+// a = a1 + a2 + a3 EXACTLY: a1 = the top 16 bits of the fp32 pattern (a bf16 by truncation), a2 = the top 16 bits of the
+// exact residual, a3 = what is left (<= 8 significant bits: a bf16 as it stands).  Pure LOP3 / FADD work -- the rounding
+// conversions (F2F) this replaces are quarter-rate instructions and dominated the first version of this kernel.
+struct Split3 { uint32_t w1, w2, w3; };      // fp32 bit patterns whose HIGH halves are the three bf16 terms
+__device__ __forceinline__ Split3 at_split3(float v) {
+  Split3 s;
+  s.w1 = __float_as_uint(v) & 0xFFFF0000u;
+  const float r1 = v - __uint_as_float(s.w1);
+  s.w2 = __float_as_uint(r1) & 0xFFFF0000u;
+  s.w3 = __float_as_uint(r1 - __uint_as_float(s.w2));
+  return s;
 }
-__device__ __forceinline__ uint32_t at_pack(unsigned short lo, unsigned short hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
+// {high half of lo_word, high half of hi_word} -> one 32-bit pair of bf16 (lo_word's term at the lower address)
+__device__ __forceinline__ uint32_t at_pack_hi(uint32_t lo_word, uint32_t hi_word) {
+  return __byte_perm(lo_word, hi_word, 0x7632);
+}
+__device__ __forceinline__ void at_sts16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void at_sts64(uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void at_sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float4 at_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 
 // six products per k-step, small terms first: a3b1 a1b3 a2b2 a2b1 a1b2 a1b1
 __device__ __forceinline__ void at_issue(uint32_t d_tmem, const uint64_t (&a)[3], const uint64_t (&b)[3], uint32_t idesc,
@@ -152,17 +172,20 @@ __device__ __forceinline__ void at_issue(uint32_t d_tmem, const uint64_t (&a)[3]
   }
 }
 
+// LQ: words handled in registers (20 covers the 12..18-word captions of the hot path; 32 = the MMA extent)
+template <int LQ>
 __global__ void __launch_bounds__(AT_Q, 2)
 att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ src,
                           const unsigned char* __restrict__ mask, int B, int Q, int L, int nslots,
                           float* __restrict__ wc, float* __restrict__ attn) {
   extern __shared__ uint8_t at_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;                                  // 3 copies; reused for the probabilities and the staged context
-  uint8_t* sB1 = smem + 3 * AT_A_BYTES;
-  uint8_t* sB2 = sB1 + 3 * AT_B1_BYTES;
+  const uint32_t smem = (at_smem_u32(at_smem_raw) + 1023u) & ~1023u;   // shared-window address of the operand tiles
+  const uint32_t sA = smem;                            // 3 copies; reused for the probabilities and the staged context
+  const uint32_t sB1 = smem + 3 * AT_A_BYTES;
+  const uint32_t sB2 = sB1 + 3 * AT_B1_BYTES;
   __shared__ __align__(8) uint64_t bar_s, bar_o;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float ssrc[AT_C * AT_LP];                 // src[b] as [c][l], zero beyond L
 
   const int t = threadIdx.x, warp = t >> 5;
   const int b = blockIdx.x / nslots, slot = blockIdx.x - b * nslots;
@@ -174,28 +197,50 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
     at_fence_barrier_init();
   }
   if (warp == 0) at_tmem_alloc(&tmem_base_smem, 128);
-  // word-projection operand tiles of this image: B1[l][c] and B2[c][l], zero beyond L
+  // prefetch the first tile: 1536 float4 per tile, thread t takes t, t + 128, ...
+  float4 hv[12];
+  int qt = slot;
+  {
+    const float4* hp = reinterpret_cast<const float4*>(h + ((long long)b * Q + (long long)qt * AT_Q) * AT_C);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) hv[j] = __ldg(hp + t + j * AT_Q);
+  }
+  // word projections of this image -> shared (independent coalesced loads), then the two operand layouts
   {
     const float* sb = src + (long long)b * AT_C * L;
-    for (int i = t; i < AT_LP * 64; i += AT_Q) {            // B1: 32 rows x 64 k (k >= 48 never read; zero anyway)
-      const int l = i >> 6, c = i & 63;
-      const float v = (l < L && c < AT_C) ? __ldg(sb + c * L + l) : 0.f;
-      unsigned short a1, a2, a3;
-      at_split3(v, a1, a2, a3);
-      const uint32_t off = at_sw_off(l, c);
-      *reinterpret_cast<unsigned short*>(sB1 + off) = a1;
-      *reinterpret_cast<unsigned short*>(sB1 + AT_B1_BYTES + off) = a2;
-      *reinterpret_cast<unsigned short*>(sB1 + 2 * AT_B1_BYTES + off) = a3;
+    const int n = AT_C * L;
+    float v[(AT_C * AT_LP + AT_Q - 1) / AT_Q];
+#pragma unroll
+    for (int j = 0; j < (AT_C * AT_LP + AT_Q - 1) / AT_Q; ++j) {
+      const int i = t + j * AT_Q;
+      v[j] = i < n ? __ldg(sb + i) : 0.f;
     }
-    for (int i = t; i < AT_C * 64; i += AT_Q) {             // B2: 48 rows x 64 k (k >= 32 never read)
-      const int c = i >> 6, l = i & 63;
-      const float v = l < L ? __ldg(sb + c * L + l) : 0.f;
-      unsigned short a1, a2, a3;
-      at_split3(v, a1, a2, a3);
+    for (int i = t; i < AT_C * AT_LP; i += AT_Q) ssrc[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < (AT_C * AT_LP + AT_Q - 1) / AT_Q; ++j) {
+      const int i = t + j * AT_Q;
+      if (i < n) {
+        const int c = i / L;
+        ssrc[c * AT_LP + (i - c * L)] = v[j];
+      }
+    }
+    __syncthreads();
+    for (int i = t; i < AT_LP * AT_C; i += AT_Q) {         // B1[l][c]: 32 rows x 48 k
+      const int l = i / AT_C, c = i - l * AT_C;
+      const Split3 x = at_split3(ssrc[c * AT_LP + l]);
+      const uint32_t off = at_sw_off(l, c);
+      at_sts16(sB1 + off, x.w1 >> 16);
+      at_sts16(sB1 + AT_B1_BYTES + off, x.w2 >> 16);
+      at_sts16(sB1 + 2 * AT_B1_BYTES + off, x.w3 >> 16);
+    }
+    for (int i = t; i < AT_C * AT_LP; i += AT_Q) {         // B2[c][l]: 48 rows x 32 k
+      const int c = i / AT_LP, l = i - c * AT_LP;
+      const Split3 x = at_split3(ssrc[i]);
       const uint32_t off = at_sw_off(c, l);
-      *reinterpret_cast<unsigned short*>(sB2 + off) = a1;
-      *reinterpret_cast<unsigned short*>(sB2 + AT_B2_BYTES + off) = a2;
-      *reinterpret_cast<unsigned short*>(sB2 + 2 * AT_B2_BYTES + off) = a3;
+      at_sts16(sB2 + off, x.w1 >> 16);
+      at_sts16(sB2 + AT_B2_BYTES + off, x.w2 >> 16);
+      at_sts16(sB2 + 2 * AT_B2_BYTES + off, x.w3 >> 16);
     }
   }
   at_tc_fence_before();
@@ -207,37 +252,34 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
   uint64_t dA[3], dB1[3], dB2[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    dA[i] = at_desc_sw128(at_smem_u32(sA + i * AT_A_BYTES));
-    dB1[i] = at_desc_sw128(at_smem_u32(sB1 + i * AT_B1_BYTES));
-    dB2[i] = at_desc_sw128(at_smem_u32(sB2 + i * AT_B2_BYTES));
+    dA[i] = at_desc_sw128(sA + i * AT_A_BYTES);
+    dB1[i] = at_desc_sw128(sB1 + i * AT_B1_BYTES);
+    dB2[i] = at_desc_sw128(sB2 + i * AT_B2_BYTES);
   }
   const uint32_t idesc1 = at_idesc_bf16(128, AT_LP), idesc2 = at_idesc_bf16(128, AT_C);
 
-  // prefetch the first tile: 1536 float4 per tile, thread t takes t, t + 128, ...
-  float4 hv[12];
-  int qt = slot;
-  if (qt < ntiles) {
-    const float4* hp = reinterpret_cast<const float4*>(h + ((long long)b * Q + (long long)qt * AT_Q) * AT_C);
+  // tile-invariant shared-memory offsets of this thread's 12 float4 slots (A tile: swizzled; staging: padded rows)
+  uint32_t offA[12], offS[12];
 #pragma unroll
-    for (int j = 0; j < 12; ++j) hv[j] = __ldg(hp + t + j * AT_Q);
+  for (int j = 0; j < 12; ++j) {
+    const int idx = t + j * AT_Q;
+    const int r = idx / 12, cq = idx - r * 12;
+    offA[j] = at_sw_off(r, cq * 4);
+    offS[j] = (uint32_t)(r * AT_STAGE_PITCH + cq * 4) * 4u;
   }
+  const uint32_t rowP = sA + at_sw_off(t, 0) - (uint32_t)((t & 7) << 4);   // row base; chunk ch sits at ((ch ^ (t & 7)) << 4)
+  const uint32_t rowS = sA + (uint32_t)(t * AT_STAGE_PITCH) * 4u;
+
   uint32_t phase = 0;
   for (; qt < ntiles; qt += nslots, phase ^= 1) {
     const int q0 = qt * AT_Q;
     // ---------------- (1) split the h tile into the three A copies ----------------
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
-      const int idx = t + j * AT_Q;
-      const int r = idx / 12, cq = idx - r * 12;
-      unsigned short x1[4], x2[4], x3[4];
-      at_split3(hv[j].x, x1[0], x2[0], x3[0]);
-      at_split3(hv[j].y, x1[1], x2[1], x3[1]);
-      at_split3(hv[j].z, x1[2], x2[2], x3[2]);
-      at_split3(hv[j].w, x1[3], x2[3], x3[3]);
-      const uint32_t off = at_sw_off(r, cq * 4);
-      *reinterpret_cast<uint2*>(sA + off) = make_uint2(at_pack(x1[0], x1[1]), at_pack(x1[2], x1[3]));
-      *reinterpret_cast<uint2*>(sA + AT_A_BYTES + off) = make_uint2(at_pack(x2[0], x2[1]), at_pack(x2[2], x2[3]));
-      *reinterpret_cast<uint2*>(sA + 2 * AT_A_BYTES + off) = make_uint2(at_pack(x3[0], x3[1]), at_pack(x3[2], x3[3]));
+      const Split3 x0 = at_split3(hv[j].x), x1 = at_split3(hv[j].y), x2 = at_split3(hv[j].z), x3 = at_split3(hv[j].w);
+      at_sts64(sA + offA[j], at_pack_hi(x0.w1, x1.w1), at_pack_hi(x2.w1, x3.w1));
+      at_sts64(sA + AT_A_BYTES + offA[j], at_pack_hi(x0.w2, x1.w2), at_pack_hi(x2.w2, x3.w2));
+      at_sts64(sA + 2 * AT_A_BYTES + offA[j], at_pack_hi(x0.w3, x1.w3), at_pack_hi(x2.w3, x3.w3));
     }
     // the next tile's loads fly during the rest of this trip
     if (qt + nslots < ntiles) {
@@ -256,49 +298,61 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
     // ---------------- (2) softmax over the words ----------------
     at_mbar_wait(&bar_s, phase);
     at_tc_fence_after();
-    uint32_t sr[32];
-    at_tmem_ld32(tmem_row, sr);
-    at_tmem_ld_wait();
-    float sc[AT_LP];
+    float sc[LQ];
+    if (LQ == 32) {
+      uint32_t sr[32];
+      at_tmem_ld32(tmem_row, sr);
+      at_tmem_ld_wait();
 #pragma unroll
-    for (int l = 0; l < AT_LP; ++l) sc[l] = __uint_as_float(sr[l]);
+      for (int l = 0; l < LQ; ++l) sc[l] = __uint_as_float(sr[l]);
+    } else {
+      uint32_t sr[16], sr2[16];
+      at_tmem_ld16(tmem_row, sr);
+      at_tmem_ld16(tmem_row + 16, sr2);
+      at_tmem_ld_wait();
+#pragma unroll
+      for (int l = 0; l < LQ; ++l) sc[l] = __uint_as_float(l < 16 ? sr[l & 15] : sr2[l & 15]);
+    }
     const int q = q0 + t;
     if (mask) {
-      const unsigned char* mr = mask + (((long long)b * Q + q) % B) * L;
+      const unsigned char* mr = mask + (((unsigned)b * (unsigned)Q + (unsigned)q) % (unsigned)B) * L;   // B * Q < 2^31
 #pragma unroll
-      for (int l = 0; l < AT_LP; ++l)
+      for (int l = 0; l < LQ; ++l)
         if (l < L && mr[l]) sc[l] = -INFINITY;
     }
     float mx = -INFINITY;
 #pragma unroll
-    for (int l = 0; l < AT_LP; ++l)
+    for (int l = 0; l < LQ; ++l)
       if (l < L) mx = fmaxf(mx, sc[l]);
     float sum = 0.f;
 #pragma unroll
-    for (int l = 0; l < AT_LP; ++l) {
+    for (int l = 0; l < LQ; ++l) {
       sc[l] = l < L ? expf(sc[l] - mx) : 0.f;
       sum += sc[l];
     }
     const float inv = 1.f / sum;
     float* arow = attn + (long long)b * L * Q + q;
 #pragma unroll
-    for (int l = 0; l < AT_LP; ++l) {
+    for (int l = 0; l < LQ; ++l) {
       sc[l] *= inv;
       if (l < L) arow[(long long)l * Q] = sc[l];
     }
-    // probabilities -> the three A copies (row t, K = 32: four 16-byte chunks per copy)
+    // probabilities -> the three A copies (row t, K = 32: four 16-byte chunks per copy; words >= LQ are zeros)
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
-      unsigned short y1[8], y2[8], y3[8];
+      uint32_t y1[4], y2[4], y3[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) at_split3(sc[ch * 8 + e], y1[e], y2[e], y3[e]);
-      const uint32_t off = at_sw_off(t, ch * 8);
-      *reinterpret_cast<uint4*>(sA + off) =
-          make_uint4(at_pack(y1[0], y1[1]), at_pack(y1[2], y1[3]), at_pack(y1[4], y1[5]), at_pack(y1[6], y1[7]));
-      *reinterpret_cast<uint4*>(sA + AT_A_BYTES + off) =
-          make_uint4(at_pack(y2[0], y2[1]), at_pack(y2[2], y2[3]), at_pack(y2[4], y2[5]), at_pack(y2[6], y2[7]));
-      *reinterpret_cast<uint4*>(sA + 2 * AT_A_BYTES + off) =
-          make_uint4(at_pack(y3[0], y3[1]), at_pack(y3[2], y3[3]), at_pack(y3[4], y3[5]), at_pack(y3[6], y3[7]));
+      for (int e = 0; e < 4; ++e) {
+        const int l0 = ch * 8 + 2 * e;
+        Split3 u = {0u, 0u, 0u}, w = {0u, 0u, 0u};
+        if (l0 < LQ) u = at_split3(sc[l0 < LQ ? l0 : 0]);
+        if (l0 + 1 < LQ) w = at_split3(sc[l0 + 1 < LQ ? l0 + 1 : 0]);
+        y1[e] = at_pack_hi(u.w1, w.w1); y2[e] = at_pack_hi(u.w2, w.w2); y3[e] = at_pack_hi(u.w3, w.w3);
+      }
+      const uint32_t addr = rowP + (uint32_t)(((ch ^ (t & 7)) & 7) << 4);
+      at_sts128(addr, y1[0], y1[1], y1[2], y1[3]);
+      at_sts128(addr + AT_A_BYTES, y2[0], y2[1], y2[2], y2[3]);
+      at_sts128(addr + 2 * AT_A_BYTES, y3[0], y3[1], y3[2], y3[3]);
     }
     at_fence_proxy_async();
     at_tc_fence_before();
@@ -315,26 +369,17 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
     at_tmem_ld32(tmem_row + 32, o0);
     at_tmem_ld16(tmem_row + 64, o1);
     at_tmem_ld_wait();
-    float* stage = reinterpret_cast<float*>(sA);        // MMA 2 has completed: the A copies are free
-    {
-      float* srow = stage + t * AT_STAGE_PITCH;
+    // MMA 2 has completed: the A copies are free and take the staged context rows
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<uint4*>(srow + j) = make_uint4(o0[j], o0[j + 1], o0[j + 2], o0[j + 3]);
+    for (int j = 0; j < 32; j += 4) at_sts128(rowS + j * 4, o0[j], o0[j + 1], o0[j + 2], o0[j + 3]);
 #pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<uint4*>(srow + 32 + j) = make_uint4(o1[j], o1[j + 1], o1[j + 2], o1[j + 3]);
-    }
+    for (int j = 0; j < 16; j += 4) at_sts128(rowS + (32 + j) * 4, o1[j], o1[j + 1], o1[j + 2], o1[j + 3]);
     at_tc_fence_before();
     __syncthreads();
     {
       float4* op = reinterpret_cast<float4*>(wc + ((long long)b * Q + q0) * AT_C);
 #pragma unroll
-      for (int j = 0; j < 12; ++j) {
-        const int idx = t + j * AT_Q;
-        const int r = idx / 12, cq = idx - r * 12;
-        op[idx] = *reinterpret_cast<const float4*>(stage + r * AT_STAGE_PITCH + cq * 4);
-      }
+      for (int j = 0; j < 12; ++j) op[t + j * AT_Q] = at_lds128(sA + offS[j]);
     }
     __syncthreads();                                     // staging drained before the next trip overwrites the A copies
   }
@@ -352,7 +397,9 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
 // kernels of attention.cu), else a cudaError_t.
 extern "C" int og_att_general_fwd_tc(const float* h, const float* src, const unsigned char* mask, int B, int Q, int idf,
                                      int cs, int L, float* wc, float* attn, cudaStream_t stream) {
-  if (idf != AT_C || cs != AT_C || L < 1 || L > AT_LP || Q % AT_Q != 0 || Q < AT_Q || B < 1) return -1;
+  if (idf != AT_C || cs != AT_C || L < 1 || L > AT_LP || Q % AT_Q != 0 || Q < AT_Q || B < 1 ||
+      (long long)B * Q >= (1LL << 31))
+    return -1;
   const int ntiles = Q / AT_Q;
   int nslots = (2 * 148) / B;          // two CTAs per SM, every CTA stays inside one image
   if (nslots < 1) nslots = 1;
@@ -360,9 +407,13 @@ extern "C" int og_att_general_fwd_tc(const float* h, const float* src, const uns
   const size_t smem = AT_SMEM + 1024;
   static bool configured = false;
   if (!configured) {
-    OG_CHECK(cudaFuncSetAttribute(att_general_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OG_CHECK(cudaFuncSetAttribute(att_general_fwd_tc_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OG_CHECK(cudaFuncSetAttribute(att_general_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  att_general_fwd_tc_kernel<<<B * nslots, AT_Q, smem, stream>>>(h, src, mask, B, Q, L, nslots, wc, attn);
+  if (L <= 20)
+    att_general_fwd_tc_kernel<20><<<B * nslots, AT_Q, smem, stream>>>(h, src, mask, B, Q, L, nslots, wc, attn);
+  else
+    att_general_fwd_tc_kernel<32><<<B * nslots, AT_Q, smem, stream>>>(h, src, mask, B, Q, L, nslots, wc, attn);
   OG_RETURN_LAST_ERROR();
 }

@@ -475,16 +475,6 @@ class StepBTrainer(StepATrainer):
         name = os.path.basename(net_g_path)
         return int(name[name.rfind("_") + 1:name.rfind(".")]) + 1
 
-    def _update_streams(self, n):
-        """Side streams for the independent discriminator updates of one step (None: run them in sequence)."""
-        if os.environ.get("OBJGAN_D_STREAMS", "1") != "1" or not torch.cuda.is_available() or _lib.DRY_RUN:
-            return None
-        have = getattr(self, "_ustreams", [])
-        while len(have) < n:
-            have.append(torch.cuda.Stream())
-        self._ustreams = have
-        return have[:n]
-
     def _update(self, bucket, err, lr, gs):
         """backward + all-reduce + Adam for one discriminator.  ``err`` may be the int 0 of an empty roi set (the
         reference then skips the optimiser step, trainer.py:428-431); with several ranks the exchange must stay
@@ -523,33 +513,22 @@ class StepBTrainer(StepATrainer):
         for b in self._d_buckets():
             b.requires_grad_(True)
             b.zero_grad()
-        # (3-1) patch discriminators, (3-2) shape discriminators, (3-3) / (3-4) object discriminators (small scale on
-        # the 64-scale boxes, large scale on the feature-map boxes).  The eight updates are independent (own network,
-        # own bucket, read-only inputs): each runs on its own stream, forked from and joined to the step's stream, so
-        # their many small kernels overlap; host order (and so the order of the permute_seg shuffles and of the
-        # collectives under data parallelism) stays the reference's.
-        codes = bt_c_codes[-1]
-        jobs = []
+        # (3-1) patch discriminators, (3-2) shape discriminators.  The eight discriminator updates run in sequence on the
+        # step's stream: forking them onto eight streams (as Step-A does with its three patch discriminators) was
+        # measured at batch 16 and stalled the GPU for minutes once consecutive steps were enqueued without a
+        # synchronisation in between (round 2, gpurun_out/r02d_probe_on.log), so it is not done here.
         for i, (d, b) in enumerate(zip(self.netsPatD, self.bD)):
-            jobs.append((f"errPatD{i}", b, lambda d=d, i=i: losses.patD_loss(d, imgs[i], fake_imgs[i], sent)))
+            out[f"errPatD{i}"] = self._update(b, losses.patD_loss(d, imgs[i], fake_imgs[i], sent), lr_d, gs)
         for i, (d, b) in enumerate(zip(self.netsShpD, self.bShp)):
-            jobs.append((f"errShpD{i}", b,
-                         lambda d=d, i=i: losses.shpD_loss(d, imgs[i], fake_imgs[i], hmaps[i], rois_h[i], nr_h)))
-        jobs.append(("errObjSSD", self.bObj[0], lambda: losses.objD_loss(
-            self.netObjSSD, imgs[-1], fake_imgs[-1], hmaps[-1], inp["clabels_emb"], codes, rois_h[0], nr_h)))
-        jobs.append(("errObjLSD", self.bObj[1], lambda: losses.objD_loss(
+            out[f"errShpD{i}"] = self._update(b, losses.shpD_loss(d, imgs[i], fake_imgs[i], hmaps[i], rois_h[i], nr_h),
+                                              lr_d, gs)
+        # (3-3) / (3-4) object discriminators (small scale on the 64-scale boxes, large scale on the feature-map boxes)
+        codes = bt_c_codes[-1]
+        out["errObjSSD"] = self._update(self.bObj[0], losses.objD_loss(
+            self.netObjSSD, imgs[-1], fake_imgs[-1], hmaps[-1], inp["clabels_emb"], codes, rois_h[0], nr_h), lr_d, gs)
+        out["errObjLSD"] = self._update(self.bObj[1], losses.objD_loss(
             self.netObjLSD, imgs[-1], fake_imgs[-1], hmaps[-1], inp["clabels_emb"], codes, fm_h, nr_h,
-            is_large_scale=True)))
-        streams = self._update_streams(len(jobs))
-        main = torch.cuda.current_stream() if streams else None
-        for k, (name, bucket, loss_fn) in enumerate(jobs):
-            if streams:
-                streams[k].wait_stream(main)
-            with (torch.cuda.stream(streams[k]) if streams else contextlib.nullcontext()):
-                out[name] = self._update(bucket, loss_fn(), lr_d, gs)
-        if streams:
-            for st in streams:
-                main.wait_stream(st)
+            is_large_scale=True), lr_d, gs)
         # (4) generator
         for b in self._d_buckets():
             b.requires_grad_(False)

@@ -34,7 +34,7 @@ CASES = [
     (384, 384, "k4s1", 0, 130, 5, 5),            # roi_code of the object discriminators: 4x4 stride 1 pad 1 on 5x5 pooled rois
     (384, 384, "k4s1", 0, 70, 5, 5),             # ... roi count that does not fill the last pixel tile / wgrad image group
     (192, 384, "s2", 0, 13, 16, 16),             # sub-batch of the permuted-shape pass: 13 images, tiles span 2 images
-    (384, 768, "s2", 0, 11, 8, 8),               # ... 4x4 outputs, 8 images per tile
+    (384, 768, "s2", 0, 19, 8, 8),               # ... 4x4 outputs, 8 images per tile
     (96, 48, UPSAMPLE2X, 24, 3, 8, 8),           # upsample phases with a batch that does not fill the 2-image tile
 ]
 
