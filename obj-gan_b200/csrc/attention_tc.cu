@@ -7,19 +7,22 @@
 //
 // Why tensor cores for a bandwidth-bound op: the two tiny GEMMs cost 1920 fp32 FMAs per query; on the CUDA cores that
 // instruction stream (plus the shared-memory operand traffic it needs) capped the kernel at 0.37 of the HBM
-// bandwidth.  Here the FMA work is 30 small MMAs per 128 queries and the threads only move and convert data.
+// bandwidth.  Here the FMA work is 15 small MMAs per 128 queries and the threads only move and convert data.
 //
-// fp32 parity: every operand is split into THREE bf16 terms (a = a1 + a2 + a3, 24 mantissa bits, bf16 keeps the fp32
-// exponent so no scaling pass is needed) and six products (a1b1 + a1b2 + a2b1 + a2b2 + a1b3 + a3b1) accumulate in the
-// fp32 TMEM accumulator: the dropped terms are below 2^-24 of the product, i.e. fp32 rounding level.
+// fp32 parity: the convolution engine's error-compensated scheme (conv_tc.cu): x * 2^k = hi + lo with hi, lo fp16
+// (22 mantissa bits), three products hi*hi + lo*hi + hi*lo into the fp32 TMEM accumulator.  The power of two comes from
+// max|x| of the TILE (a register max + one shuffle reduction; no extra pass over the tensor) resp. of the image's
+// word projections; the accumulator is scaled back before the softmax / the store.  hi is the fp32 value truncated to
+// 11 significant bits (one LOP3), lo the exact remainder; the only conversions are packed cvt.rn.f16x2 (no F2F).
 //
 // One CTA = 128 threads = 128 queries per trip; thread t owns query row t (= TMEM lane t).  Per trip:
 //   (1) the h tile (24.5 KB, contiguous) arrives through coalesced 16-byte loads issued one trip AHEAD (registers),
-//       is split and stored into three K-major 128B-swizzled A tiles;                      -> MMA 1 (18 instructions)
+//       is split and stored into two K-major 128B-swizzled A tiles;                        -> MMA 1 (9 instructions)
 //   (2) tcgen05.ld of the thread's score row, softmax in registers, coalesced attn stores (lanes = adjacent queries),
-//       the probabilities are split into the same three tiles (K = 32);                    -> MMA 2 (12 instructions)
+//       the probabilities are split into the same two tiles (K = 32);                      -> MMA 2 (6 instructions)
 //   (3) tcgen05.ld of the context row, staged through shared memory, written with coalesced 16-byte stores.
-// CTAs are persistent over the query tiles of ONE image (the word-projection operand tiles are built once).
+// CTAs are persistent over the query tiles of ONE image (the word-projection operand tiles are built once).  52 KB of
+// shared memory and <= 128 registers per thread: four CTAs per SM cover each other's MMA round trips.
 #include "common.cuh"
 #include <cuda_bf16.h>
 
@@ -28,11 +31,13 @@ namespace {
 constexpr int AT_Q = 128;          // queries per tile = threads per CTA
 constexpr int AT_C = 48;           // channels (idf == row stride)
 constexpr int AT_LP = 32;          // words padded to the MMA N / K extent
-constexpr uint32_t AT_A_BYTES = 128 * 128;            // one bf16 copy of the A tile: 128 rows x 128-byte swizzle rows
+constexpr uint32_t AT_A_BYTES = 128 * 128;            // one fp16 copy of the A tile: 128 rows x 128-byte swizzle rows
 constexpr uint32_t AT_B1_BYTES = AT_LP * 128;         // src as [l][c]  (N = 32 rows, K = 48)
 constexpr uint32_t AT_B2_BYTES = AT_C * 128;          // src as [c][l]  (N = 48 rows, K = 32)
-constexpr uint32_t AT_SMEM = 3 * AT_A_BYTES + 3 * AT_B1_BYTES + 3 * AT_B2_BYTES;
+constexpr uint32_t AT_SMEM = 2 * AT_A_BYTES + 2 * AT_B1_BYTES + 2 * AT_B2_BYTES;     // 52 KB: four CTAs per SM
 constexpr int AT_STAGE_PITCH = AT_C + 4;              // floats per staged context row (conflict-free 16-byte accesses)
+constexpr int AT_MAXB = 128;                          // batch sizes whose caption masks fit the bit table
+constexpr int AT_PSCALE = 13;                          // probabilities enter MMA 2 as p * 2^13 (fp16 subnormals start at 7e-9)
 
 __device__ __forceinline__ uint32_t at_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void at_mbar_init(uint64_t* bar, uint32_t count) {
@@ -117,9 +122,9 @@ __device__ __forceinline__ uint64_t at_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// D = f32, A = B = bf16 (format code 1), both K-major
-__device__ __forceinline__ uint32_t at_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// D = f32, A = B = f16 (format code 0), both K-major
+__device__ __forceinline__ uint32_t at_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // byte offset of element (row r, 16-bit column k) in a K-major SWIZZLE_128B tile
@@ -127,21 +132,17 @@ __device__ __forceinline__ uint32_t at_sw_off(int r, int k) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2);
 }
 
-// a = a1 + a2 + a3 EXACTLY: a1 = the top 16 bits of the fp32 pattern (a bf16 by truncation), a2 = the top 16 bits of the
-// exact residual, a3 = what is left (<= 8 significant bits: a bf16 as it stands).  Pure LOP3 / FADD work -- the rounding
-// conversions (F2F) this replaces are quarter-rate instructions and dominated the first version of this kernel.
-struct Split3 { uint32_t w1, w2, w3; };      // fp32 bit patterns whose HIGH halves are the three bf16 terms
-__device__ __forceinline__ Split3 at_split3(float v) {
-  Split3 s;
-  s.w1 = __float_as_uint(v) & 0xFFFF0000u;
-  const float r1 = v - __uint_as_float(s.w1);
-  s.w2 = __float_as_uint(r1) & 0xFFFF0000u;
-  s.w3 = __float_as_uint(r1 - __uint_as_float(s.w2));
-  return s;
+// x (already scaled) = hi + lo: hi = x rounded to 11 significant bits in the fp32 domain (half an ulp added to the
+// magnitude, then truncated: exact in fp16 while |x| >= 2^-14), lo = x - hi exactly (|lo| <= 2^-11 |x|)
+__device__ __forceinline__ void at_hilo(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
 }
-// {high half of lo_word, high half of hi_word} -> one 32-bit pair of bf16 (lo_word's term at the lower address)
-__device__ __forceinline__ uint32_t at_pack_hi(uint32_t lo_word, uint32_t hi_word) {
-  return __byte_perm(lo_word, hi_word, 0x7632);
+// two floats -> packed f16x2 (first argument in the low half)
+__device__ __forceinline__ uint32_t at_cvt2(float lo_el, float hi_el) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_el), "f"(lo_el));
+  return r;
 }
 __device__ __forceinline__ void at_sts16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
@@ -157,37 +158,51 @@ __device__ __forceinline__ float4 at_lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ float at_amax4(float m, const float4& v) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
+// max over the CTA's 128 threads (4 warps) through a 4-word shared scratch; every thread gets the result
+__device__ __forceinline__ float at_cta_max(float m, float* scratch) {
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(scratch[0], scratch[1]), fmaxf(scratch[2], scratch[3]));
+  return m;
+}
 
-// six products per k-step, small terms first: a3b1 a1b3 a2b2 a2b1 a1b2 a1b1
-__device__ __forceinline__ void at_issue(uint32_t d_tmem, const uint64_t (&a)[3], const uint64_t (&b)[3], uint32_t idesc,
+// three products per k-step, small terms first: lo*hi, hi*lo, hi*hi
+__device__ __forceinline__ void at_issue(uint32_t d_tmem, const uint64_t (&a)[2], const uint64_t (&b)[2], uint32_t idesc,
                                          int ksteps) {
   for (int k = 0; k < ksteps; ++k) {
     const uint64_t koff = (uint64_t)((k * 32) >> 4);
-    at_umma(d_tmem, a[2] + koff, b[0] + koff, idesc, k > 0 ? 1u : 0u);
-    at_umma(d_tmem, a[0] + koff, b[2] + koff, idesc, 1u);
-    at_umma(d_tmem, a[1] + koff, b[1] + koff, idesc, 1u);
-    at_umma(d_tmem, a[1] + koff, b[0] + koff, idesc, 1u);
+    at_umma(d_tmem, a[1] + koff, b[0] + koff, idesc, k > 0 ? 1u : 0u);
     at_umma(d_tmem, a[0] + koff, b[1] + koff, idesc, 1u);
     at_umma(d_tmem, a[0] + koff, b[0] + koff, idesc, 1u);
   }
 }
 
 // LQ: words handled in registers (20 covers the 12..18-word captions of the hot path; 32 = the MMA extent)
+//
+// Thread <-> data mapping of the two coalesced passes over a tile (1536 float4 = 128 rows x 12): warp w owns rows
+// [32w, 32w + 32); it walks them in four groups g of 8 rows (= 96 float4 = three warp-wide accesses j), so float4
+// number 32j + lane of a group is (row r8[j], quad c8[j]) with r8 / c8 fixed per thread, and a group step is exactly
+// one 1024-byte swizzle atom of the operand tile: every shared-memory offset is base[j] + g * constant.
 template <int LQ>
-__global__ void __launch_bounds__(AT_Q, 2)
+__global__ void __launch_bounds__(AT_Q, 4)
 att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ src,
                           const unsigned char* __restrict__ mask, int B, int Q, int L, int nslots,
                           float* __restrict__ wc, float* __restrict__ attn) {
   extern __shared__ uint8_t at_smem_raw[];
   const uint32_t smem = (at_smem_u32(at_smem_raw) + 1023u) & ~1023u;   // shared-window address of the operand tiles
-  const uint32_t sA = smem;                            // 3 copies; reused for the probabilities and the staged context
-  const uint32_t sB1 = smem + 3 * AT_A_BYTES;
-  const uint32_t sB2 = sB1 + 3 * AT_B1_BYTES;
+  const uint32_t sA = smem;                            // hi, lo; reused for the probabilities and the staged context
+  const uint32_t sB1 = smem + 2 * AT_A_BYTES;
+  const uint32_t sB2 = sB1 + 2 * AT_B1_BYTES;
   __shared__ __align__(8) uint64_t bar_s, bar_o;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float ssrc[AT_C * AT_LP];                 // src[b] as [c][l], zero beyond L
+  __shared__ float red[2][4];                          // CTA max scratch
+  __shared__ uint32_t mbits[AT_MAXB];                  // caption masks of the batch, one bit per word
 
-  const int t = threadIdx.x, warp = t >> 5;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int b = blockIdx.x / nslots, slot = blockIdx.x - b * nslots;
   const int ntiles = Q / AT_Q;
 
@@ -197,50 +212,54 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
     at_fence_barrier_init();
   }
   if (warp == 0) at_tmem_alloc(&tmem_base_smem, 128);
-  // prefetch the first tile: 1536 float4 per tile, thread t takes t, t + 128, ...
+  // per-thread constants of the tile walk
+  uint32_t offA[3], offS[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int f = j * 32 + lane, r8 = (f * 43691) >> 19, c8 = f - r8 * 12;        // f / 12 for f < 96
+    offA[j] = (uint32_t)(warp * 4 * 1024) + at_sw_off(r8, c8 * 4);
+    offS[j] = (uint32_t)(((warp * 32 + r8) * AT_STAGE_PITCH + c8 * 4) * 4);
+  }
+  // prefetch the first tile
   float4 hv[12];
   int qt = slot;
   {
-    const float4* hp = reinterpret_cast<const float4*>(h + ((long long)b * Q + (long long)qt * AT_Q) * AT_C);
+    const float4* hp = reinterpret_cast<const float4*>(h + ((long long)b * Q + (long long)qt * AT_Q) * AT_C) + warp * 384 + lane;
 #pragma unroll
-    for (int j = 0; j < 12; ++j) hv[j] = __ldg(hp + t + j * AT_Q);
+    for (int i = 0; i < 12; ++i) hv[i] = __ldg(hp + i * 32);
   }
-  // word projections of this image -> shared (independent coalesced loads), then the two operand layouts
+  // word projections of this image -> the two operand layouts B1[l][c] and B2[c][l] as scaled fp16 hi / lo (zero beyond
+  // L), straight from registers: thread t holds word l = t & 31 of channels (t >> 5) + 4j
+  int ksrc;
   {
     const float* sb = src + (long long)b * AT_C * L;
-    const int n = AT_C * L;
-    float v[(AT_C * AT_LP + AT_Q - 1) / AT_Q];
+    const int l = lane, c0 = warp;
+    float v[12];
+    float m = 0.f;
 #pragma unroll
-    for (int j = 0; j < (AT_C * AT_LP + AT_Q - 1) / AT_Q; ++j) {
-      const int i = t + j * AT_Q;
-      v[j] = i < n ? __ldg(sb + i) : 0.f;
+    for (int j = 0; j < 12; ++j) {
+      v[j] = l < L ? __ldg(sb + (c0 + 4 * j) * L + l) : 0.f;
+      m = fmaxf(m, fabsf(v[j]));
     }
-    for (int i = t; i < AT_C * AT_LP; i += AT_Q) ssrc[i] = 0.f;
-    __syncthreads();
+    if (mask && t < B) {
+      uint32_t w = 0;
+      for (int i = 0; i < L; ++i) w |= (mask[t * L + i] ? 1u : 0u) << i;
+      mbits[t] = w;
+    }
+    m = at_cta_max(m, red[0]);
+    ksrc = og_scale_exp(__float_as_uint(m));
+    const float s = og_exp2i(ksrc);
 #pragma unroll
-    for (int j = 0; j < (AT_C * AT_LP + AT_Q - 1) / AT_Q; ++j) {
-      const int i = t + j * AT_Q;
-      if (i < n) {
-        const int c = i / L;
-        ssrc[c * AT_LP + (i - c * L)] = v[j];
-      }
-    }
-    __syncthreads();
-    for (int i = t; i < AT_LP * AT_C; i += AT_Q) {         // B1[l][c]: 32 rows x 48 k
-      const int l = i / AT_C, c = i - l * AT_C;
-      const Split3 x = at_split3(ssrc[c * AT_LP + l]);
-      const uint32_t off = at_sw_off(l, c);
-      at_sts16(sB1 + off, x.w1 >> 16);
-      at_sts16(sB1 + AT_B1_BYTES + off, x.w2 >> 16);
-      at_sts16(sB1 + 2 * AT_B1_BYTES + off, x.w3 >> 16);
-    }
-    for (int i = t; i < AT_C * AT_LP; i += AT_Q) {         // B2[c][l]: 48 rows x 32 k
-      const int c = i / AT_LP, l = i - c * AT_LP;
-      const Split3 x = at_split3(ssrc[i]);
-      const uint32_t off = at_sw_off(c, l);
-      at_sts16(sB2 + off, x.w1 >> 16);
-      at_sts16(sB2 + AT_B2_BYTES + off, x.w2 >> 16);
-      at_sts16(sB2 + 2 * AT_B2_BYTES + off, x.w3 >> 16);
+    for (int j = 0; j < 12; ++j) {
+      const int c = c0 + 4 * j;
+      float hi, lo;
+      at_hilo(v[j] * s, hi, lo);
+      const uint32_t pk = at_cvt2(hi, lo);             // low half = hi, high half = lo
+      const uint32_t o1 = at_sw_off(l, c), o2 = at_sw_off(c, l);
+      at_sts16(sB1 + o1, pk & 0xFFFFu);
+      at_sts16(sB1 + AT_B1_BYTES + o1, pk >> 16);
+      at_sts16(sB2 + o2, pk & 0xFFFFu);
+      at_sts16(sB2 + AT_B2_BYTES + o2, pk >> 16);
     }
   }
   at_tc_fence_before();
@@ -249,43 +268,49 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
 
-  uint64_t dA[3], dB1[3], dB2[3];
+  uint64_t dA[2], dB1[2], dB2[2];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 2; ++i) {
     dA[i] = at_desc_sw128(sA + i * AT_A_BYTES);
     dB1[i] = at_desc_sw128(sB1 + i * AT_B1_BYTES);
     dB2[i] = at_desc_sw128(sB2 + i * AT_B2_BYTES);
   }
-  const uint32_t idesc1 = at_idesc_bf16(128, AT_LP), idesc2 = at_idesc_bf16(128, AT_C);
-
-  // tile-invariant shared-memory offsets of this thread's 12 float4 slots (A tile: swizzled; staging: padded rows)
-  uint32_t offA[12], offS[12];
-#pragma unroll
-  for (int j = 0; j < 12; ++j) {
-    const int idx = t + j * AT_Q;
-    const int r = idx / 12, cq = idx - r * 12;
-    offA[j] = at_sw_off(r, cq * 4);
-    offS[j] = (uint32_t)(r * AT_STAGE_PITCH + cq * 4) * 4u;
-  }
-  const uint32_t rowP = sA + at_sw_off(t, 0) - (uint32_t)((t & 7) << 4);   // row base; chunk ch sits at ((ch ^ (t & 7)) << 4)
+  const uint32_t idesc1 = at_idesc_f16(128, AT_LP), idesc2 = at_idesc_f16(128, AT_C);
+  const uint32_t rowP = sA + (uint32_t)((t >> 3) * 1024 + (t & 7) * 128);   // row t of an A tile; chunk ch at ((ch ^ (t & 7)) << 4)
   const uint32_t rowS = sA + (uint32_t)(t * AT_STAGE_PITCH) * 4u;
+  const float so = og_exp2i(-AT_PSCALE) * og_exp2i(-ksrc);                   // context rows: undo both operand scales
+  const float ss2 = og_exp2i(-ksrc);
+  // caption-mask row of query (b, q): sample (b * Q + q) mod B (ref: GlobalAttention.py:108); advanced incrementally
+  uint32_t mrow = ((uint32_t)b * (uint32_t)Q + (uint32_t)(qt * AT_Q + t)) % (uint32_t)B;
+  const uint32_t mstep = ((uint32_t)nslots * AT_Q) % (uint32_t)B;
 
   uint32_t phase = 0;
   for (; qt < ntiles; qt += nslots, phase ^= 1) {
     const int q0 = qt * AT_Q;
-    // ---------------- (1) split the h tile into the three A copies ----------------
+    // ---------------- (1) scale by the tile's power of two, split into the two A copies ----------------
+    float m = 0.f;
 #pragma unroll
-    for (int j = 0; j < 12; ++j) {
-      const Split3 x0 = at_split3(hv[j].x), x1 = at_split3(hv[j].y), x2 = at_split3(hv[j].z), x3 = at_split3(hv[j].w);
-      at_sts64(sA + offA[j], at_pack_hi(x0.w1, x1.w1), at_pack_hi(x2.w1, x3.w1));
-      at_sts64(sA + AT_A_BYTES + offA[j], at_pack_hi(x0.w2, x1.w2), at_pack_hi(x2.w2, x3.w2));
-      at_sts64(sA + 2 * AT_A_BYTES + offA[j], at_pack_hi(x0.w3, x1.w3), at_pack_hi(x2.w3, x3.w3));
-    }
+    for (int i = 0; i < 12; ++i) m = at_amax4(m, hv[i]);
+    m = at_cta_max(m, red[1]);                          // the __syncthreads of the trip order the reuse of the slot
+    const int kh = og_scale_exp(__float_as_uint(m));
+    const float sh = og_exp2i(kh);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float4 x = hv[g * 3 + j];
+        float h0, l0, h1, l1, h2, l2, h3, l3;
+        at_hilo(x.x * sh, h0, l0); at_hilo(x.y * sh, h1, l1);
+        at_hilo(x.z * sh, h2, l2); at_hilo(x.w * sh, h3, l3);
+        const uint32_t a = sA + offA[j] + g * 1024;
+        at_sts64(a, at_cvt2(h0, h1), at_cvt2(h2, h3));
+        at_sts64(a + AT_A_BYTES, at_cvt2(l0, l1), at_cvt2(l2, l3));
+      }
     // the next tile's loads fly during the rest of this trip
     if (qt + nslots < ntiles) {
-      const float4* hp = reinterpret_cast<const float4*>(h + ((long long)b * Q + (long long)(qt + nslots) * AT_Q) * AT_C);
+      const float4* hp = reinterpret_cast<const float4*>(h + ((long long)b * Q + (long long)(qt + nslots) * AT_Q) * AT_C) + warp * 384 + lane;
 #pragma unroll
-      for (int j = 0; j < 12; ++j) hv[j] = __ldg(hp + t + j * AT_Q);
+      for (int i = 0; i < 12; ++i) hv[i] = __ldg(hp + i * 32);
     }
     at_fence_proxy_async();
     at_tc_fence_before();
@@ -299,60 +324,66 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
     at_mbar_wait(&bar_s, phase);
     at_tc_fence_after();
     float sc[LQ];
-    if (LQ == 32) {
-      uint32_t sr[32];
-      at_tmem_ld32(tmem_row, sr);
-      at_tmem_ld_wait();
+    {
+      const float ss1 = og_exp2i(-kh);
+      if (LQ == 32) {
+        uint32_t sr[32];
+        at_tmem_ld32(tmem_row, sr);
+        at_tmem_ld_wait();
 #pragma unroll
-      for (int l = 0; l < LQ; ++l) sc[l] = __uint_as_float(sr[l]);
-    } else {
-      uint32_t sr[16], sr2[16];
-      at_tmem_ld16(tmem_row, sr);
-      at_tmem_ld16(tmem_row + 16, sr2);
-      at_tmem_ld_wait();
+        for (int l = 0; l < LQ; ++l) sc[l] = __uint_as_float(sr[l]) * ss1 * ss2;
+      } else {
+        uint32_t sr[16], sr2[16];
+        at_tmem_ld16(tmem_row, sr);
+        at_tmem_ld16(tmem_row + 16, sr2);
+        at_tmem_ld_wait();
 #pragma unroll
-      for (int l = 0; l < LQ; ++l) sc[l] = __uint_as_float(l < 16 ? sr[l & 15] : sr2[l & 15]);
+        for (int l = 0; l < LQ; ++l) sc[l] = __uint_as_float(l < 16 ? sr[l & 15] : sr2[l & 15]) * ss1 * ss2;
+      }
     }
-    const int q = q0 + t;
-    if (mask) {
-      const unsigned char* mr = mask + (((unsigned)b * (unsigned)Q + (unsigned)q) % (unsigned)B) * L;   // B * Q < 2^31
+    {
+      // words beyond L and masked words leave the softmax (exp2(-inf) = 0)
+      uint32_t dead = L >= 32 ? 0u : ~((1u << L) - 1u);
+      if (mask) dead |= mbits[mrow];
+      mrow += mstep;
+      if (mrow >= (uint32_t)B) mrow -= (uint32_t)B;
+      float mx = -INFINITY;
 #pragma unroll
-      for (int l = 0; l < LQ; ++l)
-        if (l < L && mr[l]) sc[l] = -INFINITY;
+      for (int l = 0; l < LQ; ++l) {
+        if ((dead >> l) & 1u) sc[l] = -INFINITY;
+        mx = fmaxf(mx, sc[l]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int l = 0; l < LQ; ++l) {
+        sc[l] = exp2f((sc[l] - mx) * 1.4426950408889634f);
+        sum += sc[l];
+      }
+      const float inv = 1.f / sum;
+      float* arow = attn + (long long)b * L * Q + (q0 + t);
+#pragma unroll
+      for (int l = 0; l < LQ; ++l) {
+        sc[l] *= inv;
+        if (l < L) *arow = sc[l];
+        arow += Q;
+      }
     }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int l = 0; l < LQ; ++l)
-      if (l < L) mx = fmaxf(mx, sc[l]);
-    float sum = 0.f;
-#pragma unroll
-    for (int l = 0; l < LQ; ++l) {
-      sc[l] = l < L ? expf(sc[l] - mx) : 0.f;
-      sum += sc[l];
-    }
-    const float inv = 1.f / sum;
-    float* arow = attn + (long long)b * L * Q + q;
-#pragma unroll
-    for (int l = 0; l < LQ; ++l) {
-      sc[l] *= inv;
-      if (l < L) arow[(long long)l * Q] = sc[l];
-    }
-    // probabilities -> the three A copies (row t, K = 32: four 16-byte chunks per copy; words >= LQ are zeros)
+    // probabilities * 2^13 -> the two A copies (row t, K = 32: four 16-byte chunks per copy; words >= LQ are zeros)
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
-      uint32_t y1[4], y2[4], y3[4];
+      uint32_t yh[4], yl[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int l0 = ch * 8 + 2 * e;
-        Split3 u = {0u, 0u, 0u}, w = {0u, 0u, 0u};
-        if (l0 < LQ) u = at_split3(sc[l0 < LQ ? l0 : 0]);
-        if (l0 + 1 < LQ) w = at_split3(sc[l0 + 1 < LQ ? l0 + 1 : 0]);
-        y1[e] = at_pack_hi(u.w1, w.w1); y2[e] = at_pack_hi(u.w2, w.w2); y3[e] = at_pack_hi(u.w3, w.w3);
+        float ha = 0.f, la = 0.f, hb = 0.f, lb = 0.f;
+        if (l0 < LQ) at_hilo(sc[l0 < LQ ? l0 : 0] * (float)(1 << AT_PSCALE), ha, la);
+        if (l0 + 1 < LQ) at_hilo(sc[l0 + 1 < LQ ? l0 + 1 : 0] * (float)(1 << AT_PSCALE), hb, lb);
+        yh[e] = at_cvt2(ha, hb);
+        yl[e] = at_cvt2(la, lb);
       }
       const uint32_t addr = rowP + (uint32_t)(((ch ^ (t & 7)) & 7) << 4);
-      at_sts128(addr, y1[0], y1[1], y1[2], y1[3]);
-      at_sts128(addr + AT_A_BYTES, y2[0], y2[1], y2[2], y2[3]);
-      at_sts128(addr + 2 * AT_A_BYTES, y3[0], y3[1], y3[2], y3[3]);
+      at_sts128(addr, yh[0], yh[1], yh[2], yh[3]);
+      at_sts128(addr + AT_A_BYTES, yl[0], yl[1], yl[2], yl[3]);
     }
     at_fence_proxy_async();
     at_tc_fence_before();
@@ -365,21 +396,26 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
     // ---------------- (3) context rows: TMEM -> shared staging -> coalesced stores ----------------
     at_mbar_wait(&bar_o, phase);
     at_tc_fence_after();
-    uint32_t o0[32], o1[16];
-    at_tmem_ld32(tmem_row + 32, o0);
-    at_tmem_ld16(tmem_row + 64, o1);
-    at_tmem_ld_wait();
-    // MMA 2 has completed: the A copies are free and take the staged context rows
+    // MMA 2 has completed: the A copies are free and take the staged context rows, 16 columns at a time
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) at_sts128(rowS + j * 4, o0[j], o0[j + 1], o0[j + 2], o0[j + 3]);
+    for (int cb = 0; cb < AT_C; cb += 16) {
+      uint32_t o[16];
+      at_tmem_ld16(tmem_row + 32 + cb, o);
+      at_tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) at_sts128(rowS + (32 + j) * 4, o1[j], o1[j + 1], o1[j + 2], o1[j + 3]);
+      for (int j = 0; j < 16; j += 4)
+        at_sts128(rowS + (cb + j) * 4, __float_as_uint(__uint_as_float(o[j]) * so), __float_as_uint(__uint_as_float(o[j + 1]) * so),
+                  __float_as_uint(__uint_as_float(o[j + 2]) * so), __float_as_uint(__uint_as_float(o[j + 3]) * so));
+    }
     at_tc_fence_before();
     __syncthreads();
     {
-      float4* op = reinterpret_cast<float4*>(wc + ((long long)b * Q + q0) * AT_C);
+      float4* op = reinterpret_cast<float4*>(wc + ((long long)b * Q + q0) * AT_C) + warp * 384 + lane;
 #pragma unroll
-      for (int j = 0; j < 12; ++j) op[t + j * AT_Q] = at_lds128(sA + offS[j]);
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          op[g * 96 + j * 32] = at_lds128(sA + offS[j] + (uint32_t)(g * 8 * AT_STAGE_PITCH * 4));
     }
     __syncthreads();                                     // staging drained before the next trip overwrites the A copies
   }
@@ -398,10 +434,10 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
 extern "C" int og_att_general_fwd_tc(const float* h, const float* src, const unsigned char* mask, int B, int Q, int idf,
                                      int cs, int L, float* wc, float* attn, cudaStream_t stream) {
   if (idf != AT_C || cs != AT_C || L < 1 || L > AT_LP || Q % AT_Q != 0 || Q < AT_Q || B < 1 ||
-      (long long)B * Q >= (1LL << 31))
+      (long long)B * Q >= (1LL << 31) || B > AT_MAXB)
     return -1;
   const int ntiles = Q / AT_Q;
-  int nslots = (2 * 148) / B;          // two CTAs per SM, every CTA stays inside one image
+  int nslots = (4 * 148) / B;          // four CTAs per SM, every CTA stays inside one image
   if (nslots < 1) nslots = 1;
   if (nslots > ntiles) nslots = ntiles;
   const size_t smem = AT_SMEM + 1024;
