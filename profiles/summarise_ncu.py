@@ -63,7 +63,7 @@ def main(reps):
             k, r["dur_us"], r.get("rd", 0) / 1e6, r.get("wr", 0) / 1e6, gbs, gbs / HBM,
             ("%.0f %%" % r["tensor"]) if r.get("tensor", 0) > 0.5 else "-", r.get("issue", 0), int(r.get("regs", 0)), r["rep"]))
         traffic[k] = {"dram_bytes": byt, "duration_us": r["dur_us"], "source": "profiles/" + r["rep"]}
-    alias = {"conv_tc2_res3_conv1": "conv_tcp_kernel<208, 1> #0", "att_general_fwd": "att_general_fwd_reg_kernel<4> #1"}
+    alias = {"conv_tc2_res3_conv1": "conv_tcp_kernel<208, 1> #0", "att_general_fwd": "att_general_fwd_tc_kernel<20> #1"}
     for a, k in alias.items():
         if k in traffic:
             traffic[a] = traffic[k]
