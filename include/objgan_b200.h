@@ -138,6 +138,15 @@ int og_norm_stats(const float* x, int groups, long long P, int C, float eps, dou
 int og_norm_apply(const float* y, int groups, long long P, int Cy, const float* mean, const float* rstd,
                   const float* gamma, const float* beta, const float* res, int act, float slope, float* out,
                   unsigned* amax_out, cudaStream_t stream);
+/* og_norm_apply that also emits the fp16 hi / lo tensor-core operand copies of its output (what og_prep_split would
+ * make of it, optionally with the reflection halo), scaled by the a-priori bound og_norm_bound leaves in bound_word;
+ * out (fp32) may be null when nothing else reads the activation */
+int og_norm_bound(const float* gamma, const float* beta, int C, long long count, const unsigned* res_word,
+                  unsigned* out_word, cudaStream_t stream);
+int og_norm_apply_split(const float* y, int N, int H, int W, int Cy, int instance, const float* mean,
+                        const float* rstd, const float* gamma, const float* beta, const float* res, int act,
+                        float slope, float* out, const unsigned* bound_word, int pad, void* xh, void* xl,
+                        cudaStream_t stream);
 int og_norm_backward(const float* y, const float* g, int groups, long long P, int Cy, const float* mean,
                      const float* rstd, const float* gamma, const float* beta, int act, float slope, double* bstats,
                      float* dy, float* dgamma, float* dbeta, int accumulate_param_grads, unsigned* amax_dy,

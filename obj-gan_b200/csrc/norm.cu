@@ -13,6 +13,7 @@
 // Layout: contiguous NHWC, rows = pixels, C % 4 == 0.  "groups" = N for instance norm, 1 for batch norm;
 // each group covers P pixels (H*W, resp. N*H*W).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 // grid: (ceil(C4/32), chunks, groups)   block: (32, 8)
 // A thread owns one channel quad and walks the rows p0 + ty, p0 + ty + 8, ...: four rows are loaded back to back (four
@@ -388,6 +389,108 @@ __global__ void norm_param_grad_kernel(const double* __restrict__ bstats, int C,
   dbeta[i] = accumulate ? dbeta[i] + db : db;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forward apply that ALSO emits the tensor-core operand copies of its output (what og_prep_split would make of it):
+// fp16 hi / lo of out * 2^k, optionally with the ReflectionPad2d(1) halo of the consuming convolution.  The scale has to
+// be known before the pass, so it comes from an a-priori bound of max|out| (og_norm_bound): a normalised value is at
+// most sqrt(P - 1) in magnitude (biased variance over P values), so |out| <= max|gamma| sqrt(P) + max|beta| (+ the
+// bound of the residual) whatever the data -- any upper bound is a valid operand scale, it only positions the 22-bit
+// window (an element 2^-18 below the BOUND keeps all 22 bits; typical activations sit 2^-7 .. 2^-10 below it).
+// The walk is over the DESTINATION grid [N][H + 2 pad][W + 2 pad][C / 8] (a halo position recomputes its source
+// pixel: ~3 % more reads at 128^2); the fp32 output, when asked for, is written from the interior positions.
+// ------------------------------------------------------------------------------------------------
+__global__ void norm_bound_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, int C, double count,
+                                  const unsigned* __restrict__ res_word, unsigned* __restrict__ out_word) {
+  float mg = gamma ? 0.f : 1.f, mb = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    if (gamma) mg = fmaxf(mg, fabsf(gamma[i]));
+    if (beta) mb = fmaxf(mb, fabsf(beta[i]));
+  }
+  __shared__ float sg[8], sb[8];
+  mg = warp_max(mg);
+  mb = warp_max(mb);
+  if ((threadIdx.x & 31) == 0) { sg[threadIdx.x >> 5] = mg; sb[threadIdx.x >> 5] = mb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) { mg = fmaxf(mg, sg[i]); mb = fmaxf(mb, sb[i]); }
+    float bound = mg * (float)(sqrt(count) * 1.001) + mb;
+    if (res_word) bound += __uint_as_float(*res_word & 0x7fffffffu);
+    *out_word = __float_as_uint(bound);
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256) norm_apply_split_kernel(
+    const float* __restrict__ y, int N, int H, int W, int Cy, int instance, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ res, float slope, float* __restrict__ out, const unsigned* __restrict__ bound_word,
+    int pad, long long total, __half* __restrict__ xh, __half* __restrict__ xl) {
+  const int Co = (ACT == OG_NA_GLU) ? Cy / 2 : Cy;
+  const int C8 = Co >> 3;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const float scale = og_exp2i(og_scale_exp(__ldg(bound_word)));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    long long t = i / C8;
+    const int w = (int)(t % Wp);
+    t /= Wp;
+    const int h = (int)(t % Hp);
+    const long long n = t / Hp;
+    int sh = h - pad, sw = w - pad;
+    const bool interior = sh >= 0 && sh < H && sw >= 0 && sw < W;
+    if (sh < 0) sh = -sh;
+    if (sh >= H) sh = 2 * H - 2 - sh;
+    if (sw < 0) sw = -sw;
+    if (sw >= W) sw = 2 * W - 2 - sw;
+    const long long p = (n * H + sh) * W + sw;
+    const long long g = instance ? n : 0;
+    const float* yp = y + p * Cy + c;
+    const float* mrow = mean + g * Cy + c;
+    const float* rrow = rstd + g * Cy + c;
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 v = ldg4(yp + 4 * q), m = ldg4(mrow + 4 * q), r = ldg4(rrow + 4 * q);
+      const float4 ga = gamma ? ldg4(gamma + c + 4 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float4 be = beta ? ldg4(beta + c + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float a[4] = {(v.x - m.x) * r.x * ga.x + be.x, (v.y - m.y) * r.y * ga.y + be.y,
+                    (v.z - m.z) * r.z * ga.z + be.z, (v.w - m.w) * r.w * ga.w + be.w};
+      if (ACT == OG_NA_GLU) {
+        const float4 v2 = ldg4(yp + Co + 4 * q), m2 = ldg4(mrow + Co + 4 * q), r2 = ldg4(rrow + Co + 4 * q);
+        const float4 ga2 = gamma ? ldg4(gamma + Co + c + 4 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 be2 = beta ? ldg4(beta + Co + c + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a[0] *= sigmoid_fast((v2.x - m2.x) * r2.x * ga2.x + be2.x);
+        a[1] *= sigmoid_fast((v2.y - m2.y) * r2.y * ga2.y + be2.y);
+        a[2] *= sigmoid_fast((v2.z - m2.z) * r2.z * ga2.z + be2.z);
+        a[3] *= sigmoid_fast((v2.w - m2.w) * r2.w * ga2.w + be2.w);
+      } else if (ACT == OG_NA_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = a[j] > 0.f ? a[j] : a[j] * slope;
+      }
+      if (res) {
+        const float4 rr = ldg4(res + p * Co + c + 4 * q);
+        a[0] += rr.x; a[1] += rr.y; a[2] += rr.z; a[3] += rr.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[4 * q + j] = a[j];
+    }
+    if (out && interior) {
+      st4(out + p * Co + c, make_float4(o[0], o[1], o[2], o[3]));
+      st4(out + p * Co + c + 4, make_float4(o[4], o[5], o[6], o[7]));
+    }
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = o[j] * scale;
+      hi[j] = __float2half_rn(v);
+      lo[j] = __float2half_rn(v - __half2float(hi[j]));
+    }
+    *reinterpret_cast<uint4*>(xh + i * 8) = *reinterpret_cast<const uint4*>(hi);
+    if (xl) *reinterpret_cast<uint4*>(xl + i * 8) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 static int elem_blocks(long long total) {
   long long b = (total + 255) / 256;
   long long cap = 148LL * 32;
@@ -463,5 +566,36 @@ OG_API int og_norm_backward(const float* y, const float* g, int groups, long lon
     OG_LAUNCH_BWD(OG_NA_NONE)
   }
 #undef OG_LAUNCH_BWD
+  OG_RETURN_LAST_ERROR();
+}
+
+// *out_word = float bits of an upper bound of max|og_norm_apply output| (see norm_apply_split_kernel): max|gamma| *
+// sqrt(count) + max|beta| (+ the bound / amax word of the residual).  gamma / beta null = InstanceNorm without affine.
+OG_API int og_norm_bound(const float* gamma, const float* beta, int C, long long count, const unsigned* res_word,
+                         unsigned* out_word, cudaStream_t stream) {
+  norm_bound_kernel<<<1, 256, 0, stream>>>(gamma, beta, C, (double)count, res_word, out_word);
+  OG_RETURN_LAST_ERROR();
+}
+
+// og_norm_apply fused with og_prep_split of its output: y [N][H][W][Cy] -> fp16 hi / lo [N][H + 2 pad][W + 2 pad][Co]
+// scaled by the power of two of *bound_word (og_norm_bound), pad = 1 adds the reflection halo; out (fp32, [N][H][W][Co])
+// may be null when nothing else reads the activation; xl may be null (single-product mode).
+OG_API int og_norm_apply_split(const float* y, int N, int H, int W, int Cy, int instance, const float* mean,
+                               const float* rstd, const float* gamma, const float* beta, const float* res, int act,
+                               float slope, float* out, const unsigned* bound_word, int pad, void* xh, void* xl,
+                               cudaStream_t stream) {
+  const int Co = act == OG_NA_GLU ? Cy / 2 : Cy;
+  if (Co % 8 || pad < 0 || pad > 1 || (pad && (H < 2 || W < 2))) return (int)cudaErrorInvalidValue;
+  const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad) * (Co / 8);
+  if (total == 0) return 0;
+  long long b = (total + 255) / 256;
+  if (b > 148LL * 32) b = 148LL * 32;
+#define OG_LAUNCH_AS(A)                                                                                              \
+  norm_apply_split_kernel<A><<<(int)b, 256, 0, stream>>>(y, N, H, W, Cy, instance, mean, rstd, gamma, beta, res, slope, \
+                                                         out, bound_word, pad, total, (__half*)xh, (__half*)xl)
+  if (act == OG_NA_GLU) OG_LAUNCH_AS(OG_NA_GLU);
+  else if (act == OG_NA_LRELU) OG_LAUNCH_AS(OG_NA_LRELU);
+  else OG_LAUNCH_AS(OG_NA_NONE);
+#undef OG_LAUNCH_AS
   OG_RETURN_LAST_ERROR();
 }

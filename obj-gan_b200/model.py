@@ -164,9 +164,24 @@ class HmapResBlock(nn.Module):
         self.block = _Slots(_1=Conv2dP(c, 2 * c, 3, 1, 1, mode=PAD_REFLECT, split=c),
                             _5=Conv2dP(c, c, 3, 1, 1, mode=PAD_REFLECT))
 
+    next_pad = None      # set by the owner: halo (1 / 0) of the convolution that consumes this block's output
+
     def forward(self, x):  # NHWC
-        y = ops.instance_norm_act(self.block[1](x), NA_GLU)
-        return ops.instance_norm_act(self.block[5](y), NA_NONE, res=x)
+        # the GLU output is read by block.5 only: it is written directly as that convolution's fp16 operand copies
+        # (reflection halo included) and never as fp32; the block output goes out as fp32 (the next residual add reads
+        # it) plus, when the owner said what consumes it, the operand copies of that convolution
+        y = ops.instance_norm_act(self.block[1](x), NA_GLU, split_pad=1, keep_f32=False)
+        return ops.instance_norm_act(self.block[5](y), NA_NONE, res=x, split_pad=self.next_pad)
+
+
+def _chain_res_blocks(blocks, last_pad):
+    """Tell every block of a residual chain which operand layout its consumer wants: the next block's reflection-padded
+    conv (halo 1), or ``last_pad`` for what follows the chain."""
+    blocks = list(blocks)
+    for b in blocks[:-1]:
+        b.next_pad = 1
+    if blocks:
+        blocks[-1].next_pad = last_pad
 
 
 class CA_NET(_Base):
@@ -333,6 +348,7 @@ class INIT_STAGE_G_MAIN(_Base):
         c = ngf * 3 + nef2
         self.residual = nn.Sequential(*[HmapResBlock(c) for _ in range(cfg.GAN.GLB_R_NUM)])
         self.upsample = upBlock(c, ngf)
+        _chain_res_blocks(self.residual, 0)          # the upsample conv reads the plain (halo-free) operand copies
 
     def forward_nhwc(self, h_code_hmap, h_code1_sent, word_embs, glove_word_embs, slabels_feat, mask, bt_mask):
         ngf = self.gf_dim
@@ -363,6 +379,7 @@ class NEXT_STAGE_G_MAIN(_Base):
         c = ngf * 3 + nef2
         self.residual = nn.Sequential(*[HmapResBlock(c) for _ in range(cfg.GAN.LOCAL_R_NUM)])
         self.upsample = upBlock(c, ngf)
+        _chain_res_blocks(self.residual, 0)
 
     def forward_nhwc(self, h_code, h_code_hmap, word_embs, glove_word_embs, slabels_feat, mask, bt_mask,
                      glb_max_num_roi):

@@ -194,6 +194,7 @@ CONV_ENGINE = _os.environ.get("OBJGAN_CONV", "f16x3")
 TC_WGRAD = _os.environ.get("OBJGAN_TC_WGRAD", "1") == "1"
 FUSED_AMAX = _os.environ.get("OBJGAN_FUSED_AMAX", "1") == "1"   # producers leave max|x| for the consuming conv
 KEEP_SPLIT = _os.environ.get("OBJGAN_KEEP_SPLIT", "1") == "1"   # keep x's hi/lo copies from forward for the wgrad
+FUSED_SPLIT = _os.environ.get("OBJGAN_FUSED_SPLIT", "1") == "1"  # norm-apply emits the consumer conv's hi/lo operand copies
 TC_MIN_PIXELS = 256        # smaller problems go to the exact-fp32 SIMT kernels (the tc kernel splits K on small maps)
 
 
@@ -220,6 +221,12 @@ def _split(x, pad=0, s2d=False):
     """(fp16 hi, fp16 lo, scale word) of an NHWC tensor scaled by a power of two from its max|x|; pad=1 adds the
     reflection halo; s2d gives [4N, H/2, W/2, C]."""
     n, h, w, c = x.shape
+    ready_made = getattr(x, "og_split", None)          # the producer already wrote them (og_norm_apply_split)
+    if ready_made is not None and ready_made[3:] == (pad, bool(s2d), x._version, _nsplit()):
+        return ready_made[:3]
+    if getattr(x, "og_f32_invalid", False):
+        raise RuntimeError("this activation exists only as tensor-core operand copies (pad=%s); a consumer asked for "
+                           "another layout" % (ready_made[3] if ready_made else None))
     shape = (4 * n, h // 2, w // 2, c) if s2d else (n, h + 2 * pad, w + 2 * pad, c)
     xh = _empty_slack(shape, x.device)
     xl = _empty_slack(shape, x.device) if CONV_ENGINE == "f16x3" else None
@@ -493,10 +500,14 @@ class _Conv2d(torch.autograd.Function):
                 bias_p = torch.zeros(kp, device=x.device, dtype=torch.float32)
                 bias_p[:co] = bias.detach()
         narrow = kind is None and kp == 8 and mode == PAD_ZERO and n * oh * ow <= 65536
+        f32_missing = getattr(x, "og_f32_invalid", False)
+        if f32_missing and not kind:
+            raise RuntimeError("input exists only as tensor-core operand copies, but this convolution runs on the CUDA cores")
         xs = None
         if kind:
             y, xs = _tc_fprop(kind, x, cache, weight, kp, split, splitp, mode, bias_p, act)
-            if not (KEEP_SPLIT and ctx.needs_input_grad[1] and TC_WGRAD and _tc_wgrad_ok(kind, mode, n, oh, ow)):
+            if not (KEEP_SPLIT and ctx.needs_input_grad[1] and TC_WGRAD and _tc_wgrad_ok(kind, mode, n, oh, ow)) \
+                    and not f32_missing:
                 xs = None
         elif narrow:
             wf, _ = cache.get(weight, c, kp, split, splitp, False)
@@ -595,7 +606,7 @@ class _NormAct(torch.autograd.Function):
     """InstanceNorm2d (groups = N) or train-mode BatchNorm (groups = 1) + fused activation (+ residual)."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, res, bn_buffers, instance, act):
+    def forward(ctx, y, gamma, beta, res, bn_buffers, instance, act, split_pad=None, keep_f32=True):
         _chk(y, gamma, beta, res)
         y = y.contiguous()
         n, h, w, cy = y.shape
@@ -616,8 +627,24 @@ class _NormAct(torch.autograd.Function):
         if res is not None:
             res = res.contiguous()
             assert res.shape == out.shape
-        _call("og_norm_apply", _p(y), groups, P, cy, _p(mean), _p(rstd), _p(gamma), _p(beta), _p(res), act,
-              LRELU_SLOPE, _p(out), _p(_tag_amax(out)))
+        fused = (split_pad is not None and FUSED_SPLIT and CONV_ENGINE in ("f16x3", "f16") and not _lib.DRY_RUN
+                 and (res is None or _known_amax(res) is not None) and (split_pad == 0 or (h > 1 and w > 1)))
+        if fused:
+            # the consuming convolution's operand copies straight from this pass, scaled by an a-priori bound of max|out|
+            word = torch.empty(1, device=dev, dtype=torch.int32)
+            _call("og_norm_bound", _p(gamma), _p(beta), cy if gamma is not None else 0, P,
+                  _p(_known_amax(res)) if res is not None else 0, _p(word))
+            xh = _empty_slack((n, h + 2 * split_pad, w + 2 * split_pad, co), dev)
+            xl = _empty_slack((n, h + 2 * split_pad, w + 2 * split_pad, co), dev) if CONV_ENGINE == "f16x3" else None
+            _call("og_norm_apply_split", _p(y), n, h, w, cy, 1 if instance else 0, _p(mean), _p(rstd), _p(gamma),
+                  _p(beta), _p(res), act, LRELU_SLOPE, _p(out) if keep_f32 else 0, _p(word), split_pad, _p(xh), _p(xl))
+            out.og_amax = (word, out._version)          # an upper bound is a valid operand scale for other consumers
+            out.og_split = (xh, xl, word, split_pad, False, out._version, _nsplit())
+            if not keep_f32:
+                out.og_f32_invalid = True               # nothing may read the fp32 tensor: it was never written
+        else:
+            _call("og_norm_apply", _p(y), groups, P, cy, _p(mean), _p(rstd), _p(gamma), _p(beta), _p(res), act,
+                  LRELU_SLOPE, _p(out), _p(_tag_amax(out)))
         ctx.cfg = (groups, P, cy, act, res is not None)
         ctx.sinks = (_grad_sink(gamma), _grad_sink(beta)) if gamma is not None else (None, None)
         ctx.save_for_backward(y, mean, rstd, gamma, beta)
@@ -642,11 +669,14 @@ class _NormAct(torch.autograd.Function):
               LRELU_SLOPE, _p(bstats), _p(dy), _p(dgamma), _p(dbeta), 1 if direct else 0, _p(_tag_amax(dy)))
         if direct:
             dgamma = dbeta = None
-        return dy, dgamma, dbeta, (g if has_res else None), None, None, None
+        return dy, dgamma, dbeta, (g if has_res else None), None, None, None, None, None
 
 
-def instance_norm_act(y, act, res=None):
-    return _NormAct.apply(y, None, None, res, None, True, act)
+def instance_norm_act(y, act, res=None, split_pad=None, keep_f32=True):
+    """``split_pad`` (0 / 1): also emit the fp16 hi / lo operand copies the NEXT convolution needs (plain / with the
+    reflection halo), so that convolution skips its split pass; ``keep_f32=False``: the fp32 tensor is not written at
+    all (only valid when that convolution is the ONLY reader and runs on the tensor cores)."""
+    return _NormAct.apply(y, None, None, res, None, True, act, split_pad, keep_f32)
 
 
 def batch_norm_act(y, gamma, beta, buffers, act):

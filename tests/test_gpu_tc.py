@@ -187,3 +187,37 @@ def test_persistent_cta_pair_kernel_all_tile_widths():
                        env=env, capture_output=True, text=True, timeout=900,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("engine", ["f16x3", "f16"])
+def test_norm_apply_emits_operand_copies(engine, monkeypatch):
+    """A chain of residual blocks + upBlock with the producer-side operand split (og_norm_apply_split: the normalisation
+    pass writes the next convolution's fp16 hi / lo copies, reflection halo included, scaled by an a-priori bound) against
+    the same chain with separate og_norm_apply + og_prep_split passes: outputs and all gradients agree to fp32
+    rounding level (the two differ only in the power of two the operands are scaled by)."""
+    monkeypatch.setattr(ops, "CONV_ENGINE", engine)
+    torch.manual_seed(3)
+    c = 194
+    blocks = torch.nn.Sequential(*[model.HmapResBlock(c) for _ in range(3)]).to(DEV)
+    up = model.upBlock(c, 48).to(DEV)
+    model._chain_res_blocks(blocks, 0)
+    x0 = torch.randn(2, 32, 32, ops.cpad(c), device=DEV)
+    x0[..., c:] = 0
+    res = {}
+    for fused in (False, True, False):     # the first pass also packs the weights: only the last two are compared / counted
+        monkeypatch.setattr(ops, "FUSED_SPLIT", fused)
+        calls0 = ops._lib.get().launches
+        x = x0.clone().requires_grad_(True)
+        for p_ in list(blocks.parameters()) + list(up.parameters()):
+            p_.grad = None
+        out = up(blocks(x))
+        gout = torch.ones_like(out) * torch.linspace(-1, 1, out.shape[-1], device=DEV)
+        out.backward(gout)
+        res[fused] = (out.detach().clone(), x.grad.clone(), [p_.grad.clone() for p_ in blocks.parameters()],
+                      ops._lib.get().launches - calls0)
+    tol = 1e-5 if engine == "f16x3" else 4e-3
+    assert _rel(res[True][0], res[False][0]) <= tol
+    assert _rel(res[True][1], res[False][1]) <= 10 * tol
+    for a, b in zip(res[True][2], res[False][2]):
+        assert _rel(a, b) <= 10 * tol
+    assert res[True][3] < res[False][3]            # fewer library calls: the split passes are gone
