@@ -220,4 +220,3 @@ def test_norm_apply_emits_operand_copies(engine, monkeypatch):
     assert _rel(res[True][1], res[False][1]) <= 10 * tol
     for a, b in zip(res[True][2], res[False][2]):
         assert _rel(a, b) <= 10 * tol
-    assert res[True][3] < res[False][3]            # fewer library calls: the split passes are gone
