@@ -642,12 +642,20 @@ att_general_bwd20_kernel(const float* __restrict__ h, const float* __restrict__ 
   }
 }
 
+extern "C" int og_att_general_bwd_tc(const float* h, const float* src, const float* attn, const float* g_wc, int B, int Q,
+                                     int idf, int cs, int L, float* g_h, float* g_src, cudaStream_t stream);
+
 OG_API int og_att_general_bwd(const float* h, const float* src, const float* attn, const float* g_wc,
                               const float* g_attn, int B, int Q, int idf, int cs, int L, float* g_h, float* g_src,
                               cudaStream_t stream) {
   if (L > LMAX || cs % 4 || idf > cs) return (int)cudaErrorInvalidValue;
   OG_CHECK(cudaMemsetAsync(g_src, 0, sizeof(float) * (size_t)B * idf * L, stream));
   if (B == 0 || Q == 0) return 0;
+  static const int bwd_tc = getenv("OG_ATT_TC_BWD") ? atoi(getenv("OG_ATT_TC_BWD")) : 1;
+  if (bwd_tc && !g_attn && Q >= 4096) {
+    const int rc = og_att_general_bwd_tc(h, src, attn, g_wc, B, Q, idf, cs, L, g_h, g_src, stream);
+    if (rc >= 0) return rc;
+  }
   static const bool old_bwd = getenv("OG_ATT_OLD_BWD") != nullptr;
   if (!old_bwd && L <= 20 && idf <= 64) {
     const size_t sm20 = sizeof(float) * ((size_t)idf * 20 + 2 * ATT_Q * 20 + 2 * (size_t)ATT_Q * (cs + 1));

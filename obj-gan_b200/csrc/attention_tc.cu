@@ -429,6 +429,332 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward (g_attn = null: the attention maps are only visualised in training).  Per query q:
+//   gP[l]   = sum_c g_wc[q][c] src[c][l]                          MMA 1:  Gw (128 x 48)   . B1           -> TMEM [0, 32)
+//   gS[l]   = P[l] (gP[l] - sum_l' P[l'] gP[l'])                  registers (P read from the saved attention map)
+//   g_h[c]  = sum_l gS[l] src[c][l]                               MMA 2:  gS (128 x 32)   . B2           -> TMEM [32, 80)
+//   g_src[c][l] += sum_q g_wc[q][c] P[q][l] + h[q][c] gS[q][l]    MMA 3a: Gw^T . P, 3b: H^T . gS  (contraction over the
+//       tile's 128 queries: the SAME shared-memory tiles read as MN-major operands, ref. conv_tc.cu make_desc_mn: a
+//       slab = 128 query rows x 64 elements, k-step = 16 rows = 2048 bytes)                              -> TMEM [80, 112), [112, 144)
+// The two g_src terms carry different operand scales, so each tile's pair of 48 x 32 results is read back, rescaled and
+// summed in registers (thread c < 48 owns row c); one atomicAdd per (c, l) per CTA at the end.  M = 128 for MMA 3: the
+// second 64-row slab of the A operand is whatever tile follows in shared memory -- rows 64..127 (and the pad rows
+// 48..63) of the result are never read.
+// Shared memory: X = {Gw, then H} hi / lo, Y = {P, then gS} hi / lo, B1, B2: 84 KB, two CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t at_desc_mn(uint32_t saddr, uint32_t slab_pitch) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(slab_pitch >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// D (+)= A^T-style contraction over the 128 rows of two MN-major tiles: 8 k-steps x (lo*hi, hi*lo, hi*hi)
+__device__ __forceinline__ void at_issue_mn(uint32_t d_tmem, const uint64_t (&a)[2], const uint64_t (&b)[2], uint32_t idesc) {
+  for (int k = 0; k < AT_Q / 16; ++k) {
+    const uint64_t koff = (uint64_t)((k * 2048) >> 4);
+    at_umma(d_tmem, a[1] + koff, b[0] + koff, idesc, k > 0 ? 1u : 0u);
+    at_umma(d_tmem, a[0] + koff, b[1] + koff, idesc, 1u);
+    at_umma(d_tmem, a[0] + koff, b[0] + koff, idesc, 1u);
+  }
+}
+// two CTA-wide maxima at once
+__device__ __forceinline__ void at_cta_max2(float& m0, float& m1, float (*scratch)[4]) {
+  m0 = warp_max(m0);
+  m1 = warp_max(m1);
+  if ((threadIdx.x & 31) == 0) { scratch[0][threadIdx.x >> 5] = m0; scratch[1][threadIdx.x >> 5] = m1; }
+  __syncthreads();
+  m0 = fmaxf(fmaxf(scratch[0][0], scratch[0][1]), fmaxf(scratch[0][2], scratch[0][3]));
+  m1 = fmaxf(fmaxf(scratch[1][0], scratch[1][1]), fmaxf(scratch[1][2], scratch[1][3]));
+}
+
+template <int LQ>
+__global__ void __launch_bounds__(AT_Q, 2)
+att_general_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ src, const float* __restrict__ attn,
+                          const float* __restrict__ g_wc, int B, int Q, int L, int nslots, float* __restrict__ g_h,
+                          float* __restrict__ g_src) {
+  extern __shared__ uint8_t at_smem_raw[];
+  const uint32_t smem = (at_smem_u32(at_smem_raw) + 1023u) & ~1023u;
+  const uint32_t sX = smem;                            // Gw, then H (hi, lo); finally the staged g_h rows
+  const uint32_t sY = smem + 2 * AT_A_BYTES;           // P, then gS (hi, lo)
+  const uint32_t sB1 = sY + 2 * AT_A_BYTES;
+  const uint32_t sB2 = sB1 + 2 * AT_B1_BYTES;
+  __shared__ __align__(8) uint64_t bar1, bar2;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float red[4][4];
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int b = blockIdx.x / nslots, slot = blockIdx.x - b * nslots;
+  const int ntiles = Q / AT_Q;
+
+  if (t == 0) {
+    at_mbar_init(&bar1, 1);
+    at_mbar_init(&bar2, 1);
+    at_fence_barrier_init();
+  }
+  if (warp == 0) at_tmem_alloc(&tmem_base_smem, 256);
+  uint32_t offA[3], offS[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int f = j * 32 + lane, r8 = (f * 43691) >> 19, c8 = f - r8 * 12;
+    offA[j] = (uint32_t)(warp * 4 * 1024) + at_sw_off(r8, c8 * 4);
+    offS[j] = (uint32_t)(((warp * 32 + r8) * AT_STAGE_PITCH + c8 * 4) * 4);
+  }
+  // word projections of this image -> B1[l][c], B2[c][l] (as in the forward kernel)
+  int ksrc;
+  {
+    const float* sb = src + (long long)b * AT_C * L;
+    const int l = lane, c0 = warp;
+    float v[12];
+    float m = 0.f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      v[j] = l < L ? __ldg(sb + (c0 + 4 * j) * L + l) : 0.f;
+      m = fmaxf(m, fabsf(v[j]));
+    }
+    m = at_cta_max(m, red[0]);
+    ksrc = og_scale_exp(__float_as_uint(m));
+    const float s = og_exp2i(ksrc);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const int c = c0 + 4 * j;
+      float hi, lo;
+      at_hilo(v[j] * s, hi, lo);
+      const uint32_t pk = at_cvt2(hi, lo);
+      const uint32_t o1 = at_sw_off(l, c), o2 = at_sw_off(c, l);
+      at_sts16(sB1 + o1, pk & 0xFFFFu);
+      at_sts16(sB1 + AT_B1_BYTES + o1, pk >> 16);
+      at_sts16(sB2 + o2, pk & 0xFFFFu);
+      at_sts16(sB2 + AT_B2_BYTES + o2, pk >> 16);
+    }
+  }
+  at_tc_fence_before();
+  __syncthreads();
+  at_tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+
+  uint64_t dX[2], dY[2], dB1[2], dB2[2], dXmn[2], dYmn[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    dX[i] = at_desc_sw128(sX + i * AT_A_BYTES);
+    dY[i] = at_desc_sw128(sY + i * AT_A_BYTES);
+    dB1[i] = at_desc_sw128(sB1 + i * AT_B1_BYTES);
+    dB2[i] = at_desc_sw128(sB2 + i * AT_B2_BYTES);
+    dXmn[i] = at_desc_mn(sX + i * AT_A_BYTES, AT_A_BYTES);
+    dYmn[i] = at_desc_mn(sY + i * AT_A_BYTES, AT_A_BYTES);
+  }
+  const uint32_t idesc1 = at_idesc_f16(128, AT_LP), idesc2 = at_idesc_f16(128, AT_C);
+  const uint32_t idesc3 = at_idesc_f16(128, AT_LP) | (1u << 15) | (1u << 16);      // both operands MN-major
+  const uint32_t rowY = sY + (uint32_t)((t >> 3) * 1024 + (t & 7) * 128);
+  const uint32_t rowS = sX + (uint32_t)(t * AT_STAGE_PITCH) * 4u;
+  const float ss2 = og_exp2i(-ksrc);
+
+  float gacc[LQ];                                      // g_src[c = t][l], summed over this CTA's tiles
+#pragma unroll
+  for (int l = 0; l < LQ; ++l) gacc[l] = 0.f;
+
+  uint32_t phase = 0;
+  for (int qt = slot; qt < ntiles; qt += nslots, phase ^= 1) {
+    const int q0 = qt * AT_Q;
+    const long long tile = ((long long)b * Q + q0) * AT_C;
+    // ---- loads of the tile: g_wc and h (coalesced float4), the saved probabilities of this thread's query ----
+    float4 gw[12], hh[12];
+    {
+      const float4* gp = reinterpret_cast<const float4*>(g_wc + tile) + warp * 384 + lane;
+      const float4* hp = reinterpret_cast<const float4*>(h + tile) + warp * 384 + lane;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) gw[i] = __ldg(gp + i * 32);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) hh[i] = __ldg(hp + i * 32);
+    }
+    float pr[LQ];
+    {
+      const float* arow = attn + (long long)b * L * Q + (q0 + t);
+#pragma unroll
+      for (int l = 0; l < LQ; ++l) {
+        pr[l] = l < L ? __ldg(arow) : 0.f;
+        arow += Q;
+      }
+    }
+    // ---- (1) Gw -> X, P -> Y ----
+    float mg = 0.f, mh = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { mg = at_amax4(mg, gw[i]); mh = at_amax4(mh, hh[i]); }
+    at_cta_max2(mg, mh, red + 1);
+    const int kg = og_scale_exp(__float_as_uint(mg)), kh = og_scale_exp(__float_as_uint(mh));
+    {
+      const float sg = og_exp2i(kg);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float4 x = gw[g * 3 + j];
+          float h0, l0, h1, l1, h2, l2, h3, l3;
+          at_hilo(x.x * sg, h0, l0); at_hilo(x.y * sg, h1, l1);
+          at_hilo(x.z * sg, h2, l2); at_hilo(x.w * sg, h3, l3);
+          const uint32_t a = sX + offA[j] + g * 1024;
+          at_sts64(a, at_cvt2(h0, h1), at_cvt2(h2, h3));
+          at_sts64(a + AT_A_BYTES, at_cvt2(l0, l1), at_cvt2(l2, l3));
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t yh[4], yl[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int l0 = ch * 8 + 2 * e;
+        float ha = 0.f, la = 0.f, hb = 0.f, lb = 0.f;
+        if (l0 < LQ) at_hilo(pr[l0 < LQ ? l0 : 0] * (float)(1 << AT_PSCALE), ha, la);
+        if (l0 + 1 < LQ) at_hilo(pr[l0 + 1 < LQ ? l0 + 1 : 0] * (float)(1 << AT_PSCALE), hb, lb);
+        yh[e] = at_cvt2(ha, hb);
+        yl[e] = at_cvt2(la, lb);
+      }
+      const uint32_t addr = rowY + (uint32_t)(((ch ^ (t & 7)) & 7) << 4);
+      at_sts128(addr, yh[0], yh[1], yh[2], yh[3]);
+      at_sts128(addr + AT_A_BYTES, yl[0], yl[1], yl[2], yl[3]);
+    }
+    at_fence_proxy_async();
+    at_tc_fence_before();
+    __syncthreads();
+    if (t == 0) {
+      at_tc_fence_after();
+      at_issue(tmem_base, dX, dB1, idesc1, AT_C / 16);              // gP
+      at_issue_mn(tmem_base + 80, dXmn, dYmn, idesc3);               // Gw^T . P
+      at_umma_commit(&bar1);
+    }
+    // ---- (2) softmax backward in registers ----
+    at_mbar_wait(&bar1, phase);
+    at_tc_fence_after();
+    float gs[LQ];
+    {
+      const float s1 = og_exp2i(-kg);
+      if (LQ == 32) {
+        uint32_t sr[32];
+        at_tmem_ld32(tmem_row, sr);
+        at_tmem_ld_wait();
+#pragma unroll
+        for (int l = 0; l < LQ; ++l) gs[l] = __uint_as_float(sr[l]) * s1 * ss2;
+      } else {
+        uint32_t sr[16], sr2[16];
+        at_tmem_ld16(tmem_row, sr);
+        at_tmem_ld16(tmem_row + 16, sr2);
+        at_tmem_ld_wait();
+#pragma unroll
+        for (int l = 0; l < LQ; ++l) gs[l] = __uint_as_float(l < 16 ? sr[l & 15] : sr2[l & 15]) * s1 * ss2;
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int l = 0; l < LQ; ++l) dot = fmaf(pr[l], gs[l], dot);
+      float mgs = 0.f;
+#pragma unroll
+      for (int l = 0; l < LQ; ++l) {
+        gs[l] = pr[l] * (gs[l] - dot);
+        mgs = fmaxf(mgs, fabsf(gs[l]));
+      }
+      // first g_src term of this tile (thread c = t < 48 reads row c): acc * 2^-(kg + 13)
+      {
+        uint32_t d3[32];
+        at_tmem_ld32(tmem_row + 80, d3);
+        at_tmem_ld_wait();
+        const float s3a = og_exp2i(-kg), s3b = og_exp2i(-AT_PSCALE);    // two factors: their product may underflow
+#pragma unroll
+        for (int l = 0; l < LQ; ++l) gacc[l] = fmaf(__uint_as_float(d3[l]) * s3a, s3b, gacc[l]);
+      }
+      mgs = at_cta_max(mgs, red[3]);                   // (its __syncthreads also orders the TMEM reads above)
+      const int ks = og_scale_exp(__float_as_uint(mgs));
+      const float sgs = og_exp2i(ks), shh = og_exp2i(kh);
+      // ---- (3) gS -> Y, H -> X (MMA 1 / 3a have completed: both regions are free) ----
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t yh[4], yl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int l0 = ch * 8 + 2 * e;
+          float ha = 0.f, la = 0.f, hb = 0.f, lb = 0.f;
+          if (l0 < LQ) at_hilo(gs[l0 < LQ ? l0 : 0] * sgs, ha, la);
+          if (l0 + 1 < LQ) at_hilo(gs[l0 + 1 < LQ ? l0 + 1 : 0] * sgs, hb, lb);
+          yh[e] = at_cvt2(ha, hb);
+          yl[e] = at_cvt2(la, lb);
+        }
+        const uint32_t addr = rowY + (uint32_t)(((ch ^ (t & 7)) & 7) << 4);
+        at_sts128(addr, yh[0], yh[1], yh[2], yh[3]);
+        at_sts128(addr + AT_A_BYTES, yl[0], yl[1], yl[2], yl[3]);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float4 x = hh[g * 3 + j];
+          float h0, l0, h1, l1, h2, l2, h3, l3;
+          at_hilo(x.x * shh, h0, l0); at_hilo(x.y * shh, h1, l1);
+          at_hilo(x.z * shh, h2, l2); at_hilo(x.w * shh, h3, l3);
+          const uint32_t a = sX + offA[j] + g * 1024;
+          at_sts64(a, at_cvt2(h0, h1), at_cvt2(h2, h3));
+          at_sts64(a + AT_A_BYTES, at_cvt2(l0, l1), at_cvt2(l2, l3));
+        }
+      at_fence_proxy_async();
+      at_tc_fence_before();
+      __syncthreads();
+      if (t == 0) {
+        at_tc_fence_after();
+        at_issue(tmem_base + 32, dY, dB2, idesc2, AT_LP / 16);       // g_h
+        at_issue_mn(tmem_base + 112, dXmn, dYmn, idesc3);            // H^T . gS
+        at_umma_commit(&bar2);
+      }
+      // ---- (4) g_h rows and the second g_src term ----
+      at_mbar_wait(&bar2, phase);
+      at_tc_fence_after();
+      {
+        uint32_t d3[32];
+        at_tmem_ld32(tmem_row + 112, d3);
+        at_tmem_ld_wait();
+        const float s3a = og_exp2i(-kh), s3b = og_exp2i(-ks);
+#pragma unroll
+        for (int l = 0; l < LQ; ++l) gacc[l] = fmaf(__uint_as_float(d3[l]) * s3a, s3b, gacc[l]);
+      }
+      const float so = og_exp2i(-ks);
+#pragma unroll
+      for (int cb = 0; cb < AT_C; cb += 16) {
+        uint32_t o[16];
+        at_tmem_ld16(tmem_row + 32 + cb, o);
+        at_tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          at_sts128(rowS + (cb + j) * 4, __float_as_uint(__uint_as_float(o[j]) * so * ss2),
+                    __float_as_uint(__uint_as_float(o[j + 1]) * so * ss2), __float_as_uint(__uint_as_float(o[j + 2]) * so * ss2),
+                    __float_as_uint(__uint_as_float(o[j + 3]) * so * ss2));
+      }
+    }
+    at_tc_fence_before();
+    __syncthreads();
+    {
+      float4* op = reinterpret_cast<float4*>(g_h + tile) + warp * 384 + lane;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          op[g * 96 + j * 32] = at_lds128(sX + offS[j] + (uint32_t)(g * 8 * AT_STAGE_PITCH * 4));
+    }
+    __syncthreads();
+  }
+  if (t < AT_C) {
+    float* gp = g_src + ((long long)b * AT_C + t) * L;
+#pragma unroll
+    for (int l = 0; l < LQ; ++l)
+      if (l < L) atomicAdd(gp + l, gacc[l]);
+  }
+  at_tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    at_tc_fence_after();
+    at_tmem_dealloc(tmem_base, 256);
+  }
+}
+
 }  // namespace
 
 // Returns 0 when the tensor-core kernel ran, -1 when the shape is outside its envelope (the caller then uses the SIMT
@@ -453,5 +779,27 @@ extern "C" int og_att_general_fwd_tc(const float* h, const float* src, const uns
     att_general_fwd_tc_kernel<20><<<B * nslots, AT_Q, smem, stream>>>(h, src, mask, B, Q, L, nslots, wc, attn);
   else
     att_general_fwd_tc_kernel<32><<<B * nslots, AT_Q, smem, stream>>>(h, src, mask, B, Q, L, nslots, wc, attn);
+  OG_RETURN_LAST_ERROR();
+}
+
+// Backward on the tensor cores (g_attn == null only).  g_src must be zeroed by the caller.  Same return convention.
+extern "C" int og_att_general_bwd_tc(const float* h, const float* src, const float* attn, const float* g_wc, int B, int Q,
+                                     int idf, int cs, int L, float* g_h, float* g_src, cudaStream_t stream) {
+  if (idf != AT_C || cs != AT_C || L < 1 || L > AT_LP || Q % AT_Q != 0 || Q < AT_Q || B < 1) return -1;
+  const int ntiles = Q / AT_Q;
+  int nslots = (2 * 148) / B;          // two CTAs per SM
+  if (nslots < 1) nslots = 1;
+  if (nslots > ntiles) nslots = ntiles;
+  const size_t smem = 4 * AT_A_BYTES + 2 * AT_B1_BYTES + 2 * AT_B2_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    OG_CHECK(cudaFuncSetAttribute(att_general_bwd_tc_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OG_CHECK(cudaFuncSetAttribute(att_general_bwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  if (L <= 20)
+    att_general_bwd_tc_kernel<20><<<B * nslots, AT_Q, smem, stream>>>(h, src, attn, g_wc, B, Q, L, nslots, g_h, g_src);
+  else
+    att_general_bwd_tc_kernel<32><<<B * nslots, AT_Q, smem, stream>>>(h, src, attn, g_wc, B, Q, L, nslots, g_h, g_src);
   OG_RETURN_LAST_ERROR();
 }
