@@ -54,6 +54,14 @@ res = torch.randn(B, 128, 128, 200, device=DEV)
 for _ in range(2):
     a = ops.instance_norm_act(y2, NA_NONE, res)
     a.backward(torch.ones_like(a))
+# residual block of stage 3 (194 channels at 128^2, B = 16): the producer-side operand split (norm_apply_split_kernel)
+blk = torch.nn.Sequential(model.HmapResBlock(194), model.HmapResBlock(194)).to(DEV)
+model._chain_res_blocks(blk, 1)
+xb = torch.randn(B, 128, 128, 200, device=DEV)
+xb[..., 194:] = 0
+for _ in range(2):
+    with torch.no_grad():
+        blk(xb)
 n = 19_340_000
 pp, g, mm, v, avg = (torch.randn(n, device=DEV) for _ in range(5))
 for t in (1, 2):
