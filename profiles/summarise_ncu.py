@@ -44,11 +44,16 @@ def short(name):
 
 
 def main(reps):
-    last, seen = {}, {}
+    last, seen, owner = {}, {}, {}
     for rep in reps:
         for rec in rows_of(rep):
             rec["rep"] = os.path.basename(rep)
             k = short(rec["name"])
+            if owner.get(k, rep) != rep:                 # a later report re-captured this kernel: it replaces the older rows
+                for old in [key for key in last if key.rsplit(" #", 1)[0] == k]:
+                    del last[old]
+                seen.pop(k, None)
+            owner[k] = rep
             seen[k] = seen.get(k, -1) + 1
             last["%s #%d" % (k, seen[k])] = rec          # every captured launch, numbered per kernel name
     print("| kernel | duration | DRAM read + write | DRAM GB/s | of measured copy peak (%.0f GB/s) | tensor pipe | issue active | regs | report |" % HBM)
@@ -65,6 +70,8 @@ def main(reps):
         traffic[k] = {"dram_bytes": byt, "duration_us": r["dur_us"], "source": "profiles/" + r["rep"]}
     alias = {"conv_tc2_res3_conv1": "conv_tcp_kernel<208, 1> #0", "att_general_fwd": "att_general_fwd_tc_kernel<20> #1"}
     for a, k in alias.items():
+        if k not in traffic and k.endswith("#1") and k[:-1] + "0" in traffic:
+            k = k[:-1] + "0"
         if k in traffic:
             traffic[a] = traffic[k]
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1, sort_keys=True)
