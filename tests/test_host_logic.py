@@ -191,3 +191,17 @@ def test_checkpoint_files_round_trip(dry, tmp_path):
             net.load_state_dict(sd)                                         # strict, like trainer.py:155-191
             back = net.state_dict()
             assert all(torch.equal(back[k], sd[k]) for k in sd), name
+
+
+def test_res_chain_tells_each_block_its_consumer(dry):
+    """Producer-side operand split (ops.FUSED_SPLIT): every residual block of the generator knows which operand layout
+    the convolution after it wants -- the next block's reflection-padded conv (halo 1) or the upsample conv that ends
+    the chain (plain copies, halo 0) -- and the C ABI declares the two launchers the fused pass needs."""
+    from objgan_b200 import lib as L
+    g = model.G_NET(80)
+    for main in (g.h_net1_main, g.h_net2_main, g.h_net3_main):
+        pads = [b.next_pad for b in main.residual]
+        assert pads == [1] * (len(pads) - 1) + [0], pads
+    protos = L.get().protos
+    assert "og_norm_bound" in protos and "og_norm_apply_split" in protos
+    assert len(protos["og_norm_apply_split"]) == 19          # 18 arguments + the stream
