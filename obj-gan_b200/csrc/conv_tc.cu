@@ -57,6 +57,7 @@ struct TcParams {
   float slope;
   int ksplit;               // > 1: gridDim.z CTAs share one output tile, each reduces a slice of the (tap, chunk) loop
   int tall;                 // taps come in groups of 3 consecutive source rows: load one (TH+2)-row A patch per group
+  int stacked;              // CTA-pair kernel, <= 16 output channels: B = [w_hi (CTA 0) | w_lo (CTA 1)] along N, two MMAs per k-step
   TcTaps taps;
 };
 
@@ -927,9 +928,16 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         auto load_b = [&](int tap, int c0) {
           mbar_wait_bounded(&emptyB[bs], bph ^ 1);
           uint8_t* sb = smem_b + (size_t)bs * B_SLOT;
-          if (leader) mbar_expect_tx(&fullB[bs], 2 * (split3 ? B_SLOT : B_BYTES));
-          tma2_load_3d(sb, &map_bh, &fullB[bs], c0, col0 + (int)rank * BNH, p.taps.widx[tap]);
-          if (split3) tma2_load_3d(sb + B_BYTES, &map_bl, &fullB[bs], c0, col0 + (int)rank * BNH, p.taps.widx[tap]);
+          if (p.stacked) {
+            // one 4-D map over the {hi, lo} weight copies: CTA 0 takes the hi rows, CTA 1 the lo rows -- together the
+            // N = 32 operand [w_hi | w_lo]
+            if (leader) mbar_expect_tx(&fullB[bs], 2 * B_BYTES);
+            tma2_load_4d(sb, &map_bh, &fullB[bs], c0, 0, (int)rank, p.taps.widx[tap]);
+          } else {
+            if (leader) mbar_expect_tx(&fullB[bs], 2 * (split3 ? B_SLOT : B_BYTES));
+            tma2_load_3d(sb, &map_bh, &fullB[bs], c0, col0 + (int)rank * BNH, p.taps.widx[tap]);
+            if (split3) tma2_load_3d(sb + B_BYTES, &map_bl, &fullB[bs], c0, col0 + (int)rank * BNH, p.taps.widx[tap]);
+          }
           if (++bs == BS) { bs = 0; bph ^= 1; }
         };
         auto load_a = [&](int tap, int c0) {
@@ -973,7 +981,12 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
           if (kk >= ks) break;
           const uint64_t koff = (uint64_t)((kk * 32) >> 4);
           const uint32_t acc = (!first || kk > 0) ? 1u : 0u;
-          if (split3) {
+          if (split3 && p.stacked) {
+            // columns [0, 16): a_lo w_hi + a_hi w_hi; columns [16, 32): a_lo w_lo (negligible) + a_hi w_lo: each A copy
+            // is read from shared memory ONCE (these narrow layers are bound by the A reads, not by the MMA rate)
+            umma2_f16(d, al + koff, bh + koff, idesc, acc);
+            umma2_f16(d, ah + koff, bh + koff, idesc, 1u);
+          } else if (split3) {
             umma2_f16(d, al + koff, bh + koff, idesc, acc);
             umma2_f16(d, ah + koff, bl + koff, idesc, 1u);
             umma2_f16(d, ah + koff, bh + koff, idesc, 1u);
@@ -1041,6 +1054,12 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * ACC_STRIDE + c), r);
+        if (p.stacked) {      // the hi and lo weight halves of the same 16 output channels
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r[j + 16]));
+#pragma unroll
+          for (int j = 16; j < 32; ++j) r[j] = 0u;
+        }
         if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -1579,6 +1598,7 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
   p.TN = TN; p.TH = TH; p.TW = TW;
   p.bias = bias; p.act = act; p.slope = slope;
   p.tall = 0;
+  p.stacked = 0;
   p.tiles_w = og_cdiv(OW, TW);
   p.tiles_h = og_cdiv(OH, TH);
   const int tiles_n = og_cdiv(N, TN);
@@ -1645,11 +1665,23 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
   if (tcp && p.ksplit == 1 && (tcp > 1 || BNsel == 208 || BNsel == 256) && (long long)grid.x * grid.y >= tcp_min) {
     CUtensorMap pbh, pbl;
     unsigned hbox[3] = {(unsigned)TC_BK, (unsigned)(BNsel / 2), 1u};
-    if ((rc = make_map(&pbh, wh, 3, bdims, bstr, hbox))) return rc;
-    if (nsplit == 3) {
-      if ((rc = make_map(&pbl, wl, 3, bdims, bstr, hbox))) return rc;
-    } else {
+    // <= 16 output channels with the lo copy stored right behind the hi copy: stack them along N (two MMAs per k-step)
+    static const int stacked_on = getenv("OG_STACKED") ? atoi(getenv("OG_STACKED")) : 0;
+    p.stacked = (stacked_on && nsplit == 3 && BNsel == 32 && K <= 16 && Kw <= 16 && wl != nullptr &&
+                 (const char*)wl == (const char*)wh + sizeof(__half) * (size_t)ntaps_w * Kw * C) ? 1 : 0;
+    if (p.stacked) {
+      unsigned long long sdims[4] = {(unsigned long long)C, (unsigned long long)Kw, 2ull, (unsigned long long)ntaps_w};
+      unsigned long long sstr[3] = {(unsigned long long)C, (unsigned long long)ntaps_w * Kw * C, (unsigned long long)Kw * C};
+      unsigned sbox[4] = {(unsigned)TC_BK, 16u, 1u, 1u};
+      if ((rc = make_map(&pbh, wh, 4, sdims, sstr, sbox))) return rc;
       pbl = pbh;
+    } else {
+      if ((rc = make_map(&pbh, wh, 3, bdims, bstr, hbox))) return rc;
+      if (nsplit == 3) {
+        if ((rc = make_map(&pbl, wl, 3, bdims, bstr, hbox))) return rc;
+      } else {
+        pbl = pbh;
+      }
     }
     static const bool no_tall = getenv("OG_NO_TALL") != nullptr;
     if (!no_tall && tap_layout == 1 && ntaps % 3 == 0 && BNsel == 208 && TN == 1 && TH == 8 && TW == 16) {

@@ -118,8 +118,12 @@ class PackedWeights:
         self._refresh(w, cip, kp, split)
         if transposed not in self.hl:
             co, ci, kh, kw = w.shape
-            hi = torch.empty(kh * kw * cip * kp, device=w.device, dtype=torch.float16)
-            lo = torch.empty_like(hi) if _nsplit() == 3 else None
+            # hi and lo live back to back in ONE buffer: the CTA-pair kernel can then address them as the two halves of
+            # an [hi | lo] operand stacked along N (narrow layers, conv_tc.cu: TcParams::stacked)
+            nel = kh * kw * cip * kp
+            buf = torch.empty(nel * (2 if _nsplit() == 3 else 1), device=w.device, dtype=torch.float16)
+            hi = buf[:nel]
+            lo = buf[nel:] if _nsplit() == 3 else None
             _call("og_pack_weights_f16", _p(w), co, ci, kh, kw, cip, kp, split, splitp, transposed,
                   _p(self._amax(w)), _p(hi), _p(lo))
             self.hl[transposed] = (hi, lo, self._amax(w))
