@@ -36,6 +36,8 @@ CASES = [
     (192, 384, "s2", 0, 13, 16, 16),             # sub-batch of the permuted-shape pass: 13 images, tiles span 2 images
     (384, 768, "s2", 0, 19, 8, 8),               # ... 4x4 outputs, 8 images per tile
     (96, 48, UPSAMPLE2X, 24, 3, 8, 8),           # upsample phases with a batch that does not fill the 2-image tile
+    (80, 12, PAD_REFLECT, 0, 2, 128, 128),       # shape code of the object discriminators: 12 (-> 16) output channels
+    (15, 96, "s2", 0, 2, 128, 128),              # their first encoder layer: the input gradient has 15 (-> 16) channels
 ]
 
 
@@ -140,6 +142,20 @@ def test_two_tile_kernels_on_small_cases():
     env = dict(os.environ, OG_TC2_MIN="4")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-k",
                         "test_tc_conv_fwd_dgrad and f16x3 and (case0 or case1 or case3 or case6)"],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_stacked_hi_lo_weights_on_narrow_layers():
+    """OG_STACKED=1: layers with <= 16 output channels run the CTA-pair kernel with B = [w_hi | w_lo] stacked along N
+    and two MMAs per k-step (each A copy read once) instead of three; same parity bound as the three-MMA form.  Fresh
+    process: the library reads the variable once."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, OG_STACKED="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k",
+                        "test_tc_conv_fwd_dgrad and f16x3 and (case10 or case12 or case21 or case22)"],
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
