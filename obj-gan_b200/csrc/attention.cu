@@ -651,7 +651,7 @@ OG_API int og_att_general_bwd(const float* h, const float* src, const float* att
   if (L > LMAX || cs % 4 || idf > cs) return (int)cudaErrorInvalidValue;
   OG_CHECK(cudaMemsetAsync(g_src, 0, sizeof(float) * (size_t)B * idf * L, stream));
   if (B == 0 || Q == 0) return 0;
-  static const int bwd_tc = getenv("OG_ATT_TC_BWD") ? atoi(getenv("OG_ATT_TC_BWD")) : 0;   // opt-in until validated on hardware
+  static const int bwd_tc = getenv("OG_ATT_TC_BWD") ? atoi(getenv("OG_ATT_TC_BWD")) : 1;
   if (bwd_tc && !g_attn && Q >= 4096) {
     const int rc = og_att_general_bwd_tc(h, src, attn, g_wc, B, Q, idf, cs, L, g_h, g_src, stream);
     if (rc >= 0) return rc;
