@@ -1666,7 +1666,7 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
     CUtensorMap pbh, pbl;
     unsigned hbox[3] = {(unsigned)TC_BK, (unsigned)(BNsel / 2), 1u};
     // <= 16 output channels with the lo copy stored right behind the hi copy: stack them along N (two MMAs per k-step)
-    static const int stacked_on = getenv("OG_STACKED") ? atoi(getenv("OG_STACKED")) : 0;
+    static const int stacked_on = getenv("OG_STACKED") ? atoi(getenv("OG_STACKED")) : 1;
     p.stacked = (stacked_on && nsplit == 3 && BNsel == 32 && K <= 16 && Kw <= 16 && wl != nullptr &&
                  (const char*)wl == (const char*)wh + sizeof(__half) * (size_t)ntaps_w * Kw * C) ? 1 : 0;
     if (p.stacked) {

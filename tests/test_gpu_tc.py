@@ -147,13 +147,14 @@ def test_two_tile_kernels_on_small_cases():
 
 
 def test_stacked_hi_lo_weights_on_narrow_layers():
-    """OG_STACKED=1: layers with <= 16 output channels run the CTA-pair kernel with B = [w_hi | w_lo] stacked along N
-    and two MMAs per k-step (each A copy read once) instead of three; same parity bound as the three-MMA form.  Fresh
-    process: the library reads the variable once."""
+    """Layers with <= 16 output channels run the CTA-pair kernel with B = [w_hi | w_lo] stacked along N and two MMAs per
+    k-step (each A copy read once) instead of three (the default; the normal run of these cases covers it).  Here the
+    three-MMA form (OG_STACKED=0) is checked against the same parity bound in a fresh process (the library reads the
+    variable once)."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, OG_STACKED="1")
+    env = dict(os.environ, OG_STACKED="0")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k",
                         "test_tc_conv_fwd_dgrad and f16x3 and (case10 or case12 or case21 or case22)"],
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
