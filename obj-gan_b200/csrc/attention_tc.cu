@@ -11,7 +11,8 @@
 //
 // fp32 parity: the convolution engine's error-compensated scheme (conv_tc.cu): x * 2^k = hi + lo with hi, lo fp16
 // (22 mantissa bits), three products hi*hi + lo*hi + hi*lo into the fp32 TMEM accumulator.  The power of two comes from
-// max|x| of the TILE (a register max + one shuffle reduction; no extra pass over the tensor) resp. of the image's
+// max|x| of the 32 rows a WARP stages (a register max + one shuffle reduction; no extra pass over the tensor, no block
+// barrier: the same warp owns those rows in the softmax and undoes its factor there) resp. of the image's
 // word projections; the accumulator is scaled back before the softmax / the store.  hi is the fp32 value truncated to
 // 11 significant bits (one LOP3), lo the exact remainder; the only conversions are packed cvt.rn.f16x2 (no F2F).
 //
@@ -27,6 +28,7 @@
 // shared memory and <= 128 registers per thread: four CTAs per SM cover each other's MMA round trips.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -289,11 +291,14 @@ att_general_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
   uint32_t phase = 0;
   for (; qt < ntiles; qt += nslots, phase ^= 1) {
     const int q0 = qt * AT_Q;
-    // ---------------- (1) scale by the tile's power of two, split into the two A copies ----------------
+    // ---------------- (1) scale by a power of two, split into the two A copies ----------------
+    // The scale is per WARP: warp w stages rows [32w, 32w + 32) here and owns the same rows (TMEM lanes) in the softmax,
+    // where it divides its scores by its own factor again -- a row scale of A is a row scale of A.B -- so a shuffle
+    // reduction is enough (no block-wide barrier).
     float m = 0.f;
 #pragma unroll
     for (int i = 0; i < 12; ++i) m = at_amax4(m, hv[i]);
-    m = at_cta_max(m, red[1]);                          // the __syncthreads of the trip order the reuse of the slot
+    m = warp_max(m);
     const int kh = og_scale_exp(__float_as_uint(m));
     const float sh = og_exp2i(kh);
 #pragma unroll
@@ -557,29 +562,40 @@ att_general_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
 #pragma unroll
   for (int l = 0; l < LQ; ++l) gacc[l] = 0.f;
 
+  // g_wc rows and the saved probabilities of a tile are loaded one tile AHEAD (into the registers the current tile has
+  // finished with); h is loaded at the top of its own tile (it is needed last)
+  float4 gw[12];
+  float pr[LQ];
+  auto load_gw = [&](int tileq) {
+    const float4* gp = reinterpret_cast<const float4*>(g_wc + ((long long)b * Q + (long long)tileq * AT_Q) * AT_C) + warp * 384 + lane;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) gw[i] = __ldg(gp + i * 32);
+  };
+  auto load_pr = [&](int tileq) {
+    const float* arow = attn + (long long)b * L * Q + ((long long)tileq * AT_Q + t);
+#pragma unroll
+    for (int l = 0; l < LQ; ++l) {
+      pr[l] = l < L ? __ldg(arow) : 0.f;
+      arow += Q;
+    }
+  };
+  if (slot < ntiles) {
+    load_gw(slot);
+    load_pr(slot);
+  }
   uint32_t phase = 0;
   for (int qt = slot; qt < ntiles; qt += nslots, phase ^= 1) {
     const int q0 = qt * AT_Q;
     const long long tile = ((long long)b * Q + q0) * AT_C;
-    // ---- loads of the tile: g_wc and h (coalesced float4), the saved probabilities of this thread's query ----
-    float4 gw[12], hh[12];
+    float4 hh[12];
     {
-      const float4* gp = reinterpret_cast<const float4*>(g_wc + tile) + warp * 384 + lane;
       const float4* hp = reinterpret_cast<const float4*>(h + tile) + warp * 384 + lane;
-#pragma unroll
-      for (int i = 0; i < 12; ++i) gw[i] = __ldg(gp + i * 32);
 #pragma unroll
       for (int i = 0; i < 12; ++i) hh[i] = __ldg(hp + i * 32);
     }
-    float pr[LQ];
-    {
-      const float* arow = attn + (long long)b * L * Q + (q0 + t);
+    float prc[LQ];                                     // this tile's probabilities (pr is refilled below)
 #pragma unroll
-      for (int l = 0; l < LQ; ++l) {
-        pr[l] = l < L ? __ldg(arow) : 0.f;
-        arow += Q;
-      }
-    }
+    for (int l = 0; l < LQ; ++l) prc[l] = pr[l];
     // ---- (1) Gw -> X, P -> Y ----
     float mg = 0.f, mh = 0.f;
 #pragma unroll
@@ -608,14 +624,18 @@ att_general_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
       for (int e = 0; e < 4; ++e) {
         const int l0 = ch * 8 + 2 * e;
         float ha = 0.f, la = 0.f, hb = 0.f, lb = 0.f;
-        if (l0 < LQ) at_hilo(pr[l0 < LQ ? l0 : 0] * (float)(1 << AT_PSCALE), ha, la);
-        if (l0 + 1 < LQ) at_hilo(pr[l0 + 1 < LQ ? l0 + 1 : 0] * (float)(1 << AT_PSCALE), hb, lb);
+        if (l0 < LQ) at_hilo(prc[l0 < LQ ? l0 : 0] * (float)(1 << AT_PSCALE), ha, la);
+        if (l0 + 1 < LQ) at_hilo(prc[l0 + 1 < LQ ? l0 + 1 : 0] * (float)(1 << AT_PSCALE), hb, lb);
         yh[e] = at_cvt2(ha, hb);
         yl[e] = at_cvt2(la, lb);
       }
       const uint32_t addr = rowY + (uint32_t)(((ch ^ (t & 7)) & 7) << 4);
       at_sts128(addr, yh[0], yh[1], yh[2], yh[3]);
       at_sts128(addr + AT_A_BYTES, yl[0], yl[1], yl[2], yl[3]);
+    }
+    if (qt + nslots < ntiles) {                        // gw and pr are dead from here on: next tile's loads
+      load_gw(qt + nslots);
+      load_pr(qt + nslots);
     }
     at_fence_proxy_async();
     at_tc_fence_before();
@@ -648,11 +668,11 @@ att_general_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__
       }
       float dot = 0.f;
 #pragma unroll
-      for (int l = 0; l < LQ; ++l) dot = fmaf(pr[l], gs[l], dot);
+      for (int l = 0; l < LQ; ++l) dot = fmaf(prc[l], gs[l], dot);
       float mgs = 0.f;
 #pragma unroll
       for (int l = 0; l < LQ; ++l) {
-        gs[l] = pr[l] * (gs[l] - dot);
+        gs[l] = prc[l] * (gs[l] - dot);
         mgs = fmaxf(mgs, fabsf(gs[l]));
       }
       // first g_src term of this tile (thread c = t < 48 reads row c): acc * 2^-(kg + 13)
@@ -765,7 +785,8 @@ extern "C" int og_att_general_fwd_tc(const float* h, const float* src, const uns
       (long long)B * Q >= (1LL << 31) || B > AT_MAXB)
     return -1;
   const int ntiles = Q / AT_Q;
-  int nslots = (4 * 148) / B;          // four CTAs per SM, every CTA stays inside one image
+  static const int cps = getenv("OG_ATT_CPS") ? atoi(getenv("OG_ATT_CPS")) : 4;
+  int nslots = (cps * 148) / B;        // four CTAs per SM, every CTA stays inside one image
   if (nslots < 1) nslots = 1;
   if (nslots > ntiles) nslots = ntiles;
   const size_t smem = AT_SMEM + 1024;
