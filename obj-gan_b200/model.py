@@ -639,7 +639,8 @@ class _ObjD(_Base):
         LeakyReLU) of a segmentation map, NHWC.  It depends on the map and this net's weights only, so a loss that
         runs the net on several images with the SAME map (objD_loss: real and fake) computes it once and passes it
         to ``forward`` (autograd sums both uses' gradients): same values, one 80-channel 512^2 pass instead of two."""
-        s = ops.bilinear(ops.to_nhwc(s_var), img_size, img_size)
+        s = ops.cached_const(s_var, ("bilinear_nhwc", img_size),
+                             lambda: ops.bilinear(ops.to_nhwc(s_var), img_size, img_size))   # same map for both object Ds
         return ops.instance_norm_act(self.shp_code[1](s), NA_LRELU)
 
     def forward(self, x_var, s_var, fm_rois, num_rois, img_size=512, shape_features=None):

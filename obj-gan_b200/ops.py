@@ -728,8 +728,32 @@ class _ToNCHW(torch.autograd.Function):
         return gy, None
 
 
+# Derived copies of CONSTANT inputs (no gradient: segmentation maps, real images): a step converts / resizes the same
+# input tensor for several networks (the 80-channel 256^2 class maps go through NCHW -> NHWC eight times and through the
+# 512^2 bilinear resize four times in one Step-B); the copy is kept while the source tensor is the same object at the
+# same version.  Never used while a CUDA graph is being captured (a replay must recompute from the static buffers).
+_CONST_CACHE = []          # [(weakref to the source, version, key, value)], newest last
+_CONST_CACHE_SLOTS = 12
+
+
+def cached_const(src, key, fn):
+    import weakref
+    if src.requires_grad or _lib.DRY_RUN or not src.is_cuda or torch.cuda.is_current_stream_capturing():
+        return fn()
+    for ref, ver, k, val in _CONST_CACHE:
+        if k == key and ver == src._version and ref() is src:
+            return val
+    val = fn()
+    _CONST_CACHE[:] = [e for e in _CONST_CACHE if e[0]() is not None][-(_CONST_CACHE_SLOTS - 1):]
+    _CONST_CACHE.append((weakref.ref(src), src._version, key, val))
+    return val
+
+
 def to_nhwc(x, cp=None):
-    return _ToNHWC.apply(x, cpad(x.shape[1]) if cp is None else cp)
+    cp = cpad(x.shape[1]) if cp is None else cp
+    if not x.requires_grad:
+        return cached_const(x, ("nhwc", cp), lambda: _ToNHWC.apply(x, cp))
+    return _ToNHWC.apply(x, cp)
 
 
 def to_nchw(y, c):
