@@ -462,6 +462,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the operator lines (configs 3/4) and the Step-B section")
     args = ap.parse_args()
+    if os.environ.get("OBJGAN_BENCH_WATCHDOG"):      # debugging aid: dump every thread's Python stack after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["OBJGAN_BENCH_WATCHDOG"]), repeat=False, file=sys.stderr)
     if args.impl == "reference":
         run_reference(args)
     else:
