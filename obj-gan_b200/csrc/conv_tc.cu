@@ -1054,11 +1054,20 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * ACC_STRIDE + c), r);
-        if (p.stacked) {      // the hi and lo weight halves of the same 16 output channels
+        if (p.stacked) {      // columns [0, BN/2): products with w_hi, [BN/2, BN): with w_lo, of the same output channels
+          constexpr int HALF = BN / 2;
+          if (c >= HALF) break;
+          if (HALF >= 32) {
+            uint32_t r2[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * ACC_STRIDE + c + HALF), r2);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r[j + 16]));
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          } else {
 #pragma unroll
-          for (int j = 16; j < 32; ++j) r[j] = 0u;
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r[j + 16]));
+#pragma unroll
+            for (int j = 16; j < 32; ++j) r[j] = 0u;
+          }
         }
         if (row_ok) {
 #pragma unroll
@@ -1667,14 +1676,17 @@ OG_API int og_conv2d_tc(const void* xh, const void* xl, const unsigned* amax_x, 
     unsigned hbox[3] = {(unsigned)TC_BK, (unsigned)(BNsel / 2), 1u};
     // <= 16 output channels with the lo copy stored right behind the hi copy: stack them along N (two MMAs per k-step)
     static const int stacked_on = getenv("OG_STACKED") ? atoi(getenv("OG_STACKED")) : 1;
-    p.stacked = (stacked_on && nsplit == 3 && BNsel == 32 && K <= 16 && Kw <= 16 && wl != nullptr &&
+    // up to 16 output channels: N = 32 = [16 hi | 16 lo]; 17..32: N = 64 = [32 hi | 32 lo]
+    const int stk_rows = (K <= 16 && Kw <= 16) ? 16 : (K <= 32 && Kw <= 32) ? 32 : 0;
+    p.stacked = (stacked_on && nsplit == 3 && BNsel == 32 && stk_rows > 0 && wl != nullptr &&
                  (const char*)wl == (const char*)wh + sizeof(__half) * (size_t)ntaps_w * Kw * C) ? 1 : 0;
     if (p.stacked) {
       unsigned long long sdims[4] = {(unsigned long long)C, (unsigned long long)Kw, 2ull, (unsigned long long)ntaps_w};
       unsigned long long sstr[3] = {(unsigned long long)C, (unsigned long long)ntaps_w * Kw * C, (unsigned long long)Kw * C};
-      unsigned sbox[4] = {(unsigned)TC_BK, 16u, 1u, 1u};
+      unsigned sbox[4] = {(unsigned)TC_BK, (unsigned)stk_rows, 1u, 1u};
       if ((rc = make_map(&pbh, wh, 4, sdims, sstr, sbox))) return rc;
       pbl = pbh;
+      if (stk_rows == 32) return launch_tcp<64, false>(mah, mal, pbh, pbl, p, (int)grid.x, (int)grid.y, stream);
     } else {
       if ((rc = make_map(&pbh, wh, 3, bdims, bstr, hbox))) return rc;
       if (nsplit == 3) {
