@@ -314,3 +314,27 @@ def test_torch_extension_registers_reference_entry_points():
         assert len(schema.arguments) == 6
     with pytest.raises(Exception):
         ops_.roi_align_forward_cuda(6, 6, 1 / 16, torch.zeros(1, 2, 8, 8), torch.zeros(1, 5), torch.zeros(1, 2, 6, 6))
+
+
+def test_hi_lo_operand_split_arithmetic():
+    """The integer form of the fp16 hi / lo operand split used by attention_tc.cu (at_hilo: hi = (bits + 0x1000) &
+    0xFFFFE000, lo = x - hi) restated in numpy: hi has 11 significant bits (exactly an fp16 once scaled into the fp16
+    range), x - hi is exact in fp32, |lo| <= 2^-11 |x|, and hi + fp16(lo) reproduces x to 2^-21 relative -- the
+    22-bit operand the three-product MMA scheme assumes.  Also the algebra of the stacked-weight form used for narrow
+    layers: a_lo [w_hi | w_lo] + a_hi [w_hi | w_lo] = the three-product sum + a_lo w_lo."""
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(200000) * 2.0 ** rng.integers(-6, 13, 200000)).astype(np.float32)   # |x| < 2^14 after scaling
+    bits = x.view(np.uint32)
+    hi = ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    lo = x - hi
+    normal = np.abs(x) >= 2.0 ** -14                                             # fp16 normal range
+    assert np.array_equal(hi[normal].astype(np.float16).astype(np.float32), hi[normal])   # hi is an fp16 value there
+    assert np.array_equal(hi.astype(np.float64) + lo.astype(np.float64), x.astype(np.float64))   # the remainder is exact
+    assert np.all(np.abs(lo) <= np.abs(x) * 2.0 ** -11 * (1 + 1e-6))
+    rec = hi.astype(np.float64) + lo.astype(np.float16).astype(np.float64)
+    big = np.abs(x) >= 2.0 ** -3                                                 # lo stays a normal fp16 there
+    assert np.max(np.abs(rec[big] - x[big]) / np.abs(x[big])) <= 2.0 ** -21
+    a_hi, a_lo, w_hi, w_lo = (rng.standard_normal(64) for _ in range(4))
+    three = a_lo * w_hi + a_hi * w_lo + a_hi * w_hi
+    stacked = (a_lo * w_hi + a_hi * w_hi) + (a_lo * w_lo + a_hi * w_lo)
+    assert np.allclose(stacked, three + a_lo * w_lo)
